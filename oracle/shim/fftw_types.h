@@ -1,0 +1,11 @@
+/* TEST INFRASTRUCTURE (oracle): FFTW2 type names only (powerspectrum.h:5-14 includes
+ * <dfftw.h>/<sfftw.h> just for fftw_real / fftw_complex). */
+#ifndef KSN_ORACLE_FFTW_TYPES_H
+#define KSN_ORACLE_FFTW_TYPES_H
+#ifdef DOUBLEPRECISION_FFTW
+typedef double fftw_real;
+#else
+typedef float fftw_real;
+#endif
+typedef struct { fftw_real re, im; } fftw_complex;
+#endif

@@ -1,0 +1,1 @@
+#include "rfftw_naive.h"

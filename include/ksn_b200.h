@@ -1,0 +1,151 @@
+/* ksn_b200.h -- the thin C-ABI between the host C code and the CUDA (sm_100a) kernels.
+ *
+ * Plain pointers and sizes only.  Host C (kspace_neutrinos_b200/src) calls these; so can
+ * any FFI (ctypes stubs in kspace_neutrinos_b200/capi.py, cgo/JNI sketches in
+ * INTEGRATION.md).  Every function returns 0 on success or a negative KSN_E* code and
+ * records a message retrievable with ksn_last_error(); nothing here calls terminate().
+ * There is no CPU fallback: without a usable CUDA device every compute entry fails with
+ * KSN_ENODEV.
+ *
+ * Reference loops replaced (file:line under /root/reference):
+ *   ksn_powerspectrum_sums  <- powerspectrum.c:56-95   (hot loop 1 + the 4 MPI_Allreduce)
+ *   ksn_delta_nu_integrate  <- delta_tot_table.c:522-599 (fslength table + per-k QAG)
+ *   ksn_scale_modes         <- interface_gadget.c:163-188 (hot loop 3)
+ */
+#ifndef KSN_B200_H
+#define KSN_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    KSN_OK = 0,
+    KSN_ENODEV = -1,     /* no CUDA device / driver */
+    KSN_ECUDA = -2,      /* a CUDA runtime call failed */
+    KSN_EINVAL = -3,     /* bad argument */
+    KSN_ENOMEM = -4,     /* device or pinned allocation failed */
+    KSN_ECOMM = -5,      /* collective backend failed */
+    KSN_EQUAD = -6       /* quadrature did not converge (GSL would have raised) */
+};
+
+/* ---- lifecycle ---------------------------------------------------------------- */
+/* Bind this process to a CUDA device (default: env KSN_DEVICE, else LOCAL_RANK, else 0).
+ * Called implicitly by the first compute entry. */
+int ksn_init(int device);
+void ksn_shutdown(void);
+const char *ksn_last_error(void);
+/* 1 if a CUDA device is usable from this process, else 0 (never fails). */
+int ksn_device_available(void);
+/* device selected by ksn_init, -1 before */
+int ksn_device(void);
+
+/* ---- collective backend --------------------------------------------------------- */
+/* One rank (default). */
+int ksn_comm_single(void);
+/* NCCL over NVLink/NVSwitch, one process per GPU: rank 0 calls ksn_comm_nccl_unique_id,
+ * ships the 128 bytes to the other ranks by any means (torch.distributed, MPI_Bcast, a
+ * file), then every rank calls ksn_comm_nccl_init. */
+int ksn_comm_nccl_unique_id(void *id128);
+int ksn_comm_nccl_init(const void *id128, int nranks, int rank);
+/* Host all-reduce callback: buf (n doubles, host memory) must be summed over ranks in
+ * place.  This is what an MPI host uses (MPI_Allreduce on its communicator). */
+typedef int (*ksn_allreduce_fn)(double *buf, size_t n, void *user);
+int ksn_comm_host_callback(ksn_allreduce_fn fn, void *user, int nranks, int rank);
+int ksn_comm_rank(void);
+int ksn_comm_size(void);
+
+/* ---- memory helpers (for harnesses that want the grid resident in HBM) ------------ */
+int ksn_device_malloc(void **ptr, size_t bytes);
+int ksn_device_free(void *ptr);
+int ksn_host_alloc_pinned(void **ptr, size_t bytes);
+int ksn_host_free_pinned(void *ptr);
+int ksn_memcpy_h2d(void *dst, const void *src, size_t bytes);
+int ksn_memcpy_d2h(void *dst, const void *src, size_t bytes);
+int ksn_memcpy_d2d(void *dst, const void *src, size_t bytes);
+int ksn_device_synchronize(void);
+/* 1 = device or managed pointer, 0 = host pointer */
+int ksn_pointer_is_device(const void *ptr);
+/* Fill a device slab with the synthetic k-space Gaussian field used by bench.py and the
+ * parity tests: element (i,j,k) = sigma(|k|) * (n1, n2), n ~ N(0,1) from a counter-based
+ * generator keyed by (seed, global mode index), so any slab split yields the same values.
+ * sigma^2 ~ |k|^slope (slope 0 = white); element (0,0,0) = (dims^3, 0). */
+int ksn_fill_synthetic_grid(void *dgrid, int real_bytes, int dims, long long startslab, long long nslab,
+                            unsigned long long seed, double slope);
+
+/* ---- K1: power-spectrum bin sums (powerspectrum.c:33-95) --------------------------- */
+/* thresholds[b] = smallest integer k^2 whose reference bin index
+ * floor(binsperunit*log(sqrt(k^2))) is >= b, b = 0..nrbins-1, computed by the caller
+ * with the host libm (bit-exact mode counts depend on it); invwin[q] = pi q/(dims
+ * sin(pi q/dims)), q = 0..dims/2, invwin[0] = 1.
+ * Outputs are the sums over ALL ranks of the active communicator (length nrbins each):
+ * power_sum[b] = sum m*|F|^2*W, keff_sum[b] = sum m*|k|, count[b] = sum m, and
+ * *total_mass2 = |F(0,0,0)|^2.  keff_sum and count depend only on the geometry
+ * (dims, nrbins, slab) and are cached between calls unless KSN_NO_GEOM_CACHE=1.
+ * grid: device pointer (used in place) or host pointer (staged through HBM in chunks). */
+int ksn_powerspectrum_sums(const void *grid, int real_bytes, int dims, int nrbins,
+                           long long startslab, long long nslab,
+                           const unsigned int *thresholds, const double *invwin,
+                           double *power_sum, double *keff_sum, long long *count, double *total_mass2);
+
+/* ---- K3: scale every mode by 1 + norm*interp(log k) (interface_gadget.c:163-188) ---- */
+/* logkk/ratio: the _delta_pow table (delta_pow.c:19-37: clamped, piecewise linear in
+ * log k); a mode with integer wave vector n has k = |n| * 2 pi / boxsize. */
+int ksn_scale_modes(void *grid, int real_bytes, int dims, long long startslab, long long nslab,
+                    double boxsize, const double *logkk, const double *ratio, int nbins, double norm);
+
+/* Fused hot path for a host-resident grid: upload once, K1, callback, K3, download.
+ * between(): called after the bin sums are known; must fill the _delta_pow table. */
+typedef int (*ksn_between_fn)(void *user, const double *power_sum, const double *keff_sum,
+                              const long long *count, double total_mass2,
+                              const double **logkk, const double **ratio, int *nbins, double *norm);
+int ksn_step_staged(void *hgrid, int real_bytes, int dims, int nrbins, long long startslab, long long nslab,
+                    const unsigned int *thresholds, const double *invwin, double boxsize,
+                    ksn_between_fn between, void *user);
+
+/* ---- K2: linear-response integral (delta_tot_table.c:507-611) ----------------------- */
+typedef struct ksn_delta_nu_args {
+    int nk;                    /* k bins */
+    int Na;                    /* stored rows incl. the guess row (d_tot->ia) */
+    int namax;                 /* row stride of delta_tot */
+    int nspecies;              /* independent mass species integrated in this launch (<=3) */
+    double a;                  /* current scale factor */
+    double TimeTransfer;       /* a0 */
+    double light;              /* c in internal units */
+    double delta_nu_prefac;    /* 1.5 Omega0 H0^2 / c */
+    double deriv_prefac;       /* a0^2 H(a0) / c  (delta_tot_table.c:524) */
+    double mnubykT[3];         /* m_nu / (k_B T_nu) per species */
+    double qc[3];              /* hybrid momentum cut per species, 0 = none (:545) */
+    double nufrac_low0;        /* hybnu.nufrac_low[0] (:533,569) */
+    double relerr[3];          /* QAG epsrel per species (:518,547) */
+    int integrate[3];          /* 0: initial-condition term only (:543-544,551) */
+    const double *scalefact;   /* host, Na log-a knots */
+    const double *delta_tot;   /* host, nk rows of stride namax */
+    const double *wavenum;     /* host, nk */
+    const double *delta_nu_init; /* host, nk */
+} ksn_delta_nu_args;
+/* out: nspecies*nk doubles, species-major.  n_evals (may be NULL): integrand evaluations. */
+int ksn_delta_nu_integrate(const ksn_delta_nu_args *args, double *out, unsigned long long *n_evals);
+
+/* Tabulate 1/(a H(a)) for the device integrand.  hub(a, user) is called on the host at
+ * n uniform points in log a over [loga_lo, loga_hi]. */
+typedef double (*ksn_hubble_fn)(double a, void *user);
+int ksn_set_background(ksn_hubble_fn hub, void *user, double loga_lo, double loga_hi, int n);
+/* device fslength (same table), for tests: light * int_{logai}^{logaf} dloga /(a^2 H) */
+int ksn_fslength_device(const double *logai, int n, double logaf, double light, double *out);
+
+/* ---- introspection for bench.py --------------------------------------------------- */
+typedef struct ksn_timing {
+    float k1_ms, k1_reduce_ms, comm_ms, k2_ms, k3_ms, h2d_ms, d2h_ms;
+    unsigned long long launches;   /* kernels launched since ksn_timing_reset */
+} ksn_timing;
+int ksn_timing_enable(int on);
+int ksn_timing_reset(void);
+int ksn_timing_get(ksn_timing *out);
+/* CUDA stream all kernels are launched on (cudaStream_t as void*). */
+void *ksn_stream(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,3 @@
+/* Forwarding header: keeps the reference include line "kspace-neutrinos/powerspectrum.h" working.
+ * All declarations live in kspace_neutrinos.h (each cites the reference line it replaces). */
+#include "kspace_neutrinos.h"

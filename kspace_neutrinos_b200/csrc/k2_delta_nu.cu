@@ -1,0 +1,595 @@
+// K2 -- the linear-response integral for delta_nu(k)  (sm_100a).
+//
+// Replaces the body of get_delta_nu, delta_tot_table.c:522-599: the table of Nfs = 16*Na
+// free-streaming lengths (one adaptive Gauss-Kronrod quadrature each, :574-584), the natural
+// cubic splines over it and over every delta_tot(k, a) history (:559-596), and the per-k
+// adaptive 61-point Gauss-Kronrod integral of get_delta_nu_int (:492-500, :597).
+//
+// Latency-bound, not bandwidth-bound: the whole state is < 2 MB.  One CTA of 128 threads per
+// (k bin, mass species): the 2 x 61 abscissae of the two halves of the interval being bisected
+// are evaluated by 122 lanes at once; Kronrod/Gauss/|f|/|f-mean| sums are fixed-shape shuffle
+// trees (deterministic); the QAG interval list (limit 200, as the reference's GSL_VAL) lives in
+// shared memory and follows GSL's qag.c decision logic step by step, so bisection decisions
+// agree with the CPU oracle except on exact floating-point ties.
+//
+// hubble_function(a) is a HOST callback in the reference (gadget_defines.h:11).  The device
+// integrand reads 1/(a H(a)) from a table sampled once on a uniform log-a grid
+// (ksn_set_background) with 4-point Lagrange interpolation (relative error ~1e-16 at the
+// default 16384 points, far inside the 1e-10 parity budget).
+#include "ksn_internal.cuh"
+#include "ksn_gk61_tables.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace ksn {
+
+__constant__ double c_xgk[31] = KSN_XGK61_INIT;
+__constant__ double c_wgk[31] = KSN_WGK61_INIT;
+__constant__ double c_wg[15] = KSN_WG30_INIT;
+
+constexpr int K2_THREADS = 128;
+constexpr int QAG_LIMIT = 200;      // GSL_VAL, kspace_neutrino_const.h:19
+
+enum { Q_OK = 0, Q_EROUND = 18, Q_ESING = 21, Q_EMAXITER = 11, Q_EFAILED = 5 };
+
+struct BgTable {
+    const double *g;   // 1/(a H(a)) at x_i = lo + i*h
+    int n;
+    double lo, h, inv_h;
+};
+
+__device__ __forceinline__ double bg_eval(const BgTable &t, double x)
+{
+    const double s = (x - t.lo) * t.inv_h;
+    int i = (int) floor(s);
+    i = max(1, min(i, t.n - 3));
+    const double u = s - i, um1 = u - 1.0, up1 = u + 1.0, um2 = u - 2.0;
+    const double w0 = -u * um1 * um2 * (1.0 / 6.0);
+    const double w1 = up1 * um1 * um2 * 0.5;
+    const double w2 = -up1 * u * um2 * 0.5;
+    const double w3 = up1 * u * um1 * (1.0 / 6.0);
+    return w0 * __ldg(t.g + i - 1) + w1 * __ldg(t.g + i) + w2 * __ldg(t.g + i + 1) + w3 * __ldg(t.g + i + 2);
+}
+
+// ---------------------------------------------------------------- specialJ (delta_tot_table.c:417-463)
+__device__ __forceinline__ double specialJ_fit_d(double x)
+{
+    if (x <= 0.) return 1.;
+    const double x2 = x * x, x4 = x2 * x2, x8 = x4 * x4;
+    return (1. + 0.0168 * x2 + 0.0407 * x4) / (1. + 2.1734 * x2 + 1.6787 * exp(4.1811 * log(x)) + 0.1467 * x8);
+}
+
+__device__ __forceinline__ double bessel_j0_d(double x)
+{
+    const double ax = fabs(x);
+    if (ax < 0.5) {
+        const double y = x * x;
+        return 1.0 + y * (-1.0 / 6.0 + y * (1.0 / 120.0 + y * (-1.0 / 5040.0 + y * (1.0 / 362880.0 + y * (-1.0 / 39916800.0 + y * (1.0 / 6227020800.0))))));
+    }
+    return sin(x) / x;
+}
+
+__device__ double Jfrac_high_d(double x, double qc, double nufrac_low)
+{
+    double integ = 0;
+    const double j0 = bessel_j0_d(qc * x), cs = cos(qc * x), x2 = x * x;
+    for (int n = 1; n < 20; n++) {
+        const double dn = (double) n, n2 = dn * dn;
+        const double II = (n2 + n2 * dn * qc + dn * qc * x2 - x2) * qc * j0 + (2 * dn + n2 * qc + qc * x2) * cs;
+        const double sgn = (n & 1) ? 1.0 : -1.0;     // -1 * (-1)^n
+        integ += sgn * exp(-dn * qc) / (n2 + x2) / (n2 + x2) * II;
+    }
+    return integ / (1.5 * 1.202056903159594 * (1 - nufrac_low));
+}
+
+__device__ __forceinline__ double specialJ_d(double x, double qc, double nufrac_low)
+{
+    return qc > 0 ? Jfrac_high_d(x, qc, nufrac_low) : specialJ_fit_d(x);
+}
+
+// ---------------------------------------------------------------- natural cubic spline (GSL cspline.c)
+// interval index with xa[i] <= x < xa[i+1] (last interval for x == xa[n-1])
+__device__ __forceinline__ int bsearch_d(const double *xa, int n, double x)
+{
+    int lo = 0, hi = n - 1;
+    while (hi > lo + 1) {
+        const int m = (hi + lo) >> 1;
+        if (xa[m] > x) hi = m; else lo = m;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ double cspline_eval_d(const double *xa, const double *ya, const double *ca, int i, double x)
+{
+    const double x_lo = xa[i], x_hi = xa[i + 1], y_lo = ya[i], y_hi = ya[i + 1];
+    const double dx = x_hi - x_lo, dy = y_hi - y_lo, delx = x - x_lo;
+    const double c_i = ca[i], c_ip1 = ca[i + 1];
+    const double b_i = (dy / dx) - dx * (c_ip1 + 2.0 * c_i) / 3.0;
+    const double d_i = (c_ip1 - c_i) / (3.0 * dx);
+    return y_lo + delx * (b_i + delx * (c_i + delx * d_i));
+}
+
+// LDL^T factors of the natural-spline system for knots xa[0..n): alpha[i], gamma[i], i < n-2
+// (GSL linalg/tridiag.c solve_tridiag).  One thread.
+__device__ void spline_factor_seq(const double *xa, int n, double *alpha, double *gamma)
+{
+    const int N = n - 2;
+    if (N < 1) return;
+    alpha[0] = 2.0 * ((xa[2] - xa[1]) + (xa[1] - xa[0]));
+    if (N == 1) return;
+    gamma[0] = (xa[2] - xa[1]) / alpha[0];
+    for (int i = 1; i < N - 1; i++) {
+        const double diag = 2.0 * ((xa[i + 2] - xa[i + 1]) + (xa[i + 1] - xa[i]));
+        const double off_prev = xa[i + 1] - xa[i];
+        alpha[i] = diag - off_prev * gamma[i - 1];
+        gamma[i] = (xa[i + 2] - xa[i + 1]) / alpha[i];
+    }
+    {
+        const int i = N - 1;
+        const double diag = 2.0 * ((xa[i + 2] - xa[i + 1]) + (xa[i + 1] - xa[i]));
+        alpha[i] = diag - (xa[i + 1] - xa[i]) * gamma[i - 1];
+    }
+}
+
+__device__ __forceinline__ double spline_rhs(const double *xa, const double *ya, int i)
+{
+    const double h_i = xa[i + 1] - xa[i], h_ip1 = xa[i + 2] - xa[i + 1];
+    const double g_i = (h_i != 0.0) ? 1.0 / h_i : 0.0, g_ip1 = (h_ip1 != 0.0) ? 1.0 / h_ip1 : 0.0;
+    return 3.0 * ((ya[i + 2] - ya[i + 1]) * g_ip1 - (ya[i + 1] - ya[i]) * g_i);
+}
+
+// Solve for c[0..n) given factors; rhs in c[1..n-2] on entry (in place).  One thread.
+__device__ void spline_solve_seq(int n, const double *alpha, const double *gamma, double *c)
+{
+    const int N = n - 2;
+    c[0] = 0.0;
+    c[n - 1] = 0.0;
+    if (N < 1) return;
+    double *z = c + 1;
+    if (N == 1) { z[0] = z[0] / alpha[0]; return; }
+    for (int i = 1; i < N; i++) z[i] = z[i] - gamma[i - 1] * z[i - 1];
+    for (int i = 0; i < N; i++) z[i] = z[i] / alpha[i];
+    for (int i = N - 2; i >= 0; i--) z[i] = z[i] - gamma[i] * z[i + 1];
+}
+
+// ---------------------------------------------------------------- block-wide QK61 / QAG
+struct QkOut { double result, abserr, resabs, resasc; };
+
+struct QagShared {
+    double a[QAG_LIMIT], b[QAG_LIMIT], r[QAG_LIMIT], e[QAG_LIMIT];
+    double red[4][4];
+    int sel;
+};
+
+__device__ __forceinline__ double rescale_error_d(double err, double result_abs, double result_asc)
+{
+    err = fabs(err);
+    if (result_asc != 0 && err != 0) {
+        const double scale = pow((200 * err / result_asc), 1.5);
+        err = scale < 1 ? result_asc * scale : result_asc;
+    }
+    if (result_abs > DBL_MIN / (50 * DBL_EPSILON)) {
+        const double min_err = 50 * DBL_EPSILON * result_abs;
+        if (min_err > err) err = min_err;
+    }
+    return err;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// Two 61-point rules at once: threads 0..63 take [a1,b1], threads 64..127 take [a2,b2].
+// Every thread returns both results (uniform).  Must be called by all K2_THREADS threads.
+template <class F>
+__device__ void qk61_pair(const F &f, double a1, double b1, double a2, double b2, bool two,
+                          QagShared &S, QkOut &o1, QkOut &o2)
+{
+    const int tid = threadIdx.x, half = tid >> 6, n = tid & 63, warp = tid >> 5;
+    const double a = half ? a2 : a1, b = half ? b2 : b1;
+    const double center = 0.5 * (a + b), half_length = 0.5 * (b - a);
+    const bool active = n < 61 && (two || half == 0);
+    const int j = n <= 30 ? n : 60 - n;
+    double fv = 0.0, wk = 0.0, wgs = 0.0;
+    if (active) {
+        const double absc = half_length * c_xgk[j];
+        fv = f(n <= 30 ? center - absc : center + absc);
+        wk = c_wgk[j];
+        wgs = (j & 1) ? c_wg[j >> 1] : 0.0;
+    }
+    const double sk = warp_sum(wk * fv), sg = warp_sum(wgs * fv), sa = warp_sum(wk * fabs(fv));
+    if ((tid & 31) == 0) { S.red[warp][0] = sk; S.red[warp][1] = sg; S.red[warp][2] = sa; }
+    __syncthreads();
+    const double kron[2] = { S.red[0][0] + S.red[1][0], S.red[2][0] + S.red[3][0] };
+    const double gaus[2] = { S.red[0][1] + S.red[1][1], S.red[2][1] + S.red[3][1] };
+    const double rabs[2] = { S.red[0][2] + S.red[1][2], S.red[2][2] + S.red[3][2] };
+    const double mean = kron[half] * 0.5;
+    const double sc = warp_sum(active ? wk * fabs(fv - mean) : 0.0);
+    if ((tid & 31) == 0) S.red[warp][3] = sc;
+    __syncthreads();
+    const double rasc[2] = { S.red[0][3] + S.red[1][3], S.red[2][3] + S.red[3][3] };
+    __syncthreads();   // S.red is reused by the next call
+    const double hl1 = 0.5 * (b1 - a1), hl2 = 0.5 * (b2 - a2);
+    o1.result = kron[0] * hl1;
+    o1.resabs = rabs[0] * fabs(hl1);
+    o1.resasc = rasc[0] * fabs(hl1);
+    o1.abserr = rescale_error_d((kron[0] - gaus[0]) * hl1, o1.resabs, o1.resasc);
+    o2.result = kron[1] * hl2;
+    o2.resabs = rabs[1] * fabs(hl2);
+    o2.resasc = rasc[1] * fabs(hl2);
+    o2.abserr = rescale_error_d((kron[1] - gaus[1]) * hl2, o2.resabs, o2.resasc);
+}
+
+__device__ __forceinline__ bool subinterval_too_small_d(double a1, double a2, double b2)
+{
+    const double tmp = (1 + 100 * DBL_EPSILON) * (fabs(a2) + 1000 * DBL_MIN);
+    return fabs(a1) <= tmp && fabs(b2) <= tmp;
+}
+
+// gsl_integration_qag (key 6) for one integrand, executed by the whole CTA; all threads return the
+// same values.  passes (optional) counts 61-point rule applications.
+template <class F>
+__device__ int qag61_block(const F &f, double a, double b, double epsabs, double epsrel, int limit,
+                           QagShared &S, double *result, double *abserr, unsigned *passes)
+{
+    QkOut q0, qd;
+    qk61_pair(f, a, b, a, b, false, S, q0, qd);
+    unsigned np = 1;
+    double tolerance = fmax(epsabs, epsrel * fabs(q0.result));
+    const double round_off = 50 * DBL_EPSILON * q0.resabs;
+    *result = q0.result;
+    *abserr = q0.abserr;
+    if (passes) *passes = np;
+    if (q0.abserr <= round_off && q0.abserr > tolerance) return Q_EROUND;
+    if ((q0.abserr <= tolerance && q0.abserr != q0.resasc) || q0.abserr == 0.0) return Q_OK;
+    if (limit == 1) return Q_EMAXITER;
+    if (threadIdx.x == 0) { S.a[0] = a; S.b[0] = b; S.r[0] = q0.result; S.e[0] = q0.abserr; S.sel = 0; }
+    __syncthreads();
+    double area = q0.result, errsum = q0.abserr;
+    int size = 1, iteration = 1, roundoff_type1 = 0, roundoff_type2 = 0, error_type = 0;
+    do {
+        const int i = S.sel;
+        const double a_i = S.a[i], b_i = S.b[i], r_i = S.r[i], e_i = S.e[i];
+        const double a1 = a_i, b1 = 0.5 * (a_i + b_i), a2 = b1, b2 = b_i;
+        QkOut q1, q2;
+        qk61_pair(f, a1, b1, a2, b2, true, S, q1, q2);
+        np += 2;
+        const double area12 = q1.result + q2.result, error12 = q1.abserr + q2.abserr;
+        errsum += (error12 - e_i);
+        area += area12 - r_i;
+        if (q1.resasc != q1.abserr && q2.resasc != q2.abserr) {
+            const double delta = r_i - area12;
+            if (fabs(delta) <= 1.0e-5 * fabs(area12) && error12 >= 0.99 * e_i) roundoff_type1++;
+            if (iteration >= 10 && error12 > e_i) roundoff_type2++;
+        }
+        tolerance = fmax(epsabs, epsrel * fabs(area));
+        if (errsum > tolerance) {
+            if (roundoff_type1 >= 6 || roundoff_type2 >= 20) error_type = 2;
+            if (subinterval_too_small_d(a1, a2, b2)) error_type = 3;
+        }
+        if (threadIdx.x == 0) {
+            // GSL workspace update(): the half with the larger error keeps slot i, the other is appended
+            if (q2.abserr > q1.abserr) {
+                S.a[i] = a2; S.r[i] = q2.result; S.e[i] = q2.abserr;
+                S.a[size] = a1; S.b[size] = b1; S.r[size] = q1.result; S.e[size] = q1.abserr;
+            } else {
+                S.b[i] = b1; S.r[i] = q1.result; S.e[i] = q1.abserr;
+                S.a[size] = a2; S.b[size] = b2; S.r[size] = q2.result; S.e[size] = q2.abserr;
+            }
+            int best = 0;
+            double emax = S.e[0];
+            for (int k = 1; k <= size; k++) if (S.e[k] > emax) { emax = S.e[k]; best = k; }
+            S.sel = best;
+        }
+        size++;
+        iteration++;
+        __syncthreads();
+    } while (iteration < limit && !error_type && errsum > tolerance);
+    double s = 0;
+    for (int k = 0; k < size; k++) s += S.r[k];
+    __syncthreads();
+    *result = s;
+    *abserr = errsum;
+    if (passes) *passes = np;
+    if (errsum <= tolerance) return Q_OK;
+    if (error_type == 2) return Q_EROUND;
+    if (error_type == 3) return Q_ESING;
+    if (iteration == limit) return Q_EMAXITER;
+    return Q_EFAILED;
+}
+
+// ---------------------------------------------------------------- free-streaming table
+struct FsIntegrand {
+    BgTable bg;
+    // fslength_int, delta_tot_table.c:378-383: 1/a/(a H(a))
+    __device__ double operator()(double loga) const { return bg_eval(bg, loga) * exp(-loga); }
+};
+
+// One CTA per requested lower limit: out[i] = light * int_{logai[i]}^{logaf} (delta_tot_table.c:394-407)
+__global__ void __launch_bounds__(K2_THREADS)
+fslength_kernel(BgTable bg, const double *__restrict__ logai, int n, double logaf, double light,
+                double *__restrict__ out, int *__restrict__ status, unsigned long long *evals)
+{
+    __shared__ QagShared S;
+    const int i = blockIdx.x;
+    if (i >= n) return;
+    const double lo = logai[i];
+    if (lo >= logaf) {
+        if (threadIdx.x == 0) { out[i] = 0.0; status[i] = Q_OK; }
+        return;
+    }
+    FsIntegrand f{ bg };
+    double res, err;
+    unsigned passes = 0;
+    const int st = qag61_block(f, lo, logaf, 0.0, 1e-6, QAG_LIMIT, S, &res, &err, &passes);
+    if (threadIdx.x == 0) {
+        out[i] = light * res;
+        status[i] = st;
+        if (evals) atomicAdd(evals, 61ull * passes);
+    }
+}
+
+// knots of the free-streaming spline, delta_tot_table.c:582
+__global__ void fs_knots_kernel(double loga0, double loga, int Nfs, double *__restrict__ fsscales)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < Nfs) fsscales[i] = loga0 + i * (loga - loga0) / (Nfs - 1.);
+}
+
+// One thread each: spline coefficients of the fs table, and LDL^T factors for the delta_tot knots.
+__global__ void k2_prep_splines_kernel(const double *__restrict__ fsscales, const double *__restrict__ fslengths, int Nfs,
+                                       double *__restrict__ fs_c, double *__restrict__ scratch_alpha, double *__restrict__ scratch_gamma,
+                                       const double *__restrict__ scalefact, int Na, double *__restrict__ dt_alpha, double *__restrict__ dt_gamma)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        spline_factor_seq(fsscales, Nfs, scratch_alpha, scratch_gamma);
+        for (int i = 0; i < Nfs - 2; i++) fs_c[i + 1] = spline_rhs(fsscales, fslengths, i);
+        spline_solve_seq(Nfs, scratch_alpha, scratch_gamma, fs_c);
+    }
+    if (blockIdx.x == 1 && threadIdx.x == 0 && Na > 2) spline_factor_seq(scalefact, Na, dt_alpha, dt_gamma);
+}
+
+// ---------------------------------------------------------------- the per-k integral
+struct K2Dev {
+    int nk, Na, namax, Nfs;
+    double loga0, loga, light, delta_nu_prefac, deriv_prefac, nufrac_low0;
+    double mnubykT[3], qc[3], relerr[3];
+    int integrate[3];
+    const double *scalefact, *delta_tot, *wavenum, *delta_nu_init;   // device
+    const double *fsscales, *fslengths, *fs_c, *dt_alpha, *dt_gamma; // device
+    double *out;
+    int *status;
+    unsigned long long *evals;
+    BgTable bg;
+};
+
+struct DeltaNuIntegrand {
+    // get_delta_nu_int, delta_tot_table.c:492-500
+    const K2Dev *P;
+    const double *sx, *sy, *sc;   // shared: knots, delta_tot row, spline c
+    double k, mnubykT, qc, fs_x0, fs_inv_dx;
+    __device__ double operator()(double logai) const
+    {
+        const K2Dev &p = *P;
+        // free-streaming length: near-uniform knots -> direct index, then fix against the stored knots
+        int i = (int) ((logai - fs_x0) * fs_inv_dx);
+        i = max(0, min(i, p.Nfs - 2));
+        while (i > 0 && logai < __ldg(p.fsscales + i)) i--;
+        while (i < p.Nfs - 2 && logai >= __ldg(p.fsscales + i + 1)) i++;
+        const double fsl = cspline_eval_d(p.fsscales, p.fslengths, p.fs_c, i, logai);
+        double dtot;
+        if (p.Na > 2) {
+            const int m = bsearch_d(sx, p.Na, logai);
+            dtot = cspline_eval_d(sx, sy, sc, m, logai);
+        } else {
+            dtot = sy[0] + (logai - sx[0]) / (sx[1] - sx[0]) * (sy[1] - sy[0]);
+        }
+        const double specJ = specialJ_d(k * fsl / mnubykT, qc, p.nufrac_low0);
+        return fsl * bg_eval(p.bg, logai) * specJ * dtot;
+    }
+};
+
+__global__ void __launch_bounds__(K2_THREADS)
+k2_delta_nu_kernel(const __grid_constant__ K2Dev p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ QagShared S;
+    double *sx = (double *) smem_raw, *sy = sx + p.Na, *sc = sy + p.Na;
+    const int ik = blockIdx.x, sp = blockIdx.y;
+    for (int i = threadIdx.x; i < p.Na; i += blockDim.x) {
+        sx[i] = p.scalefact[i];
+        sy[i] = p.delta_tot[(size_t) ik * p.namax + i];
+    }
+    __syncthreads();
+    const double k = p.wavenum[ik], mnubykT = p.mnubykT[sp];
+    // initial-condition term, delta_tot_table.c:525-535 (always the untruncated fit: qc is still 0 there)
+    const double fsl_A0a = p.fslengths[0];
+    const double specJ0 = specialJ_fit_d(k * fsl_A0a / (mnubykT > 0 ? mnubykT : 1));
+    double dnu = specJ0 * p.delta_nu_init[ik] * (1. + p.deriv_prefac * fsl_A0a);
+    int st = Q_OK;
+    unsigned passes = 0;
+    if (p.integrate[sp]) {
+        if (p.Na > 2) {
+            for (int i = threadIdx.x; i < p.Na - 2; i += blockDim.x) sc[i + 1] = spline_rhs(sx, sy, i);
+            __syncthreads();
+            if (threadIdx.x == 0) spline_solve_seq(p.Na, p.dt_alpha, p.dt_gamma, sc);
+            __syncthreads();
+        }
+        DeltaNuIntegrand f;
+        f.P = &p; f.sx = sx; f.sy = sy; f.sc = sc;
+        f.k = k; f.mnubykT = mnubykT; f.qc = p.qc[sp];
+        f.fs_x0 = p.loga0;
+        f.fs_inv_dx = (p.Nfs - 1.) / (p.loga - p.loga0);
+        double res, err;
+        st = qag61_block(f, p.loga0, p.loga, 0.0, p.relerr[sp], QAG_LIMIT, S, &res, &err, &passes);
+        dnu += p.delta_nu_prefac * res;
+    }
+    if (threadIdx.x == 0) {
+        p.out[(size_t) sp * p.nk + ik] = dnu;
+        p.status[(size_t) sp * p.nk + ik] = st;
+        if (p.evals && passes) atomicAdd(p.evals, 61ull * passes);
+    }
+}
+
+static BgTable bg_table()
+{
+    Ctx &c = ctx();
+    BgTable t;
+    t.g = c.d_bg; t.n = c.bg_n; t.lo = c.bg_lo; t.h = c.bg_h; t.inv_h = 1.0 / c.bg_h;
+    return t;
+}
+
+// carve n doubles out of a bump allocator over c.d_k2
+struct Bump {
+    char *base; size_t off = 0;
+    template <typename T> T *take(size_t n) { off = (off + 15) & ~(size_t) 15; T *p = (T *) (base + off); off += n * sizeof(T); return p; }
+};
+
+}  // namespace ksn
+
+using namespace ksn;
+
+extern "C" int ksn_set_background(ksn_hubble_fn hub, void *user, double loga_lo, double loga_hi, int n)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!hub || !(loga_hi > loga_lo) || n < 16) return set_error(KSN_EINVAL, "ksn_set_background: bad arguments");
+    Ctx &c = ctx();
+    const double h = (loga_hi - loga_lo) / (n - 1);
+    double *tab = (double *) malloc(sizeof(double) * n);
+    for (int i = 0; i < n; i++) {
+        const double a = exp(loga_lo + i * h);
+        tab[i] = 1.0 / (a * hub(a, user));
+    }
+    if (c.d_bg) { cudaFree(c.d_bg); c.d_bg = nullptr; }
+    cudaError_t e = cudaMalloc((void **) &c.d_bg, sizeof(double) * n);
+    if (e == cudaSuccess) e = cudaMemcpy(c.d_bg, tab, sizeof(double) * n, cudaMemcpyHostToDevice);
+    free(tab);
+    KSN_CUDA(e);
+    c.bg_n = n; c.bg_lo = loga_lo; c.bg_hi = loga_hi; c.bg_h = h;
+    return KSN_OK;
+}
+
+extern "C" int ksn_fslength_device(const double *logai, int n, double logaf, double light, double *out)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    Ctx &c = ctx();
+    if (!c.d_bg) return set_error(KSN_EINVAL, "ksn_fslength_device: call ksn_set_background first");
+    if (!logai || !out || n < 1) return set_error(KSN_EINVAL, "ksn_fslength_device: bad arguments");
+    for (int i = 0; i < n; i++)
+        if (logai[i] < c.bg_lo + 2 * c.bg_h || logaf > c.bg_hi - 2 * c.bg_h)
+            return set_error(KSN_EINVAL, "ksn_fslength_device: range outside the background table");
+    rc = ensure_device_buffer((void **) &c.d_k2, &c.k2_cap, (size_t) n * 24 + 64);
+    if (rc) return rc;
+    Bump bp{ (char *) c.d_k2 };
+    double *d_in = bp.take<double>(n), *d_out = bp.take<double>(n);
+    int *d_st = bp.take<int>(n);
+    KSN_CUDA(cudaMemcpyAsync(d_in, logai, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
+    fslength_kernel<<<n, K2_THREADS, 0, c.stream>>>(bg_table(), d_in, n, logaf, light, d_out, d_st, nullptr);
+    c.launches++;
+    KSN_CUDA(cudaGetLastError());
+    int *st = (int *) malloc(sizeof(int) * n);
+    KSN_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+    KSN_CUDA(cudaMemcpyAsync(st, d_st, sizeof(int) * n, cudaMemcpyDeviceToHost, c.stream));
+    KSN_CUDA(cudaStreamSynchronize(c.stream));
+    for (int i = 0; i < n; i++)
+        if (st[i]) { rc = set_error(KSN_EQUAD, "fslength quadrature %d failed with GSL-style code %d", i, st[i]); break; }
+    free(st);
+    return rc;
+}
+
+extern "C" int ksn_delta_nu_integrate(const ksn_delta_nu_args *A, double *out, unsigned long long *n_evals)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    Ctx &c = ctx();
+    if (!A || !out || A->nk < 1 || A->Na < 1 || A->namax < A->Na || A->nspecies < 1 || A->nspecies > 3 ||
+        !A->scalefact || !A->delta_tot || !A->wavenum || !A->delta_nu_init || !(A->a > 0) || !(A->TimeTransfer > 0))
+        return set_error(KSN_EINVAL, "ksn_delta_nu_integrate: bad arguments");
+    if (!c.d_bg) return set_error(KSN_EINVAL, "ksn_delta_nu_integrate: call ksn_set_background first");
+    const int nk = A->nk, Na = A->Na, ns = A->nspecies, Nfs = 16 * Na;
+    const double loga0 = log(A->TimeTransfer), loga = log(A->a);
+    if (loga0 < c.bg_lo + 2 * c.bg_h || loga > c.bg_hi - 2 * c.bg_h)
+        return set_error(KSN_EINVAL, "ksn_delta_nu_integrate: [%g,%g] outside the background table [%g,%g]", loga0, loga, c.bg_lo, c.bg_hi);
+    bool any_integral = false;
+    for (int s = 0; s < ns; s++) any_integral |= A->integrate[s] != 0;
+
+    // one pinned staging block -> one device block
+    const size_t n_in = (size_t) Na + (size_t) nk * A->namax + 2 * (size_t) nk;
+    const size_t dev_doubles = n_in + 3 * (size_t) Nfs + 2 * (size_t) Nfs + 2 * (size_t) Na + (size_t) ns * nk + 8;
+    const size_t dev_bytes = dev_doubles * sizeof(double) + ((size_t) ns * nk + Nfs) * sizeof(int) + 256;
+    rc = ensure_device_buffer((void **) &c.d_k2, &c.k2_cap, dev_bytes);
+    if (rc) return rc;
+    const size_t h_bytes = n_in * sizeof(double) + (size_t) ns * nk * sizeof(double) + ((size_t) ns * nk + Nfs) * sizeof(int) + 64;
+    rc = ensure_pinned_buffer((void **) &c.h_k2, &c.h_k2_cap, h_bytes);
+    if (rc) return rc;
+    KSN_CUDA(cudaStreamSynchronize(c.stream));
+    double *h = c.h_k2;
+    memcpy(h, A->scalefact, sizeof(double) * Na);
+    memcpy(h + Na, A->delta_tot, sizeof(double) * (size_t) nk * A->namax);
+    memcpy(h + Na + (size_t) nk * A->namax, A->wavenum, sizeof(double) * nk);
+    memcpy(h + Na + (size_t) nk * A->namax + nk, A->delta_nu_init, sizeof(double) * nk);
+
+    Bump bp{ (char *) c.d_k2 };
+    double *d_in = bp.take<double>(n_in);
+    double *d_fsscales = bp.take<double>(Nfs), *d_fslengths = bp.take<double>(Nfs), *d_fsc = bp.take<double>(Nfs);
+    double *d_sa = bp.take<double>(Nfs), *d_sg = bp.take<double>(Nfs);
+    double *d_dta = bp.take<double>(Na), *d_dtg = bp.take<double>(Na);
+    double *d_out = bp.take<double>((size_t) ns * nk);
+    unsigned long long *d_evals = bp.take<unsigned long long>(1);
+    int *d_status = bp.take<int>((size_t) ns * nk + Nfs);
+    if (bp.off > c.k2_cap) return set_error(KSN_ENOMEM, "K2 workspace accounting error");
+
+    phase_begin(PH_K2);
+    KSN_CUDA(cudaMemcpyAsync(d_in, h, n_in * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    KSN_CUDA(cudaMemsetAsync(d_evals, 0, sizeof(unsigned long long), c.stream));
+    KSN_CUDA(cudaMemsetAsync(d_status, 0, ((size_t) ns * nk + Nfs) * sizeof(int), c.stream));
+    const BgTable bg = bg_table();
+    // The fs table is needed for the initial-condition term too (its knot 0 is fslength(log a0, log a)).
+    fs_knots_kernel<<<(Nfs + 127) / 128, 128, 0, c.stream>>>(loga0, loga, Nfs, d_fsscales);
+    fslength_kernel<<<any_integral ? Nfs : 1, K2_THREADS, 0, c.stream>>>(bg, d_fsscales, any_integral ? Nfs : 1, loga, A->light,
+                                                                        d_fslengths, d_status + (size_t) ns * nk, d_evals);
+    c.launches += 2;
+    if (any_integral) {
+        k2_prep_splines_kernel<<<2, 32, 0, c.stream>>>(d_fsscales, d_fslengths, Nfs, d_fsc, d_sa, d_sg, d_in, Na, d_dta, d_dtg);
+        c.launches++;
+    }
+    K2Dev p;
+    p.nk = nk; p.Na = Na; p.namax = A->namax; p.Nfs = Nfs;
+    p.loga0 = loga0; p.loga = loga; p.light = A->light; p.delta_nu_prefac = A->delta_nu_prefac;
+    p.deriv_prefac = A->deriv_prefac; p.nufrac_low0 = A->nufrac_low0;
+    for (int s = 0; s < 3; s++) {
+        p.mnubykT[s] = s < ns ? A->mnubykT[s] : 0; p.qc[s] = s < ns ? A->qc[s] : 0;
+        p.relerr[s] = s < ns ? A->relerr[s] : 1e-6; p.integrate[s] = s < ns ? A->integrate[s] : 0;
+    }
+    p.scalefact = d_in; p.delta_tot = d_in + Na; p.wavenum = d_in + Na + (size_t) nk * A->namax;
+    p.delta_nu_init = p.wavenum + nk;
+    p.fsscales = d_fsscales; p.fslengths = d_fslengths; p.fs_c = d_fsc; p.dt_alpha = d_dta; p.dt_gamma = d_dtg;
+    p.out = d_out; p.status = d_status; p.evals = d_evals; p.bg = bg;
+    k2_delta_nu_kernel<<<dim3(nk, ns), K2_THREADS, 3 * (size_t) Na * sizeof(double), c.stream>>>(p);
+    c.launches++;
+    KSN_CUDA(cudaGetLastError());
+    double *h_out = h + n_in;
+    int *h_status = (int *) (h_out + (size_t) ns * nk);
+    unsigned long long *h_evals = (unsigned long long *) (h_status + (size_t) ns * nk + Nfs + ((ns * nk + Nfs) & 1));
+    KSN_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(double) * ns * nk, cudaMemcpyDeviceToHost, c.stream));
+    KSN_CUDA(cudaMemcpyAsync(h_status, d_status, sizeof(int) * ((size_t) ns * nk + Nfs), cudaMemcpyDeviceToHost, c.stream));
+    KSN_CUDA(cudaMemcpyAsync(h_evals, d_evals, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
+    phase_end(PH_K2);
+    KSN_CUDA(cudaStreamSynchronize(c.stream));
+    phase_collect();
+    memcpy(out, h_out, sizeof(double) * ns * nk);
+    if (n_evals) *n_evals = *h_evals;
+    for (size_t i = 0; i < (size_t) ns * nk + Nfs; i++)
+        if (h_status[i])
+            return set_error(KSN_EQUAD, "quadrature %zu (%s) failed with GSL-style code %d at a=%g",
+                             i, i < (size_t) ns * nk ? "delta_nu" : "fslength", h_status[i], A->a);
+    return KSN_OK;
+}

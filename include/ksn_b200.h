@@ -60,6 +60,11 @@ int ksn_device_malloc(void **ptr, size_t bytes);
 int ksn_device_free(void *ptr);
 int ksn_host_alloc_pinned(void **ptr, size_t bytes);
 int ksn_host_free_pinned(void *ptr);
+/* Page-lock a host grid the caller owns so that staged copies run at full PCIe speed.  The caller
+ * must ksn_host_unregister() it before freeing it.  Without this, host grids are copied as
+ * pageable memory (correct, slower). */
+int ksn_host_register(void *ptr, size_t bytes);
+int ksn_host_unregister(void *ptr);
 int ksn_memcpy_h2d(void *dst, const void *src, size_t bytes);
 int ksn_memcpy_d2h(void *dst, const void *src, size_t bytes);
 int ksn_memcpy_d2d(void *dst, const void *src, size_t bytes);

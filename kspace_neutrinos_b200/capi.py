@@ -90,6 +90,8 @@ PROTOTYPES = {
     "ksn_device_free": (C.c_int, [C.c_void_p]),
     "ksn_host_alloc_pinned": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "ksn_host_free_pinned": (C.c_int, [C.c_void_p]),
+    "ksn_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "ksn_host_unregister": (C.c_int, [C.c_void_p]),
     "ksn_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "ksn_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "ksn_memcpy_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -190,7 +192,7 @@ def lib() -> C.CDLL:
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(there is no CPU fallback for this package)")
-        handle = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        handle = C.CDLL(LIB_PATH)
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(handle, name)     # AttributeError here = header/library mismatch
             fn.restype = res

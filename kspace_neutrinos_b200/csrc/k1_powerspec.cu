@@ -5,11 +5,11 @@
 // stored mode, nothing written but O(nrbins) partials.
 //
 // Layout and schedule
-//  * The local slab is swept as a flat array of nslab*N*(N/2+1) complex values in
-//    warp tiles of 2048 consecutive elements (32 KiB for double): every warp load is one
-//    fully coalesced 512-byte request starting on a 512-byte boundary, independent of the
-//    odd row length N/2+1.  Tiles are dealt round-robin to CTAs (persistent grid of one
-//    CTA per SM), so the sweep is a pure function of (grid size, slab) -> deterministic.
+//  * The local slab is swept row by row (a row = the N/2+1 complex values of one (i,j)):
+//    one warp per row, 32 consecutive z per warp step, so every warp load is one coalesced
+//    512-byte request and all row geometry (ki^2+kj^2, the x-y window product) is warp-uniform.
+//    Rows are dealt round-robin to the warps of a persistent grid (one CTA per SM), so the
+//    sweep is a pure function of (grid size, slab) -> deterministic.
 //  * Everything geometric is a function of the integer k^2 = kx^2+ky^2+kz^2.  The bin is
 //    estimated with one MUFU log2 and corrected against an integer threshold table that the
 //    host built with its own libm from the reference expression
@@ -31,8 +31,6 @@
 
 namespace ksn {
 
-constexpr int K1_TILE_ITERS = 64;                 // warp iterations per tile
-constexpr int K1_TILE = 32 * K1_TILE_ITERS;       // elements per warp tile
 constexpr int K1_UNROLL = 8;                      // independent 16-byte loads in flight per lane
 constexpr int K1_MAX_WARPS = 16;
 
@@ -54,6 +52,14 @@ __device__ __forceinline__ Cplx<float> ld_stream(const Cplx<float> *p)
     return v;
 }
 
+// bare MUFU.LG2 (no denormal fix-up: arguments are integers >= 1, or 0 -> -inf)
+__device__ __forceinline__ float fast_log2(float x)
+{
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // |F|^2 * W with the reference's operation order and (for the float grid) its roundings:
 // invwindow() narrows to fftw_real, powerspectrum.c:8-24,68.
 __device__ __forceinline__ double mode_power(Cplx<double> v, double wxy, double wz)
@@ -69,135 +75,301 @@ __device__ __forceinline__ double mode_power(Cplx<float> v, double wxy, double w
     return (double) (v.re * v.re + v.im * v.im) * ((double) w * (double) w);
 }
 
-struct RowState {
-    int z, j, c;        // position in the row, row index, ki^2+kj^2
-    long long pl;       // plane index relative to plane0
-    double wxy;         // iw(ki)*iw(kj)
-};
-
-template <typename real>
-__device__ __forceinline__ void row_constants(RowState &r, int N, long long plane0, const double *iw_s)
-{
-    const long long gi = plane0 + r.pl;
-    const int ki = gi <= N / 2 ? (int) gi : (int) (gi - N);
-    const int kj = r.j <= N / 2 ? r.j : r.j - N;
-    r.c = ki * ki + kj * kj;
-    const double a = iw_s[ki < 0 ? -ki : ki], b = iw_s[kj < 0 ? -kj : kj];
-    if (sizeof(real) == 4) r.wxy = (double) ((float) a * (float) b);
-    else r.wxy = a * b;
-}
-
 // Segmented inclusive scan over runs of equal `bin` (lanes with the same bin are adjacent).
-// On return the LAST lane of each run holds the run's sum.  NV values share the shuffles' control.
+// On return the LAST lane of each run holds the run's sum.  The conditional add is an FMA with an
+// exact 0.0/1.0 mask (x*1+v and x*0+v round like v+x and v), cheaper than add+select.
 template <int NV>
-__device__ __forceinline__ unsigned segmented_sum(int bin, double (&v)[NV], int lane)
+__device__ __forceinline__ unsigned segmented_sum(int bin, double (&v)[NV], int lane, unsigned le_mask)
 {
     const unsigned full = 0xffffffffu;
-    const int prev = __shfl_up_sync(full, bin, 1);
-    const bool head = lane == 0 || bin != prev;
-    const unsigned heads = __ballot_sync(full, head);
-    const int start = 31 - __clz(heads & (full >> (31 - lane)));   // first lane of my run
+    const int prev = __shfl_up_sync(full, bin, 1);            // lane 0 receives its own bin
+    const unsigned heads = __ballot_sync(full, bin != prev) | 1u;
+    const int dist = lane - (31 - __clz(heads & le_mask));    // distance to the first lane of my run
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const bool take = lane - d >= start;
+        const double m = __hiloint2double(dist >= d ? 0x3ff00000 : 0, 0);
 #pragma unroll
-        for (int i = 0; i < NV; i++) {
-            const double up = __shfl_up_sync(full, v[i], d);
-            if (take) v[i] += up;
-        }
+        for (int i = 0; i < NV; i++) v[i] = fma(__shfl_up_sync(full, v[i], d), m, v[i]);
     }
     return (heads >> 1) | 0x80000000u;   // lanes that end a run
 }
 
-template <typename real, bool FULL>
-__global__ void __launch_bounds__(K1_MAX_WARPS * 32, 1)
-k1_bin_kernel(const Cplx<real> *__restrict__ grid, long long nelem, int N, int nrbins, long long plane0,
-              float binscale, const unsigned *__restrict__ thr, const double *__restrict__ iw,
-              double *__restrict__ partial, int accumulate)
+// One group of U warp steps (32 consecutive z each) of one row.  MASKED: steps may run past the row end.
+template <typename real, bool FULL, int U, bool MASKED>
+__device__ __forceinline__ void k1_group(const Cplx<real> *__restrict__ rowptr, int z0, int L, int nyq, int c, double wxy,
+                                         float binscale, int nrbins, const uint2 *thr_s, const double *iw_s,
+                                         double *mybins, int lane, bool origin_row)
 {
     constexpr int NV = FULL ? 3 : 1;
+    const unsigned eq_mask = 1u << lane, le_mask = 0xffffffffu >> (31 - lane);
+    Cplx<real> v[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int z = z0 + 32 * u;
+        if (!MASKED || z < L) v[u] = ld_stream(rowptr + z);
+        else { v[u].re = 0; v[u].im = 0; }
+    }
+    if (origin_row && z0 == 0) { v[0].re = 0; v[0].im = 0; }   // F(0,0,0): the mean, not a mode (powerspectrum.c:65)
+    int bin[U];
+    double val[U][NV];
+    // Phase A: bin + weighted power per element (independent across u)
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int z = MASKED ? min(z0 + 32 * u, L - 1) : z0 + 32 * u;
+        const int k2 = c + z * z;
+        // MUFU estimate of floor(binsperunit*log(sqrt(k2))), exact after one step against the host thresholds
+        int b = max((int) (binscale * fast_log2((float) k2)), 0);   // <= true bin + 1 <= nrbins: table has nrbins+1 pairs
+        const uint2 t = thr_s[b];                       // {thr[b], thr[b+1]}
+        b += ((unsigned) k2 >= t.y) - ((unsigned) k2 < t.x);
+        // iw_s[z] carries the multiplicity: (2^(1/4) iw)^4 = 2 iw^4 for 0 < z < N/2 (kz=0 and Nyquist are not doubled)
+        val[u][0] = mode_power(v[u], wxy, iw_s[z]);
+        if (FULL) {
+            const double m = (z == 0 || z == nyq) ? 1.0 : 2.0;
+            val[u][1] = k2 > 0 ? sqrt((double) k2) * m : 0.0;
+            val[u][2] = k2 > 0 ? m : 0.0;
+        }
+        if (MASKED && z0 + 32 * u >= L) {
+            b = 0x7fffffff;
+#pragma unroll
+            for (int i = 0; i < NV; i++) val[u][i] = 0.0;
+        }
+        bin[u] = b;
+    }
+    // Phase B: the U segmented scans are independent -> their shuffle chains interleave
+    unsigned tails[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) tails[u] = segmented_sum<NV>(bin[u], val[u], lane, le_mask);
+    // Phase C: run tails go to the warp-private bins in element order.  Bins are monotone along a row,
+    // so the tails of one step hit distinct addresses: plain read-modify-write, no atomics.
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        if ((tails[u] & eq_mask) && (!MASKED || bin[u] != 0x7fffffff)) {
+#pragma unroll
+            for (int i = 0; i < NV; i++) mybins[i * nrbins + bin[u]] += val[u][i];
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast path (power only): every lane owns TWO consecutive modes, fetched with one 256-bit load
+// (sm_100a LDG.256), so a warp step covers 64 modes with one segmented scan.  The two modes of a
+// lane are combined first; a lane whose pair straddles a bin edge closes the lower run itself.
+template <typename real> struct Pair;
+template <> struct __align__(32) Pair<double> { double re0, im0, re1, im1; };
+template <> struct __align__(16) Pair<float> { float re0, im0, re1, im1; };
+
+__device__ __forceinline__ Pair<double> ld_pair(const Pair<double> *p)
+{
+    Pair<double> v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];"
+                 : "=d"(v.re0), "=d"(v.im0), "=d"(v.re1), "=d"(v.im1) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ Pair<float> ld_pair(const Pair<float> *p)
+{
+    Pair<float> v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.re0), "=f"(v.im0), "=f"(v.re1), "=f"(v.im1) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ int bin_of(int k2, float binscale, const uint2 *thr_s)
+{
+    int b = max((int) (binscale * fast_log2((float) k2)), 0);   // within one bin of the truth
+    const uint2 t = thr_s[b];                                    // {thr[b], thr[b+1]}
+    return b + ((unsigned) k2 >= t.y) - ((unsigned) k2 < t.x);
+}
+
+// U warp steps of 32 pairs each, starting at pair index q0 (this lane's first pair).  zfirst = z of
+// pair 0's first element (0 or 1, whichever makes the pair 32-byte aligned in this row).
+template <typename real, int U, bool MASKED>
+__device__ __forceinline__ void k1_pair_group(const Cplx<real> *__restrict__ rowptr, int q0, int npairs, int zfirst, int c, double wxy,
+                                              float binscale, int nrbins, const uint2 *thr_s, const double *iw_s,
+                                              double *mybins, int lane, bool origin_row)
+{
+    const unsigned full = 0xffffffffu, le_mask = full >> (31 - lane);
+    Pair<real> v[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int q = q0 + 32 * u;
+        if (!MASKED || q < npairs) v[u] = ld_pair((const Pair<real> *) (rowptr + zfirst + 2 * q));
+        else { v[u].re0 = 0; v[u].im0 = 0; v[u].re1 = 0; v[u].im1 = 0; }
+    }
+    if (origin_row && zfirst == 0 && q0 == 0) { v[0].re0 = 0; v[0].im0 = 0; }   // F(0,0,0) is not a mode
+    int ba[U], bb[U];
+    double pa[U], x[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int q = MASKED ? min(q0 + 32 * u, npairs - 1) : q0 + 32 * u;
+        const int z = zfirst + 2 * q;
+        const int k2a = c + z * z, k2b = k2a + 2 * z + 1;
+        ba[u] = bin_of(k2a, binscale, thr_s);
+        bb[u] = bin_of(k2b, binscale, thr_s);
+        Cplx<real> e0, e1;
+        e0.re = v[u].re0; e0.im = v[u].im0; e1.re = v[u].re1; e1.im = v[u].im1;
+        pa[u] = mode_power(e0, wxy, iw_s[z]);
+        const double pb = mode_power(e1, wxy, iw_s[z + 1]);
+        if (MASKED && q0 + 32 * u >= npairs) { ba[u] = 0x7fffffff; bb[u] = 0x7fffffff; }
+        // the lane's contribution to the run that contains its second mode
+        x[u] = fma(pa[u], __hiloint2double(ba[u] == bb[u] ? 0x3ff00000 : 0, 0), pb);
+    }
+    unsigned tails[U];
+    double carry[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int prevkey = __shfl_up_sync(full, bb[u], 1);
+        const bool cont = lane > 0 && ba[u] == prevkey;          // my first mode continues the previous lane's run
+        const unsigned contmask = __ballot_sync(full, cont);
+        const unsigned heads = __ballot_sync(full, !cont || ba[u] != bb[u]) | 1u;
+        const int dist = lane - (31 - __clz(heads & le_mask));
+        double sx = x[u];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+            sx = fma(__shfl_up_sync(full, sx, d), __hiloint2double(dist >= d ? 0x3ff00000 : 0, 0), sx);
+        const double prev_sum = __shfl_up_sync(full, sx, 1);
+        carry[u] = fma(prev_sum, __hiloint2double(cont ? 0x3ff00000 : 0, 0), pa[u]);   // closes the lower run if the pair is split
+        x[u] = sx;
+        tails[u] = ~(contmask >> 1) | 0x80000000u;               // lane l ends a run iff lane l+1 does not continue it
+    }
+    const unsigned eq_mask = 1u << lane;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        if (!MASKED || ba[u] != 0x7fffffff) {
+            if (ba[u] != bb[u]) mybins[ba[u]] += carry[u];
+            if (tails[u] & eq_mask) mybins[bb[u]] += x[u];
+        }
+        __syncwarp();
+    }
+}
+
+// one mode handled by lane 0 alone (the unpaired first or last element of a row)
+template <typename real>
+__device__ __forceinline__ void k1_single(const Cplx<real> *__restrict__ rowptr, int z, int c, double wxy, float binscale,
+                                          const uint2 *thr_s, const double *iw_s, double *mybins, int lane)
+{
+    if (lane == 0) {
+        const int k2 = c + z * z;
+        if (k2 > 0) {
+            const Cplx<real> e = ld_stream(rowptr + z);
+            mybins[bin_of(k2, binscale, thr_s)] += mode_power(e, wxy, iw_s[z]);
+        }
+    }
+    __syncwarp();
+}
+
+template <typename real>
+__global__ void __launch_bounds__(K1_MAX_WARPS * 32, 1)
+k1_pair_kernel(const Cplx<real> *__restrict__ grid, int nrows, int N, int nrbins, long long plane0,
+               float binscale, const unsigned *__restrict__ thr, const double *__restrict__ iw,
+               double *__restrict__ partial, int accumulate)
+{
+    constexpr int U = 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int L = N / 2 + 1;
     const int nyq = N / 2;
     const int nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *iw_s = (double *) smem_raw;                       // L
-    double *bins_s = iw_s + L;                                // nwarps * NV * nrbins
-    unsigned *thr_s = (unsigned *) (bins_s + (size_t) nwarps * NV * nrbins);   // nrbins + 1
+    double *iw_s = (double *) smem_raw;                       // 2L: z table (with multiplicity) | plain table
+    double *bins_s = iw_s + 2 * L;                            // nwarps * nrbins
+    uint2 *thr_s = (uint2 *) (bins_s + (size_t) nwarps * nrbins);   // nrbins+1 pairs {thr[b], thr[b+1]}
+    const double root2_4 = sizeof(real) == 4 ? (double) 1.189207115002721f : 1.189207115002721;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) iw_s[L + i] = iw[i];
+    for (int i = threadIdx.x; i < L; i += blockDim.x) iw_s[i] = (i == 0 || i == nyq) ? iw[i] : iw[i] * root2_4;
+    for (int i = threadIdx.x; i <= nrbins; i += blockDim.x)
+        thr_s[i] = make_uint2(i < nrbins ? thr[i] : 0xffffffffu, i + 1 < nrbins ? thr[i + 1] : 0xffffffffu);
+    for (int i = threadIdx.x; i < nwarps * nrbins; i += blockDim.x) bins_s[i] = 0.0;
+    __syncthreads();
 
-    for (int i = threadIdx.x; i < L; i += blockDim.x) iw_s[i] = iw[i];
-    for (int i = threadIdx.x; i <= nrbins; i += blockDim.x) thr_s[i] = i < nrbins ? thr[i] : 0xffffffffu;
+    double *mybins = bins_s + (size_t) warp * nrbins;
+    // the slab base may itself sit on an odd 16-byte boundary
+    const int base_odd = (int) (((size_t) grid / sizeof(Cplx<real>)) & 1);
+    for (int r = blockIdx.x * nwarps + warp; r < nrows; r += gridDim.x * nwarps) {
+        const int pl = r / N, j = r - pl * N;
+        const long long gi = plane0 + pl;
+        const int ki = gi <= N / 2 ? (int) gi : (int) (gi - N);
+        const int kj = j <= N / 2 ? j : j - N;
+        const int c = ki * ki + kj * kj;
+        double wxy;
+        {
+            const double a = iw_s[L + (ki < 0 ? -ki : ki)], b = iw_s[L + (kj < 0 ? -kj : kj)];
+            wxy = sizeof(real) == 4 ? (double) ((float) a * (float) b) : a * b;
+        }
+        const Cplx<real> *rowptr = grid + (size_t) r * L;
+        // pairs must start on a 2-element boundary of the slab: skip z=0 when the row starts odd
+        const int zfirst = (int) ((((size_t) r * L) + base_odd) & 1);
+        const int npairs = (L - zfirst) >> 1;
+        if (zfirst) k1_single<real>(rowptr, 0, c, wxy, binscale, thr_s, iw_s, mybins, lane);
+        if ((L - zfirst) & 1) k1_single<real>(rowptr, L - 1, c, wxy, binscale, thr_s, iw_s, mybins, lane);
+        const int nfull_groups = (npairs / 32) / U;
+        const int nsteps = (npairs + 31) / 32;
+        int g = 0;
+#pragma unroll 1
+        for (; g < nfull_groups; g++)
+            k1_pair_group<real, U, false>(rowptr, lane + g * 32 * U, npairs, zfirst, c, wxy, binscale, nrbins, thr_s, iw_s, mybins, lane, c == 0);
+#pragma unroll 1
+        for (int st = g * U; st < nsteps; st++)
+            k1_pair_group<real, 1, true>(rowptr, lane + st * 32, npairs, zfirst, c, wxy, binscale, nrbins, thr_s, iw_s, mybins, lane, c == 0);
+    }
+    __syncthreads();
+    double *out = partial + (size_t) blockIdx.x * nrbins;
+    for (int i = threadIdx.x; i < nrbins; i += blockDim.x) {
+        double s = 0.0;
+        for (int w = 0; w < nwarps; w++) s += bins_s[(size_t) w * nrbins + i];
+        out[i] = accumulate ? out[i] + s : s;
+    }
+}
+
+template <typename real, bool FULL>
+__global__ void __launch_bounds__(K1_MAX_WARPS * 32, 1)
+k1_bin_kernel(const Cplx<real> *__restrict__ grid, int nrows, int N, int nrbins, long long plane0,
+              float binscale, const unsigned *__restrict__ thr, const double *__restrict__ iw,
+              double *__restrict__ partial, int accumulate)
+{
+    constexpr int NV = FULL ? 3 : 1;
+    constexpr int U = FULL ? 4 : K1_UNROLL;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int L = N / 2 + 1;
+    const int nyq = N / 2;
+    const int nwarps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *iw_s = (double *) smem_raw;                       // 2L: z table (with multiplicity) | plain table
+    double *bins_s = iw_s + 2 * L;                            // nwarps * NV * nrbins
+    uint2 *thr_s = (uint2 *) (bins_s + (size_t) nwarps * NV * nrbins);   // nrbins+1 pairs {thr[b], thr[b+1]}
+
+    // z-window with the Hermitian multiplicity folded in as a fourth root (the weight is the 4th power)
+    const double root2_4 = sizeof(real) == 4 ? (double) 1.189207115002721f : 1.189207115002721;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) iw_s[L + i] = iw[i];          // plain table: x/y factors
+    for (int i = threadIdx.x; i < L; i += blockDim.x) iw_s[i] = (i == 0 || i == nyq) ? iw[i] : iw[i] * root2_4;
+    for (int i = threadIdx.x; i <= nrbins; i += blockDim.x)
+        thr_s[i] = make_uint2(i < nrbins ? thr[i] : 0xffffffffu, i + 1 < nrbins ? thr[i + 1] : 0xffffffffu);
     for (int i = threadIdx.x; i < nwarps * NV * nrbins; i += blockDim.x) bins_s[i] = 0.0;
     __syncthreads();
 
     double *mybins = bins_s + (size_t) warp * NV * nrbins;
-    const long long ntiles = (nelem + K1_TILE - 1) / K1_TILE;
-    // tile t -> CTA (t / nwarps) % gridDim.x, warp t % nwarps
-    for (long long t = (long long) blockIdx.x * nwarps + warp; t < ntiles; t += (long long) gridDim.x * nwarps) {
-        const long long e0 = t * K1_TILE + lane;
-        RowState r;
+    const int nfull_groups = (L / 32) / U;                     // groups of U steps that lie entirely inside the row
+    const int nsteps = (L + 31) / 32;                          // the rest of the row goes one (masked) step at a time
+    // rows are dealt to warps round-robin: the 16 warps of a CTA sweep 16 consecutive rows
+    for (int r = blockIdx.x * nwarps + warp; r < nrows; r += gridDim.x * nwarps) {
+        const int pl = r / N, j = r - pl * N;
+        const long long gi = plane0 + pl;
+        const int ki = gi <= N / 2 ? (int) gi : (int) (gi - N);
+        const int kj = j <= N / 2 ? j : j - N;
+        const int c = ki * ki + kj * kj;
+        double wxy;
         {
-            const long long row = e0 / L;
-            r.z = (int) (e0 - row * L);
-            r.j = (int) (row % N);
-            r.pl = row / N;
-            row_constants<real>(r, N, plane0, iw_s);
+            const double a = iw_s[L + (ki < 0 ? -ki : ki)], b = iw_s[L + (kj < 0 ? -kj : kj)];
+            wxy = sizeof(real) == 4 ? (double) ((float) a * (float) b) : a * b;
         }
+        const Cplx<real> *rowptr = grid + (size_t) r * L;
+        const bool origin_row = c == 0;
+        int g = 0;
 #pragma unroll 1
-        for (int it = 0; it < K1_TILE_ITERS; it += K1_UNROLL) {
-            Cplx<real> v[K1_UNROLL];
-#pragma unroll
-            for (int u = 0; u < K1_UNROLL; u++) {
-                const long long e = e0 + (long long) (it + u) * 32;
-                if (e < nelem) v[u] = ld_stream(grid + e);
-                else { v[u].re = 0; v[u].im = 0; }
-            }
-#pragma unroll
-            for (int u = 0; u < K1_UNROLL; u++) {
-                const long long e = e0 + (long long) (it + u) * 32;
-                const int k2 = r.c + r.z * r.z;
-                const bool live = e < nelem && k2 > 0;
-                int b = 0;
-                double val[NV];
-                if (live) {
-                    b = (int) (binscale * __log2f((float) k2));
-                    b = max(0, min(b, nrbins - 1));
-                    // exact correction against the host-built integer thresholds
-                    while (b > 0 && (unsigned) k2 < thr_s[b]) b--;
-                    while ((unsigned) k2 >= thr_s[b + 1]) b++;
-                    const double mult = (r.z == 0 || r.z == nyq) ? 1.0 : 2.0;
-                    val[0] = mode_power(v[u], r.wxy, iw_s[r.z]) * mult;
-                    if (FULL) { val[1] = sqrt((double) k2) * mult; val[2] = mult; }
-                } else {
-                    b = e < nelem ? 0 : 0x7fffffff;
-#pragma unroll
-                    for (int i = 0; i < NV; i++) val[i] = 0.0;
-                }
-                const unsigned tails = segmented_sum<NV>(b, val, lane);
-                // Bins are monotone along a row, so the runs of one warp step carry distinct bins --
-                // unless a new row starts inside this step; then (and only then) fall back to atomics.
-                const bool wrapped = __any_sync(0xffffffffu, r.z < lane);
-                if (((tails >> lane) & 1u) && b != 0x7fffffff) {
-                    if (wrapped) {
-#pragma unroll
-                        for (int i = 0; i < NV; i++) atomicAdd(&mybins[i * nrbins + b], val[i]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < NV; i++) mybins[i * nrbins + b] += val[i];
-                    }
-                }
-                __syncwarp();
-                // advance 32 elements along the flat index
-                r.z += 32;
-                if (r.z >= L) {
-                    do {
-                        r.z -= L;
-                        if (++r.j == N) { r.j = 0; r.pl++; }
-                    } while (r.z >= L);
-                    row_constants<real>(r, N, plane0, iw_s);
-                }
-            }
-        }
+        for (; g < nfull_groups; g++)
+            k1_group<real, FULL, U, false>(rowptr, lane + g * 32 * U, L, nyq, c, wxy, binscale, nrbins, thr_s, iw_s, mybins, lane, origin_row);
+#pragma unroll 1
+        for (int st = g * U; st < nsteps; st++)
+            k1_group<real, FULL, 1, true>(rowptr, lane + st * 32, L, nyq, c, wxy, binscale, nrbins, thr_s, iw_s, mybins, lane, origin_row);
     }
     __syncthreads();
     // CTA epilogue: fixed warp order
@@ -234,7 +406,7 @@ __global__ void k1_final_kernel(const double *__restrict__ partial, int ctas, in
 
 static size_t k1_smem_bytes(int dims, int nrbins, int nwarps, int nv)
 {
-    return (size_t) (dims / 2 + 1) * 8 + (size_t) nwarps * nv * nrbins * 8 + (size_t) (nrbins + 1) * 4 + 16;
+    return (size_t) (dims / 2 + 1) * 16 + (size_t) nwarps * nv * nrbins * 8 + (size_t) (nrbins + 1) * 8 + 16;
 }
 
 template <typename real, bool FULL>
@@ -243,8 +415,8 @@ static int k1_launch_t(const void *dgrid, int dims, int nrbins, long long plane0
 {
     Ctx &c = ctx();
     constexpr int NV = FULL ? 3 : 1;
-    const int L = dims / 2 + 1;
-    const long long nelem = nplanes * dims * L;
+    if (nplanes * dims > 0x7fffffffLL) return set_error(KSN_EINVAL, "K1: %lld rows in one slab", nplanes * dims);
+    const int nrows = (int) (nplanes * dims);
     int nwarps = K1_MAX_WARPS;
     while (nwarps > 1 && k1_smem_bytes(dims, nrbins, nwarps, NV) > c.smem_optin) nwarps--;
     const size_t smem = k1_smem_bytes(dims, nrbins, nwarps, NV);
@@ -257,13 +429,14 @@ static int k1_launch_t(const void *dgrid, int dims, int nrbins, long long plane0
     const float binscale = (float) (binsperunit * 0.5 * M_LN2);
     auto launch = [&](auto kern) -> int {
         KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        kern<<<ctas, nwarps * 32, smem, c.stream>>>((const Cplx<real> *) dgrid, nelem, dims, nrbins, plane0, binscale,
+        kern<<<ctas, nwarps * 32, smem, c.stream>>>((const Cplx<real> *) dgrid, nrows, dims, nrbins, plane0, binscale,
                                                     c.d_thr, c.d_iw, c.d_partial, accumulate ? 1 : 0);
         c.launches++;
         KSN_CUDA(cudaGetLastError());
         return KSN_OK;
     };
-    rc = launch(k1_bin_kernel<real, FULL>);
+    if (FULL || getenv("KSN_K1_NOPAIR")) rc = launch(k1_bin_kernel<real, FULL>);
+    else rc = launch(k1_pair_kernel<real>);
     if (rc) return rc;
     *ctas_out = ctas;
     *stride_out = NV * nrbins;

@@ -13,9 +13,10 @@
 // so that   smth(k2) = A_i + B_i * ln(k2 / K2_i)     for K2_i <= k2 < K2_{i+1},
 // identical to the reference's 1 + norm*(y_lo + (x-x_lo)/dx*dy) with x = log(sqrt(k2) 2pi/box).
 // ln(k2/K2_i) = log1p(u), u = k2/K2_i - 1; bins are narrow (u < 2%) for all but a handful of
-// low-k modes, so a degree-8 series is exact to < 1e-15 there and the slow log1p() is taken
-// only when u is large.  The segment is found from a 4096-cell lookup in log2(k2) (one MUFU
-// log2) followed by a short walk, all in shared memory.
+// low-k modes, so a short series is exact to < 1e-16 there and the slow log1p() is taken
+// only when u is large.  The segment comes from a cell lookup in log2(k2) (one MUFU log2, cells
+// sized by the host so that no cell holds two knots) plus one compare, all in shared memory.
+// Sweep: one warp per row, 32 consecutive z per step, rows dealt round-robin to a persistent grid.
 #include "ksn_internal.cuh"
 
 #include <math.h>
@@ -23,11 +24,9 @@
 
 namespace ksn {
 
-constexpr int K3_CELLS = 4096;
-constexpr int K3_TILE_ITERS = 32;
-constexpr int K3_TILE = 32 * K3_TILE_ITERS;
-constexpr int K3_UNROLL = 8;
-constexpr int K3_THREADS = 512;
+constexpr int K3_MAX_CELLS = 16384;
+constexpr int K3_UNROLL = 4;
+constexpr int K3_THREADS = 256;
 
 template <typename real> struct C2;
 template <> struct __align__(16) C2<double> { double re, im; };
@@ -54,157 +53,171 @@ __device__ __forceinline__ void st_cs(C2<float> *p, C2<float> v)
     asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.re), "f"(v.im) : "memory");
 }
 
-// table layout in global/shared memory (doubles): K2[n] | invK2[n] | A[n] | B[n] | then ushort cell[K3_CELLS]
+__device__ __forceinline__ float fast_log2(float x)
+{
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// per-knot record in shared memory
+struct __align__(16) K3Seg { double K2, inv, A, B; };
+
 struct K3Params {
     int n;            // knots
+    int cells;        // lookup cells in log2(k2); the host sizes them so that no cell holds two knots
     float cell_lo;    // log2(K2_0)
     float cell_scale; // cells per unit log2
 };
 
 template <typename real>
-__global__ void __launch_bounds__(K3_THREADS, 1)
-k3_scale_kernel(C2<real> *__restrict__ grid, long long nelem, int N, long long plane0,
-                const double *__restrict__ tab, K3Params prm)
+__device__ __forceinline__ double k3_factor(int k2i, const K3Seg *seg_s, const unsigned short *cell_s, const K3Params &prm)
+{
+    const double k2 = (double) k2i;
+    int cell = (int) ((fast_log2((float) k2i) - prm.cell_lo) * prm.cell_scale);
+    cell = max(0, min(cell, prm.cells - 1));
+    int s = cell_s[cell];                                   // last knot at or below the cell's lower edge
+    s += (k2 >= seg_s[s + 1].K2);                           // at most one knot inside a cell (host guarantee)
+    const K3Seg g = seg_s[s];
+    const double uu = fmax(fma(k2, g.inv, -1.0), 0.0);      // below the first knot: clamp (delta_pow.c:24-31)
+    double lg;
+    if (uu < 0.03125) {
+        // log1p(u), u < 2^-5: alternating series to u^9, truncation < 1e-16
+        lg = uu * (1.0 + uu * (-0.5 + uu * (1.0 / 3 + uu * (-0.25 + uu * (0.2 + uu * (-1.0 / 6 + uu * (1.0 / 7 + uu * (-0.125 + uu * (1.0 / 9)))))))));
+    } else {
+        lg = log1p(uu);
+    }
+    return fma(g.B, lg, g.A);
+}
+
+template <typename real, int U, bool MASKED>
+__device__ __forceinline__ void k3_group(C2<real> *__restrict__ rowptr, int z0, int L, int c, bool origin_row,
+                                         const K3Seg *seg_s, const unsigned short *cell_s, const K3Params &prm)
+{
+    C2<real> v[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int z = z0 + 32 * u;
+        if (!MASKED || z < L) v[u] = ld_cs(rowptr + z);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int z = z0 + 32 * u;
+        if (MASKED && z >= L) continue;
+        const int k2i = c + z * z;
+        if (origin_row && k2i == 0) continue;               // F(0,0,0) is skipped (interface_gadget.c:174)
+        const double smth = k3_factor<real>(k2i, seg_s, cell_s, prm);
+        C2<real> o;
+        o.re = (real) ((double) v[u].re * smth);
+        o.im = (real) ((double) v[u].im * smth);
+        st_cs(rowptr + z, o);
+    }
+}
+
+template <typename real>
+__global__ void __launch_bounds__(K3_THREADS, 4)
+k3_scale_kernel(C2<real> *__restrict__ grid, int nrows, int N, long long plane0,
+                const double *__restrict__ tab, const K3Params prm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = prm.n;
-    double *K2_s = (double *) smem_raw;
-    double *inv_s = K2_s + n;
-    double *A_s = inv_s + n;
-    double *B_s = A_s + n;
-    unsigned short *cell_s = (unsigned short *) (B_s + n);
-    for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) K2_s[i] = tab[i];
-    const unsigned short *cell_g = (const unsigned short *) (tab + 4 * n);
-    for (int i = threadIdx.x; i < K3_CELLS; i += blockDim.x) cell_s[i] = cell_g[i];
+    K3Seg *seg_s = (K3Seg *) smem_raw;                       // n + 1 records (the last one is a sentinel)
+    unsigned short *cell_s = (unsigned short *) (seg_s + n + 1);
+    double *flat = (double *) smem_raw;
+    for (int i = threadIdx.x; i < 4 * (n + 1); i += blockDim.x) flat[i] = tab[i];
+    const unsigned short *cell_g = (const unsigned short *) (tab + 4 * (n + 1));
+    for (int i = threadIdx.x; i < prm.cells; i += blockDim.x) cell_s[i] = cell_g[i];
     __syncthreads();
 
     const int L = N / 2 + 1;
     const int nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long ntiles = (nelem + K3_TILE - 1) / K3_TILE;
-    for (long long t = (long long) blockIdx.x * nwarps + warp; t < ntiles; t += (long long) gridDim.x * nwarps) {
-        const long long e0 = t * K3_TILE + lane;
-        int z, j, c;
-        long long pl;
-        {
-            const long long row = e0 / L;
-            z = (int) (e0 - row * L);
-            j = (int) (row % N);
-            pl = row / N;
-        }
-        auto rowc = [&]() {
-            const long long gi = plane0 + pl;
-            const int ki = gi <= N / 2 ? (int) gi : (int) (gi - N);
-            const int kj = j <= N / 2 ? j : j - N;
-            c = ki * ki + kj * kj;
-        };
-        rowc();
+    constexpr int U = K3_UNROLL;
+    const int nfull_groups = (L / 32) / U;
+    const int nsteps = (L + 31) / 32;
+    for (int r = blockIdx.x * nwarps + warp; r < nrows; r += gridDim.x * nwarps) {
+        const int pl = r / N, j = r - pl * N;
+        const long long gi = plane0 + pl;
+        const int ki = gi <= N / 2 ? (int) gi : (int) (gi - N);
+        const int kj = j <= N / 2 ? j : j - N;
+        const int c = ki * ki + kj * kj;
+        C2<real> *rowptr = grid + (size_t) r * L;
+        int g = 0;
 #pragma unroll 1
-        for (int it = 0; it < K3_TILE_ITERS; it += K3_UNROLL) {
-            C2<real> v[K3_UNROLL];
-#pragma unroll
-            for (int u = 0; u < K3_UNROLL; u++) {
-                const long long e = e0 + (long long) (it + u) * 32;
-                if (e < nelem) v[u] = ld_cs(grid + e);
-            }
-#pragma unroll
-            for (int u = 0; u < K3_UNROLL; u++) {
-                const long long e = e0 + (long long) (it + u) * 32;
-                const int k2i = c + z * z;
-                if (e < nelem && k2i > 0) {
-                    const double k2 = (double) k2i;
-                    int cell = (int) ((__log2f((float) k2i) - prm.cell_lo) * prm.cell_scale);
-                    cell = max(0, min(cell, K3_CELLS - 1));
-                    int s = cell_s[cell];
-                    while (s > 0 && k2 < K2_s[s]) s--;
-                    while (s + 1 < n && k2 >= K2_s[s + 1]) s++;
-                    double uu = fma(k2, inv_s[s], -1.0);
-                    if (uu < 0.0) uu = 0.0;                  // below the first knot: clamp (delta_pow.c:24-31)
-                    double lg;
-                    if (uu < 0.03125) {
-                        // log1p(u), |u| < 2^-5: alternating series to u^9, error < 3e-16
-                        lg = uu * (1.0 + uu * (-0.5 + uu * (1.0 / 3 + uu * (-0.25 + uu * (0.2 + uu * (-1.0 / 6 + uu * (1.0 / 7 + uu * (-0.125 + uu * (1.0 / 9)))))))));
-                    } else {
-                        lg = log1p(uu);
-                    }
-                    const double smth = fma(B_s[s], lg, A_s[s]);
-                    C2<real> o;
-                    o.re = (real) ((double) v[u].re * smth);
-                    o.im = (real) ((double) v[u].im * smth);
-                    st_cs(grid + e, o);
-                }
-                z += 32;
-                if (z >= L) {
-                    do {
-                        z -= L;
-                        if (++j == N) { j = 0; pl++; }
-                    } while (z >= L);
-                    rowc();
-                }
-            }
-        }
+        for (; g < nfull_groups; g++) k3_group<real, U, false>(rowptr, lane + g * 32 * U, L, c, c == 0, seg_s, cell_s, prm);
+#pragma unroll 1
+        for (int st = g * U; st < nsteps; st++) k3_group<real, 1, true>(rowptr, lane + st * 32, L, c, c == 0, seg_s, cell_s, prm);
     }
 }
 
-static size_t k3_tab_doubles(int n) { return (size_t) 4 * n + (K3_CELLS * sizeof(unsigned short) + 7) / 8; }
+static size_t k3_tab_doubles(int n, int cells) { return (size_t) 4 * (n + 1) + ((size_t) cells * sizeof(unsigned short) + 7) / 8; }
 static K3Params g_k3prm;
 
 int k3_upload_table(int dims, double boxsize, const double *logkk, const double *ratio, int nbins, double norm)
 {
     (void) dims;
     Ctx &c = ctx();
-    const size_t nd = k3_tab_doubles(nbins);
-    int rc = ensure_device_buffer((void **) &c.d_k3tab, &c.k3tab_cap, nd * sizeof(double));
+    const size_t nd_max = k3_tab_doubles(nbins, K3_MAX_CELLS);
+    int rc = ensure_device_buffer((void **) &c.d_k3tab, &c.k3tab_cap, nd_max * sizeof(double));
     if (rc) return rc;
-    rc = ensure_pinned_buffer((void **) &c.h_k3tab, &c.h_k3tab_cap, nd * sizeof(double));
+    rc = ensure_pinned_buffer((void **) &c.h_k3tab, &c.h_k3tab_cap, nd_max * sizeof(double));
     if (rc) return rc;
     // the pinned table may still be in flight from the previous step
     KSN_CUDA(cudaStreamSynchronize(c.stream));
-    double *K2 = c.h_k3tab, *inv = K2 + nbins, *A = inv + nbins, *B = A + nbins;
-    unsigned short *cell = (unsigned short *) (B + nbins);
+    K3Seg *seg = (K3Seg *) c.h_k3tab;
     const double unit = boxsize / (2 * M_PI);
+    double min_gap = 1e300;
     for (int i = 0; i < nbins; i++) {
         const double kg = exp(logkk[i]) * unit;     // knot in integer-wave-number units
-        K2[i] = kg * kg;
-        inv[i] = 1.0 / K2[i];
-        A[i] = 1.0 + norm * ratio[i];
-        B[i] = (i + 1 < nbins) ? norm * (ratio[i + 1] - ratio[i]) / (2.0 * (logkk[i + 1] - logkk[i])) : 0.0;
+        seg[i].K2 = kg * kg;
+        seg[i].inv = 1.0 / seg[i].K2;
+        seg[i].A = 1.0 + norm * ratio[i];
+        seg[i].B = (i + 1 < nbins) ? norm * (ratio[i + 1] - ratio[i]) / (2.0 * (logkk[i + 1] - logkk[i])) : 0.0;
+        if (i > 0) min_gap = fmin(min_gap, 2.0 * (logkk[i] - logkk[i - 1]) / M_LN2);   // gap in log2(k2)
     }
-    const double lo = log2(K2[0]), hi = log2(K2[nbins - 1]);
-    const double scale = hi > lo ? K3_CELLS / (hi - lo) : 0.0;
+    seg[nbins].K2 = INFINITY; seg[nbins].inv = 0; seg[nbins].A = seg[nbins - 1].A; seg[nbins].B = 0;
+    const double lo = log2(seg[0].K2), hi = log2(seg[nbins - 1].K2);
+    // cells narrow enough that (with the float-rounding guard) no cell sees two knots
+    int cells = 1024;
+    while (cells < K3_MAX_CELLS && (hi - lo) / cells * 1.05 >= min_gap) cells *= 2;
+    if ((hi - lo) / cells * 1.05 >= min_gap)
+        return set_error(KSN_EINVAL, "K3: table knots closer than %g in log2(k^2) are not supported", (hi - lo) / K3_MAX_CELLS * 1.05);
+    const double scale = cells / (hi - lo);
+    unsigned short *cell = (unsigned short *) (seg + nbins + 1);
     int s = 0;
-    for (int k = 0; k < K3_CELLS; k++) {
-        // last knot at or below the lower edge of cell k (minus a float-rounding guard)
-        const double edge = exp2(lo + (k - 0.01) / (scale > 0 ? scale : 1.0));
-        while (s + 1 < nbins && K2[s + 1] <= edge) s++;
+    for (int k = 0; k < cells; k++) {
+        // last knot at or below the lower edge of cell k, minus a guard for the float log2 on the device
+        const double edge = exp2(lo + (k - 0.02) / scale);
+        while (s + 1 < nbins && seg[s + 1].K2 <= edge) s++;
         cell[k] = (unsigned short) s;
     }
     g_k3prm.n = nbins;
+    g_k3prm.cells = cells;
     g_k3prm.cell_lo = (float) lo;
     g_k3prm.cell_scale = (float) scale;
-    KSN_CUDA(cudaMemcpyAsync(c.d_k3tab, c.h_k3tab, nd * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    KSN_CUDA(cudaMemcpyAsync(c.d_k3tab, c.h_k3tab, k3_tab_doubles(nbins, cells) * sizeof(double), cudaMemcpyHostToDevice, c.stream));
     return KSN_OK;
 }
 
 int k3_launch(void *dgrid, int real_bytes, int dims, long long plane0_global, long long nplanes, int nknots)
 {
     Ctx &c = ctx();
-    const long long nelem = nplanes * dims * (dims / 2 + 1);
-    if (nelem == 0) return KSN_OK;
-    const size_t smem = k3_tab_doubles(nknots) * sizeof(double) + 16;
+    if (nplanes * dims > 0x7fffffffLL) return set_error(KSN_EINVAL, "K3: %lld rows in one slab", nplanes * dims);
+    const int nrows = (int) (nplanes * dims);
+    if (nrows == 0) return KSN_OK;
+    const size_t smem = k3_tab_doubles(nknots, g_k3prm.cells) * sizeof(double) + 16;
     if (smem > c.smem_optin) return set_error(KSN_EINVAL, "K3: %d knots need %zu B of shared memory", nknots, smem);
-    // two resident CTAs per SM when the table is small enough
-    const int per_sm = (2 * (smem + 1024) <= c.smem_optin) ? 2 : 1;
-    const long long ntiles = (nelem + K3_TILE - 1) / K3_TILE;
-    long long want = (ntiles + (K3_THREADS / 32) - 1) / (K3_THREADS / 32);
+    int per_sm = (int) ((c.smem_optin + 1024) / (smem + 1024));
+    per_sm = per_sm > 4 ? 4 : (per_sm < 1 ? 1 : per_sm);
+    const int warps_per_cta = K3_THREADS / 32;
+    long long want = ((long long) nrows + warps_per_cta - 1) / warps_per_cta;
     int ctas = (int) (want < (long long) c.num_sms * per_sm ? want : (long long) c.num_sms * per_sm);
-    if (ctas < 1) ctas = 1;
     if (real_bytes == 8) {
         KSN_CUDA(cudaFuncSetAttribute(k3_scale_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        k3_scale_kernel<double><<<ctas, K3_THREADS, smem, c.stream>>>((C2<double> *) dgrid, nelem, dims, plane0_global, c.d_k3tab, g_k3prm);
+        k3_scale_kernel<double><<<ctas, K3_THREADS, smem, c.stream>>>((C2<double> *) dgrid, nrows, dims, plane0_global, c.d_k3tab, g_k3prm);
     } else {
         KSN_CUDA(cudaFuncSetAttribute(k3_scale_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        k3_scale_kernel<float><<<ctas, K3_THREADS, smem, c.stream>>>((C2<float> *) dgrid, nelem, dims, plane0_global, c.d_k3tab, g_k3prm);
+        k3_scale_kernel<float><<<ctas, K3_THREADS, smem, c.stream>>>((C2<float> *) dgrid, nrows, dims, plane0_global, c.d_k3tab, g_k3prm);
     }
     c.launches++;
     KSN_CUDA(cudaGetLastError());

@@ -230,7 +230,10 @@ int ensure_host_pinned(const void *p, size_t bytes)
     if (e != cudaSuccess) { cudaGetLastError(); return 0; }
     if (at.type == cudaMemoryTypeHost) return 1;
     if (at.type != cudaMemoryTypeUnregistered) return 0;
-    if (getenv("KSN_NO_HOST_REGISTER")) return 0;
+    // Page-locking memory we do not own is only safe when the owner promises to unregister it
+    // before freeing it (a freed-and-reused address would otherwise DMA from stale pages):
+    // hosts opt in with ksn_host_register(); KSN_HOST_REGISTER=1 turns it on for every staged grid.
+    if (!getenv("KSN_HOST_REGISTER")) return 0;
     auto it = g_registered.find((uintptr_t) p);
     if (it != g_registered.end() && it->second >= bytes) return 1;
     if (it != g_registered.end()) { cudaHostUnregister((void *) p); g_registered.erase(it); }
@@ -418,6 +421,28 @@ static int copy_sync(void *dst, const void *src, size_t bytes, cudaMemcpyKind ki
     if (rc) return rc;
     KSN_CUDA(cudaMemcpyAsync(dst, src, bytes, kind, g_ctx.stream));
     KSN_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return KSN_OK;
+}
+
+int ksn_host_register(void *ptr, size_t bytes)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    auto it = g_registered.find((uintptr_t) ptr);
+    if (it != g_registered.end()) { cudaHostUnregister(ptr); g_registered.erase(it); }
+    KSN_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    g_registered[(uintptr_t) ptr] = bytes;
+    return KSN_OK;
+}
+
+int ksn_host_unregister(void *ptr)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    auto it = g_registered.find((uintptr_t) ptr);
+    if (it == g_registered.end()) return set_error(KSN_EINVAL, "ksn_host_unregister: pointer was not registered here");
+    KSN_CUDA(cudaHostUnregister(ptr));
+    g_registered.erase(it);
     return KSN_OK;
 }
 

@@ -41,7 +41,13 @@ static int between_passes(void *user, const double *power_sum, const double *kef
     double *delta_nu_curr = delta_cdm_curr + nk_allocated;
     double *keff = delta_cdm_curr + 2 * nk_allocated;
     long long *cnt = mymalloc("temp_modecount", nk_allocated * sizeof(long long));
-    if (!delta_cdm_last) delta_cdm_last = mymalloc("delta_cdm", nk_allocated * sizeof(double));
+    static int last_cap = 0;
+    if (!delta_cdm_last || last_cap < nk_allocated) {
+        /* the reference sizes this once (interface_gadget.c:85-86); re-size when the module is
+         * re-initialised with more bins */
+        delta_cdm_last = mymalloc("delta_cdm", nk_allocated * sizeof(double));
+        last_cap = nk_allocated;
+    }
     if (!cnt || !delta_cdm_last) terminate(1, "Could not allocate temporary memory for power spectra\n");
     memcpy(delta_cdm_curr, power_sum, nk_allocated * sizeof(double));
     memcpy(keff, keff_sum, nk_allocated * sizeof(double));

@@ -1,0 +1,135 @@
+"""K1 (total_powerspectrum) on the GPU against the reference's known answers, the reference
+sources compiled here (oracle/_ref) and size-independent properties.  Calls go through the C-ABI."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests import refs
+
+pytestmark = pytest.mark.gpu
+
+# powerspectrum_test.c:38-45
+KAT_COUNTS = [6, 12, 8, 3, 12, 12, 3, 6, 1]
+
+
+def test_kat_4cube_host_pointer(gpu):
+    g = refs.kat_grid_4()
+    nret, power, count, keffs = refs.total_powerspectrum(gpu, g, 15, fn="total_powerspectrum_f64")
+    assert nret == 9
+    assert list(count[:9]) == KAT_COUNTS
+    assert abs(keffs[2] - 1.73205) < 1e-5
+    assert abs(power[0] - 0.254834) < 1e-5 * 0.04
+    assert abs(power[1] - 0.00212722) < 1e-5 * 0.005
+    assert abs(power[2] - 0.00323766) < 1e-5 * 0.003
+
+
+def test_kat_4cube_device_pointer_and_float(gpu):
+    g = refs.kat_grid_4()
+    d = refs.DeviceBuffer(gpu, g)
+    nret, power, count, keffs = refs.total_powerspectrum(gpu, g, 15, fn="total_powerspectrum", pointer=d.ptr)
+    d.free()
+    assert nret == 9 and list(count[:9]) == KAT_COUNTS
+    assert abs(power[0] - 0.254834) < 1e-5 * 0.04
+    g32 = g.astype(np.float32)
+    nret, power, count, keffs = refs.total_powerspectrum(gpu, g32, 15, fn="total_powerspectrum_f32")
+    assert nret == 9 and list(count[:9]) == KAT_COUNTS
+    assert abs(power[1] - 0.00212722) < 1e-5 * 0.005
+
+
+@pytest.mark.parametrize("n,nrbins", [(8, 4), (16, 8), (32, 16), (64, 32), (96, 48), (128, 64), (128, 200)])
+def test_matches_reference_double(gpu, n, nrbins):
+    ref = refs.ref_lib(True)
+    if ref is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here); covered by the oracle restatement test")
+    g = refs.random_grid(n, seed=n)
+    r_n, r_p, r_c, r_k = refs.total_powerspectrum(ref, g, nrbins)
+    d = refs.DeviceBuffer(gpu, g)
+    m_n, m_p, m_c, m_k = refs.total_powerspectrum(gpu, g, nrbins, fn="total_powerspectrum_f64", pointer=d.ptr)
+    d.free()
+    assert m_n == r_n
+    assert np.array_equal(m_c[:m_n], r_c[:r_n])                    # mode counts: bit-exact
+    np.testing.assert_allclose(m_p[:m_n], r_p[:r_n], rtol=1e-10, atol=0)   # north-star tolerance, double grid
+    np.testing.assert_allclose(m_k[:m_n], r_k[:r_n], rtol=1e-10, atol=0)
+
+
+def test_matches_reference_float(gpu):
+    ref = refs.ref_lib(False)
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    n, nrbins = 64, 32
+    g = refs.random_grid(n, seed=5, dtype=np.float32)
+    r_n, r_p, r_c, r_k = refs.total_powerspectrum(ref, g, nrbins)
+    m_n, m_p, m_c, m_k = refs.total_powerspectrum(gpu, g, nrbins, fn="total_powerspectrum_f32")
+    assert m_n == r_n and np.array_equal(m_c[:m_n], r_c[:r_n])
+    np.testing.assert_allclose(m_p[:m_n], r_p[:r_n], rtol=1e-5)    # float-grid tolerance of the north star
+    np.testing.assert_allclose(m_k[:m_n], r_k[:r_n], rtol=1e-10)
+
+
+def _sums(gpu, g, nrbins, startslab, nslab, pointer=None):
+    n = g.shape[1]
+    from kspace_neutrinos_b200 import capi
+    thr = C.POINTER(C.c_uint)()
+    iw = capi.c_double_p()
+    assert gpu.ksn_bin_tables(n, nrbins, C.byref(thr), C.byref(iw)) == 0
+    power, keff = np.zeros(nrbins), np.zeros(nrbins)
+    count = np.zeros(nrbins, dtype=np.int64)
+    m2 = C.c_double()
+    sub = np.ascontiguousarray(g[startslab:startslab + nslab])
+    p = pointer if pointer is not None else sub.ctypes.data_as(C.c_void_p)
+    capi.check(gpu.ksn_powerspectrum_sums(p, g.dtype.itemsize, n, nrbins, startslab, nslab, thr, iw, refs.dptr(power), refs.dptr(keff),
+                                          count.ctypes.data_as(capi.c_longlong_p), C.byref(m2)))
+    return power, keff, count, m2.value
+
+
+@pytest.mark.parametrize("splits", [[0, 13, 64], [0, 1, 2, 40, 64], [0, 0, 64, 64]])
+def test_slab_partition_sums_to_whole(gpu, splits):
+    """Ragged and empty slabs: per-slab bin sums add up to the whole-grid sums (exactly for counts)."""
+    n, nrbins = 64, 32
+    g = refs.random_grid(n, seed=11)
+    P, K, Cn, M2 = _sums(gpu, g, nrbins, 0, n)
+    p = np.zeros(nrbins); k = np.zeros(nrbins); c = np.zeros(nrbins, dtype=np.int64); m2 = 0.0
+    for a, b in zip(splits[:-1], splits[1:]):
+        pp, kk, cc, mm = _sums(gpu, g, nrbins, a, b - a)
+        p += pp; k += kk; c += cc; m2 += mm
+    assert np.array_equal(c, Cn) and Cn.sum() == n ** 3 - 1
+    assert m2 == M2 == float(n) ** 6
+    np.testing.assert_allclose(p, P, rtol=1e-12)
+    np.testing.assert_allclose(k, K, rtol=1e-12)
+
+
+def test_bitwise_reproducible(gpu):
+    n, nrbins = 128, 64
+    g = refs.random_grid(n, seed=3)
+    d = refs.DeviceBuffer(gpu, g)
+    first = _sums(gpu, g, nrbins, 0, n, pointer=d.ptr)   # first call per geometry: the variant that also bins keff/count
+    a = _sums(gpu, g, nrbins, 0, n, pointer=d.ptr)
+    b = _sums(gpu, g, nrbins, 0, n, pointer=d.ptr)
+    h = _sums(gpu, g, nrbins, 0, n)        # staged from host memory, chunked
+    d.free()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    np.testing.assert_allclose(first[0], a[0], rtol=1e-13)
+    np.testing.assert_allclose(h[0], a[0], rtol=1e-13)
+
+
+def test_linearity_large(gpu):
+    """At a size the CPU oracle would take minutes for: P(c*grid) == P(grid) (normalised by |F(0)|^2),
+    sum(count) == N^3-1, and the last compacted bin holds exactly the corner mode."""
+    n, nrbins = 512, 256
+    from kspace_neutrinos_b200 import capi
+    nbytes = n * n * (n // 2 + 1) * 16
+    ptr = C.c_void_p()
+    capi.check(gpu.ksn_device_malloc(C.byref(ptr), nbytes))
+    capi.check(gpu.ksn_fill_synthetic_grid(ptr, 8, n, 0, n, 20261017, -1.0))
+    shape = np.empty((n, n, 1, 1))         # only shape[0], shape[1] are read
+    n1, p1, c1, k1 = refs.total_powerspectrum(gpu, shape, nrbins, fn="total_powerspectrum_f64", pointer=ptr)
+    assert c1[:n1].sum() == n ** 3 - 1 and c1[n1 - 1] == 1
+    # scale the grid by a k-independent factor with K3 (ratio table == const) and re-measure
+    logkk = np.array([-20.0, 20.0]); ratio = np.array([1.0, 1.0])
+    capi.check(gpu.ksn_scale_modes(ptr, 8, n, 0, n, 1.0, refs.dptr(logkk), refs.dptr(ratio), 2, 0.5))
+    n2, p2, c2, k2 = refs.total_powerspectrum(gpu, shape, nrbins, fn="total_powerspectrum_f64", pointer=ptr)
+    gpu.ksn_device_free(ptr)
+    assert n2 == n1 and np.array_equal(c1, c2)
+    # every mode except (0,0,0) was multiplied by 1.5 -> P grows by 2.25 relative to the unchanged |F(0)|^2
+    np.testing.assert_allclose(p2[:n1], 2.25 * p1[:n1], rtol=1e-12)
+    np.testing.assert_array_equal(k1, k2)

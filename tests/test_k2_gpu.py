@@ -1,0 +1,90 @@
+"""K2 (the linear-response integral) on the GPU: reference known answers, the reference sources
+(oracle/_ref, mini-GSL + exact host hubble_function calls) to 1e-10, and the CAMB fixtures."""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import pytest
+
+from kspace_neutrinos_b200 import capi
+from tests import refs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def state(gpu):
+    om = refs.make_omnu(gpu)
+    refs.set_background(gpu, om)
+    kk, delta_nu, delta_tot = refs.load_golden_state()
+    delta_cdm = refs.golden_delta_cdm(gpu, om, delta_nu, delta_tot)
+    transfer = refs.load_transfer(gpu)
+    return dict(om=om, kk=kk, delta_nu=delta_nu, delta_cdm=delta_cdm, transfer=transfer)
+
+
+def test_fslength_device_matches_host_and_kat(gpu, state):
+    """test_fslength (delta_tot_table_test.c:183-191) through the device table of 1/(aH)."""
+    kT = 8.61734e-5 * ((4 / 11.) ** (1 / 3.) * 1.00328) * refs.T_CMB0
+    hub = capi.HUBBLE_FN(lambda a, _u: gpu.hubble_function(a))
+    capi.check(gpu.ksn_set_background(hub, None, math.log(0.01) - 0.01, 0.01, 16384))
+    lo = np.array([math.log(0.5), math.log(0.1), math.log(0.01), math.log(0.9)])
+    out = np.zeros(4)
+    capi.check(gpu.ksn_fslength_device(refs.dptr(lo), 4, 0.0, 299792., refs.dptr(out)))
+    assert abs(out[0] / 1272.92 / (0.45 / kT) - 1) < 1e-5
+    for i in range(4):
+        host = gpu.fslength(lo[i], 0.0, 299792.)
+        assert abs(out[i] / host - 1) < 1e-11
+    capi.check(gpu.ksn_fslength_device(refs.dptr(lo[1:2].copy()), 1, math.log(0.5), 299792., refs.dptr(out)))
+    assert abs(out[0] / 5427.8 / (0.6 / kT) - 1) < 1e-5
+    gpu.ksn_invalidate_background()
+
+
+def _resume(libh, om, st, time):
+    d = refs.new_delta_tot(libh, om, len(st["kk"]))
+    libh.read_all_nu_state(C.byref(d), os.path.join(refs.GOLDEN, "delta_tot_nu.txt").encode())
+    libh.delta_tot_init(C.byref(d), len(st["kk"]), refs.dptr(st["kk"]), refs.dptr(st["delta_cdm"]), C.byref(st["transfer"]), time)
+    return d
+
+
+def test_get_delta_nu_update_golden(gpu, state):
+    """test_get_delta_nu_update (delta_tot_table_test.c:193-228): resume at a=1/3, compare with the saved P_nu."""
+    d = _resume(gpu, state["om"], state, 0.33333333)
+    assert d.ia == 25
+    out = np.zeros(len(state["kk"]))
+    gpu.get_delta_nu_update(C.byref(d), 0.33333333, len(out), refs.dptr(state["kk"]), refs.dptr(state["delta_cdm"]), refs.dptr(out), C.byref(state["transfer"]))
+    assert d.ia == 25
+    assert np.all(np.abs(out / state["delta_nu"] - 1) < 1e-2)
+    d.ia -= 1
+    gpu.get_delta_nu_update(C.byref(d), 0.33333333, len(out), refs.dptr(state["kk"]), refs.dptr(state["delta_cdm"]), refs.dptr(out), C.byref(state["transfer"]))
+    assert d.ia == 25
+    assert np.all(np.abs(out / state["delta_nu"] - 1) < 3e-2)
+
+
+@pytest.mark.parametrize("masses,hybrid", [((0.15, 0.15, 0.15), False), ((0.2, 0.1, 0.3), False), ((0.15, 0.15, 0.15), True)])
+def test_update_sequence_matches_reference(gpu, state, masses, hybrid):
+    """A run of get_delta_nu_update steps (kept rows, dropped rows, repeated a) against the reference
+    sources: delta_nu to 1e-10 relative (north-star tolerance), identical row bookkeeping."""
+    ref = refs.ref_lib(True)
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    outs = {}
+    for name, libh in (("ref", ref), ("gpu", gpu)):
+        om = refs.make_omnu(libh, masses)
+        if hybrid:
+            m = (C.c_double * 3)(*masses)
+            libh.init_hybrid_nu(C.byref(om.hybnu), m, 500.0, 2.99792458e10 / 1e5, 0.333, om.kBtnu)
+        refs.set_background(libh, om)
+        tr = refs.load_transfer(libh)
+        st = dict(state, om=om, transfer=tr)
+        d = _resume(libh, om, st, 0.3)
+        res = []
+        for a in (0.3, 0.3005, 0.312, 0.312, 0.33, 0.335, 0.36):
+            out = np.zeros(len(state["kk"]))
+            libh.get_delta_nu_update(C.byref(d), a, len(out), refs.dptr(state["kk"]), refs.dptr(state["delta_cdm"]), refs.dptr(out), C.byref(tr))
+            res.append((d.ia, out.copy(), np.array([d.delta_tot[5][i] for i in range(d.ia)])))
+        outs[name] = res
+    for (ia_r, o_r, row_r), (ia_g, o_g, row_g) in zip(outs["ref"], outs["gpu"]):
+        assert ia_r == ia_g
+        np.testing.assert_allclose(o_g, o_r, rtol=1e-10, atol=0)
+        np.testing.assert_allclose(row_g, row_r, rtol=1e-10, atol=0)

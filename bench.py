@@ -1,0 +1,352 @@
+#!/usr/bin/env python3
+"""bench.py -- PM k-modes/s of the per-PM-step k-space hot path (BASELINE.json metric).
+
+A step = one add_nu_power_to_rhogrid call (P(k) binning K1 -> cross-rank sum -> linear-response
+integral K2 at a ~100-row stored history -> mode scaling K3) on a synthetic Gaussian grid of
+PMGRID^3 (default 2048^3, double), x-slab sharded over --gpus ranks (strong scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, sm_100a)
+  python bench.py --impl reference [...]                           the reference's CPU code on the host cores
+
+Prints ONE JSON line on rank 0 (see the driver contract in the task statement).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "PM k-modes/s (P(k) bin + nu rhogrid correction)"
+UNIT = "modes/s"
+TRANSFER = os.path.join(ROOT, "tests", "golden", "ics_transfer_99.dat")
+REF_BENCH = os.path.join(ROOT, "oracle", "_ref", "ref_bench")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pmgrid", type=int, default=int(os.environ.get("KSN_BENCH_PMGRID", "2048")))
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-planes", type=int, default=0, help="planes per rank in the CPU sample (0 = auto)")
+    return ap.parse_args()
+
+
+def workload_config(n, gpus, extra=None):
+    cfg = {"workload": f"PMGRID={n}^3 double, x-slab sharded over {gpus} GPU(s), 3x0.1 eV, hybrid neutrinos on "
+                       f"(Vcrit=500, NuPartTime=0.333), 99-row delta_tot history (a=0.98+)",
+           "pmgrid": n, "stored_modes": n * n * (n // 2 + 1), "nrbins": n // 2,
+           "parallelism": f"slab{gpus}", "l2": "grid (>= 8.6 GB per GPU) far exceeds the 126 MB L2; no flush needed"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ----------------------------------------------------------------------------- reference / CPU arm
+def run_ref_bench(n, planes, ranks, steps, hybrid=1, timeout=1500):
+    """Time the reference's CPU path (oracle/_ref/ref_bench: reference sources + shims, forked ranks)."""
+    out = subprocess.run([REF_BENCH, str(n), str(planes), str(ranks), str(steps), str(hybrid), TRANSFER],
+                         capture_output=True, text=True, timeout=timeout)
+    if out.returncode != 0:
+        raise RuntimeError("ref_bench failed: " + out.stderr[-500:])
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def run_port_bench(n, planes, ranks, steps):
+    """Fallback when oracle/_ref is absent: the oracle port (oracle/libksn_oracle.so), one forked worker per
+    core, each on its own sub-slab (no cross-rank sum -- same arithmetic per mode)."""
+    import multiprocessing as mp
+    import numpy as np
+    from tests import refs
+
+    def work(r, q):
+        o = refs.orc()
+        m = refs.orc_module(n, masses=(0.1, 0.1, 0.1), hybrid=True)
+        L = n // 2 + 1
+        start = r * (n // ranks)
+        rng = np.random.default_rng(r)
+        g = rng.standard_normal((planes, n, L, 2))
+        if r == 0:
+            g[0, 0, 0] = (n ** 3, 0)
+        o.orc_add_nu_power_to_rhogrid(C.byref(m), 0.01, 512000.0, g.ctypes.data_as(C.c_void_p), 1, n, start, planes)
+        d = m.dtot
+        nk, rows = d.nk, 98
+        for k in range(nk):
+            base = d.delta_tot[k * d.namax]
+            for i in range(1, rows):
+                d.delta_tot[k * d.namax + i] = base * (i + 1)
+        for i in range(1, rows):
+            d.scalefact[i] = np.log(0.01 * (i + 1))
+        d.ia = rows
+        ts = []
+        for s in range(steps + 1):
+            t0 = time.perf_counter()
+            o.orc_add_nu_power_to_rhogrid(C.byref(m), 0.98 + 0.001 * (s + 1), 512000.0, g.ctypes.data_as(C.c_void_p), 1, n, start, planes)
+            ts.append(time.perf_counter() - t0)
+        q.put((r, ts[1:], int(d.n_evals)))
+
+    q = mp.Queue()
+    ps = [mp.Process(target=work, args=(r, q)) for r in range(ranks)]
+    for p in ps:
+        p.start()
+    res = [q.get() for _ in ps]
+    for p in ps:
+        p.join()
+    per_step = [max(t[1][s] for t in res) for s in range(steps)]
+    return {"N": n, "P": planes, "R": ranks, "steps": [{"total": t, "k1": None, "integral": None, "k3": None} for t in per_step]}
+
+
+def cpu_throughput(n, steps, planes=0):
+    """modes/s of the CPU path on all host cores, from a bounded sample (P planes per rank)."""
+    ranks = os.cpu_count() or 1
+    while n % ranks:
+        ranks -= 1
+    if planes <= 0:
+        # ~0.5 us per mode per core for the two grid passes -> aim at ~4 s per step
+        per_plane = n * (n // 2 + 1) * 0.5e-6
+        planes = max(1, min(n // ranks, int(4.0 / per_plane)))
+    if os.path.exists(REF_BENCH):
+        kind, r = "reference", run_ref_bench(n, planes, ranks, steps)
+    else:
+        kind, r = "port", run_port_bench(n, planes, ranks, steps)
+    scale = (n / ranks) / planes
+    full = []
+    for s in r["steps"]:
+        if s.get("integral") is not None:
+            full.append((s["k1"] + s["k3"]) * scale + s["integral"])
+        else:
+            full.append(s["total"] * scale)        # port: integral not separable; scaled with the grid (pessimistic for the CPU only by the integral share)
+    t = statistics.median(full)
+    modes = n * n * (n // 2 + 1)
+    sample = (f"{kind} CPU path, {ranks} forked ranks x {planes} planes of the {n}^3 grid per step "
+              f"(grid passes scaled by {scale:.1f} to the full slab = extrapolated; integral timed in full, "
+              f"nk={r.get('nk')}, Na={r.get('Na')}), {len(full)} step(s)")
+    return modes / t, t, {"kind": kind, "cores": ranks, "sample": sample, "raw": r}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.pmgrid
+    t0 = time.time()
+    val, t_step, info = cpu_throughput(n, max(1, args.steps), args.cpu_planes)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": 1, "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(n, args.gpus),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.time() - t0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- our arm
+def ours(args):
+    import torch
+    import torch.distributed as dist
+    from kspace_neutrinos_b200 import capi, host
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this framework has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    L = capi.lib()
+    capi.check(L.ksn_init(local_rank), "ksn_init")
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+        host.init_nccl_from_torch(rank, world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        capi.check(L.ksn_device_synchronize())
+
+    n = args.pmgrid
+    slab = host.slab_partition(n, world)[rank]
+    modes_total = n * n * (n // 2 + 1)
+    cosmo = host.Cosmology(transfer_file=TRANSFER, mnu=(0.1, 0.1, 0.1), hybrid_neutrinos_on=1)
+    sim = host.KspaceNeutrinos(cosmo, n, rank=rank)
+    grid = host.DeviceGrid(n, slab)
+    grid.fill_synthetic()
+    # first PM step at a = TimeTransfer initialises the integrator; then install a 98-row history
+    sim.add_nu_power_to_rhogrid(cosmo.time_transfer, grid.ptr, slab)
+    sim.seed_history(98)
+    a = 0.98
+    da = 0.001                                   # < 0.009: the row is integrated every step but not kept -> steady state
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                          # nvidia-smi needs ~1 s to deliver its first sample
+    for _ in range(max(3, args.warmup)):
+        a += da
+        sim.add_nu_power_to_rhogrid(a, grid.ptr, slab)
+    if rank == 0:
+        time.sleep(1.0)
+        sampler.rows.clear()                     # keep only samples taken during the timed region
+    stream = torch.cuda.ExternalStream(L.ksn_stream())
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    L.ksn_timing_enable(1)
+    L.ksn_timing_reset()
+    barrier()
+    ev0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        a += da
+        sim.add_nu_power_to_rhogrid(a, grid.ptr, slab)
+    ev1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = ev0.elapsed_time(ev1)
+    tm = capi.Timing()
+    L.ksn_timing_get(C.byref(tm))
+    L.ksn_timing_enable(0)
+    t = torch.tensor([dev_ms, wall * 1e3, tm.k1_ms, tm.k2_ms, tm.k3_ms, tm.comm_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms, k1_ms, k2_ms, k3_ms, comm_ms = t.tolist()
+    step_ms = dev_ms / args.steps
+    value = modes_total / (step_ms * 1e-3)
+    launches = int(tm.launches)
+
+    # ---- end to end: the same call on HOST buffers (pinned), H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e and args.e2e_steps > 0:
+        try:
+            pin = host.PinnedGrid(n, slab)
+            capi.check(L.ksn_memcpy_d2h(pin.ptr, grid.ptr, grid.nbytes))
+            a += da
+            sim.add_nu_power_to_rhogrid(a, pin.ptr, slab)          # warm-up (allocates the staging buffer)
+            barrier()
+            te = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                a += da
+                sim.add_nu_power_to_rhogrid(a, pin.ptr, slab)
+            barrier()
+            e_ms = (time.perf_counter() - te) * 1e3
+            te_t = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
+            e_step = te_t.item() / args.e2e_steps
+            e2e = {"value": modes_total / (e_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": grid.nbytes * world,
+                   "d2h_bytes_per_step": grid.nbytes * world, "ms_per_step": e_step, "steps": args.e2e_steps,
+                   "note": "add_nu_power_to_rhogrid on pinned HOST slabs: upload, K1, K2, K3, download, every step"}
+            pin.free()
+        except capi.KsnError as exc:
+            e2e = {"value": None, "unit": UNIT, "error": str(exc)}
+
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    peak = peaks.get("hbm_gbs", 6650.0)
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
+    local_modes = host.modes_in_slab(n, slab)
+    k3_launch_ms = k3_ms / args.steps
+    k1_launch_ms = k1_ms / args.steps
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(f"k3_{n}")
+    except (OSError, ValueError):
+        pass
+    roofline = {"bound": "hbm", "kernel": "k3_scale_kernel<double> (read-modify-write, 32 B per stored mode)",
+                "achieved": 32.0 * local_modes / (k3_launch_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": 32.0 * local_modes / (k3_launch_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
+                "k1": {"kernel": "k1_pair_kernel<double> (read-only, 16 B per stored mode)",
+                       "achieved": 16.0 * local_modes / (k1_launch_ms * 1e-3) / 1e9,
+                       "frac": 16.0 * local_modes / (k1_launch_ms * 1e-3) / 1e9 / peak},
+                "step": {"achieved": 48.0 * local_modes / (step_ms * 1e-3) / 1e9,
+                         "frac": 48.0 * local_modes / (step_ms * 1e-3) / 1e9 / peak,
+                         "frac_of_nominal_8TBs": 48.0 * local_modes / (step_ms * 1e-3) / 1e9 / 8000.0},
+                "k2_ms_per_step": k2_ms / args.steps, "comm_ms_per_step": comm_ms / args.steps}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(n, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roofline, "wall_ms_per_step": wall_ms / args.steps}
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            v, t_step, info = cpu_throughput(n, 1, args.cpu_planes)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"],
+                                    "s_per_step": t_step}
+        except Exception as exc:  # noqa: BLE001 - report, never fail the GPU number on the CPU leg
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "error": repr(exc)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        pass
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+    ours(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:  # noqa: BLE001
+        pass
+
+
+if __name__ == "__main__":
+    main()

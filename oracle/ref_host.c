@@ -9,8 +9,19 @@
 #include "omega_nu_single.h"
 #include "gadget_defines.h"
 
+#include <string.h>
+#include <time.h>
+
 int ThisTask = 0;
-int ksn_ref_quiet = 1;
+int ksn_ref_quiet = 1;     /* 0: print, 1: silent, 2: silent but record when the phase messages arrive */
+double ksn_ref_t_mass, ksn_ref_t_nupower;
+
+static double stamp(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
 
 static const _omega_nu *bg_omnu;
 static double bg_Omega_nonu, bg_OmegaLambda, bg_Hubble;
@@ -44,6 +55,11 @@ void terminate(int ierr, const char *fmt, ...)
 
 void message(int ierr, const char *fmt, ...)
 {
+    if (ksn_ref_quiet == 2) {
+        /* powerspectrum.c:96 and interface_common.c:130 mark the ends of the K1 and integral phases */
+        if (!strncmp(fmt, "Total powerspectrum mass", 24)) ksn_ref_t_mass = stamp();
+        else if (!strncmp(fmt, "Done getting neutrino power", 27)) ksn_ref_t_nupower = stamp();
+    }
     if (ksn_ref_quiet) return;
     if (ierr > 0 || ThisTask == 0) {
         va_list va;

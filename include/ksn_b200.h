@@ -52,6 +52,8 @@ int ksn_comm_nccl_init(const void *id128, int nranks, int rank);
  * place.  This is what an MPI host uses (MPI_Allreduce on its communicator). */
 typedef int (*ksn_allreduce_fn)(double *buf, size_t n, void *user);
 int ksn_comm_host_callback(ksn_allreduce_fn fn, void *user, int nranks, int rank);
+/* Sum n host doubles over the ranks of the active backend, in place (identity for one rank). */
+int ksn_comm_allreduce_host(double *buf, size_t n);
 int ksn_comm_rank(void);
 int ksn_comm_size(void);
 

@@ -84,6 +84,7 @@ PROTOTYPES = {
     "ksn_comm_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "ksn_comm_nccl_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "ksn_comm_host_callback": (C.c_int, [ALLREDUCE_FN, C.c_void_p, C.c_int, C.c_int]),
+    "ksn_comm_allreduce_host": (C.c_int, [c_double_p, C.c_size_t]),
     "ksn_comm_rank": (C.c_int, []),
     "ksn_comm_size": (C.c_int, []),
     "ksn_device_malloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),

@@ -380,6 +380,29 @@ int ksn_comm_host_callback(ksn_allreduce_fn fn, void *user, int nranks, int rank
     return KSN_OK;
 }
 
+int ksn_comm_allreduce_host(double *buf, size_t n)
+{
+    Ctx &c = g_ctx;
+    if (!buf && n) return set_error(KSN_EINVAL, "ksn_comm_allreduce_host: null buffer");
+    if (c.nranks == 1 || n == 0) return KSN_OK;
+    if (c.comm_kind == COMM_HOSTCB) {
+        int rc = c.cb(buf, n, c.cb_user);
+        return rc ? set_error(KSN_ECOMM, "host all-reduce callback returned %d", rc) : KSN_OK;
+    }
+    // NCCL backend: bounce through the device reduce buffer
+    int rc = ensure_init();
+    if (rc) return rc;
+    rc = ensure_device_buffer((void **) &c.d_red, &c.red_cap, n * sizeof(double));
+    if (rc) return rc;
+    rc = ensure_pinned_buffer((void **) &c.h_red, &c.h_red_cap, n * sizeof(double));
+    if (rc) return rc;
+    KSN_CUDA(cudaMemcpyAsync(c.d_red, buf, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    rc = allreduce_to_host(c.d_red, c.h_red, n);
+    if (rc) return rc;
+    memcpy(buf, c.h_red, n * sizeof(double));
+    return KSN_OK;
+}
+
 int ksn_comm_rank(void) { return g_ctx.rank; }
 int ksn_comm_size(void) { return g_ctx.nranks; }
 

@@ -88,3 +88,51 @@ def test_update_sequence_matches_reference(gpu, state, masses, hybrid):
         assert ia_r == ia_g
         np.testing.assert_allclose(o_g, o_r, rtol=1e-10, atol=0)
         np.testing.assert_allclose(row_g, row_r, rtol=1e-10, atol=0)
+
+
+def test_reproduce_linear_theory(gpu):
+    """test_reproduce_linear (delta_tot_table_test.c:315-363): 99 get_delta_nu_update steps a = 0.01 ... 0.99 fed with
+    CAMB's delta_cdm must track CAMB's neutrino transfer function (5 % -> 2 % from step 8 -> 1.2 % from step 22) and
+    store one row per step."""
+    z = np.load(os.path.join(refs.GOLDEN, "camb_linear_steps.npz"))
+    om = refs.make_omnu(gpu)
+    refs.set_background(gpu, om)
+    tr = refs.load_transfer(gpu, os.path.join(refs.GOLDEN, "camb_ics_transfer_0.01.dat"), box=512000.0)
+    d = refs.new_delta_tot(gpu, om, 200)
+    k0, d0 = np.ascontiguousarray(z["keffs"][0]), np.ascontiguousarray(z["delta_cdm"][0])
+    gpu.delta_tot_init(C.byref(d), 200, refs.dptr(k0), refs.dptr(d0), C.byref(tr), 0.01)
+    acc = 0.05
+    for i in range(99):
+        if i == 8:
+            acc = 2e-2
+        if i == 22:
+            acc = 1.2e-2
+        k, dc = np.ascontiguousarray(z["keffs"][i]), np.ascontiguousarray(z["delta_cdm"][i])
+        out = np.zeros(200)
+        gpu.get_delta_nu_update(C.byref(d), float(z["a"][i]), 200, refs.dptr(k), refs.dptr(dc), refs.dptr(out), C.byref(tr))
+        assert d.ia == i + 1
+        assert np.all(np.abs(z["delta_nu_camb"][i] - out) < acc * out), i
+
+
+def test_update_sequence_matches_oracle_port(gpu, state):
+    """Same as the reference-sources test but against the oracle restatement, which exists on every box."""
+    o = refs.orc()
+    masses = (0.2, 0.1, 0.3)
+    om = refs.make_omnu(gpu, masses)
+    refs.set_background(gpu, om)
+    tr = refs.load_transfer(gpu)
+    d = _resume(gpu, om, dict(state, om=om, transfer=tr), 0.3)
+    oc = refs.orc_cosmo(masses)
+    od = refs.OrcDtot()
+    n = len(state["kk"])
+    o.orc_dtot_alloc(C.byref(od), n, 0.01, 1.0, refs.OMEGA0, C.byref(oc), refs.UNIT_TIME, refs.UNIT_LENGTH)
+    o.orc_dtot_read(C.byref(od), os.path.join(refs.GOLDEN, "delta_tot_nu.txt").encode())
+    tl, tt = capi.c_double_p(), capi.c_double_p()
+    nt = o.orc_transfer_read(os.path.join(refs.GOLDEN, "ics_transfer_99.dat").encode(), refs.BOX, refs.UNIT_LENGTH, refs.UNIT_LENGTH * 1e3, C.byref(tl), C.byref(tt))
+    o.orc_dtot_init(C.byref(od), n, refs.dptr(state["kk"]), refs.dptr(state["delta_cdm"]), tl, tt, nt, 0.3)
+    for a in (0.3, 0.3005, 0.312, 0.312, 0.33, 0.36):
+        g, w = np.zeros(n), np.zeros(n)
+        gpu.get_delta_nu_update(C.byref(d), a, n, refs.dptr(state["kk"]), refs.dptr(state["delta_cdm"]), refs.dptr(g), C.byref(tr))
+        assert o.orc_get_delta_nu_update(C.byref(od), a, n, refs.dptr(state["kk"]), refs.dptr(state["delta_cdm"]), refs.dptr(w), tl, tt, nt) == 0
+        assert d.ia == od.ia
+        np.testing.assert_allclose(g, w, rtol=1e-10, atol=0)

@@ -47,3 +47,20 @@ def test_add_nu_power_matches_reference(gpu, n, hybrid, masses, on_device):
         np.testing.assert_allclose(dn_g, dn_r, rtol=1e-10, atol=0)
         np.testing.assert_allclose(g_g, g_r, rtol=1e-10, atol=0)
         assert not np.array_equal(g_g, g)
+
+
+def test_add_nu_power_matches_oracle_port(gpu):
+    """Whole step against the oracle restatement (available on every box), float grid included."""
+    o = refs.orc()
+    n = 32
+    for dtype, tol, fn in ((np.float64, 1e-10, "add_nu_power_to_rhogrid_f64"), (np.float32, 1e-5, "add_nu_power_to_rhogrid_f32")):
+        g = refs.random_grid(n, seed=5, dtype=dtype)
+        times = (0.01, 0.03, 0.0305, 0.1)
+        got = _run(gpu, fn, g, times, True, masses=(0.1, 0.1, 0.1))
+        m = refs.orc_module(n, masses=(0.1, 0.1, 0.1))
+        cur = g.copy()
+        for (ia, nk, gg, dnu), a in zip(got, times):
+            assert o.orc_add_nu_power_to_rhogrid(C.byref(m), a, refs.BOX, cur.ctypes.data_as(C.c_void_p), 1 if dtype == np.float64 else 0, n, 0, n) == 0
+            assert (m.dtot.ia, m.dtot.nk) == (ia, nk)
+            np.testing.assert_allclose(dnu, np.array([m.dtot.delta_nu_last[i] for i in range(nk)]), rtol=tol)
+            np.testing.assert_allclose(gg, cur, rtol=tol, atol=0)

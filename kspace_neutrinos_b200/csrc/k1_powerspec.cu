@@ -390,7 +390,8 @@ __global__ void k1_final_kernel(const double *__restrict__ partial, int ctas, in
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nv * nrbins) {
         double s = 0.0;
-        for (int c = 0; c < ctas; c++) s += partial[(size_t) c * nv * nrbins + i];
+#pragma unroll 8
+        for (int c = 0; c < ctas; c++) s += partial[(size_t) c * nv * nrbins + i];   // fixed CTA order
         const int which = i / nrbins, b = i - which * nrbins;
         red[which == 0 ? b : which * nrbins + 1 + b] = s;
     }

@@ -181,24 +181,29 @@ __device__ __forceinline__ int bin_of(int k2, float binscale, const uint2 *thr_s
     return b + ((unsigned) k2 >= t.y) - ((unsigned) k2 < t.x);
 }
 
-// U warp steps of 32 pairs each, starting at pair index q0 (this lane's first pair).  zfirst = z of
-// pair 0's first element (0 or 1, whichever makes the pair 32-byte aligned in this row).
+// A group = U warp steps of 32 pairs each, starting at pair index q0 (this lane's first pair).  zfirst = z of pair
+// 0's first element (0 or 1, whichever makes the pairs 32-byte aligned in this row).  The work is split in three
+// so that the row loop can issue the NEXT group's loads between phase A (which consumes the loaded registers) and
+// phases B/C (shuffle scans + bin updates, ~60 % of the instructions): loads stay in flight behind the compute.
 template <typename real, int U, bool MASKED>
-__device__ __forceinline__ void k1_pair_group(const Cplx<real> *__restrict__ rowptr, int q0, int npairs, int zfirst, int c, double wxy,
-                                              float binscale, int nrbins, const uint2 *thr_s, const double *iw_s,
-                                              double *mybins, int lane, bool origin_row)
+__device__ __forceinline__ void pair_load(Pair<real> (&v)[U], const Cplx<real> *__restrict__ rowptr, int q0, int npairs, int zfirst)
 {
-    const unsigned full = 0xffffffffu, le_mask = full >> (31 - lane);
-    Pair<real> v[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
         const int q = q0 + 32 * u;
         if (!MASKED || q < npairs) v[u] = ld_pair((const Pair<real> *) (rowptr + zfirst + 2 * q));
         else { v[u].re0 = 0; v[u].im0 = 0; v[u].re1 = 0; v[u].im1 = 0; }
     }
+}
+
+// Phase A: bins and weighted powers of both modes of every pair; x = the lane's contribution to the run that
+// contains its second mode.
+template <typename real, int U, bool MASKED>
+__device__ __forceinline__ void pair_phaseA(Pair<real> (&v)[U], int q0, int npairs, int zfirst, int c, double wxy, float binscale,
+                                            const uint2 *thr_s, const double *iw_s, bool origin_row,
+                                            int (&ba)[U], int (&bb)[U], double (&pa)[U], double (&x)[U])
+{
     if (origin_row && zfirst == 0 && q0 == 0) { v[0].re0 = 0; v[0].im0 = 0; }   // F(0,0,0) is not a mode
-    int ba[U], bb[U];
-    double pa[U], x[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
         const int q = MASKED ? min(q0 + 32 * u, npairs - 1) : q0 + 32 * u;
@@ -211,9 +216,17 @@ __device__ __forceinline__ void k1_pair_group(const Cplx<real> *__restrict__ row
         pa[u] = mode_power(e0, wxy, iw_s[z]);
         const double pb = mode_power(e1, wxy, iw_s[z + 1]);
         if (MASKED && q0 + 32 * u >= npairs) { ba[u] = 0x7fffffff; bb[u] = 0x7fffffff; }
-        // the lane's contribution to the run that contains its second mode
         x[u] = fma(pa[u], __hiloint2double(ba[u] == bb[u] ? 0x3ff00000 : 0, 0), pb);
     }
+}
+
+// Phases B and C: one segmented scan per step over the lanes' run contributions, then the run totals go to the
+// warp-private bins (distinct bins within a step because bins are monotone along a row -> plain read-modify-write).
+template <int U, bool MASKED>
+__device__ __forceinline__ void pair_phaseBC(const int (&ba)[U], const int (&bb)[U], const double (&pa)[U], double (&x)[U],
+                                             double *mybins, int lane)
+{
+    const unsigned full = 0xffffffffu, le_mask = full >> (31 - lane), eq_mask = 1u << lane;
     unsigned tails[U];
     double carry[U];
 #pragma unroll
@@ -232,7 +245,6 @@ __device__ __forceinline__ void k1_pair_group(const Cplx<real> *__restrict__ row
         x[u] = sx;
         tails[u] = ~(contmask >> 1) | 0x80000000u;               // lane l ends a run iff lane l+1 does not continue it
     }
-    const unsigned eq_mask = 1u << lane;
 #pragma unroll
     for (int u = 0; u < U; u++) {
         if (!MASKED || ba[u] != 0x7fffffff) {
@@ -284,32 +296,70 @@ k1_pair_kernel(const Cplx<real> *__restrict__ grid, int nrows, int N, int nrbins
     double *mybins = bins_s + (size_t) warp * nrbins;
     // the slab base may itself sit on an odd 16-byte boundary
     const int base_odd = (int) (((size_t) grid / sizeof(Cplx<real>)) & 1);
-    for (int r = blockIdx.x * nwarps + warp; r < nrows; r += gridDim.x * nwarps) {
+    const int stride = gridDim.x * nwarps;
+
+    struct Row { const Cplx<real> *ptr; int c, zfirst, npairs, nfull; double wxy; };
+    auto setup = [&](int r) {
+        Row R;
         const int pl = r / N, j = r - pl * N;
         const long long gi = plane0 + pl;
         const int ki = gi <= N / 2 ? (int) gi : (int) (gi - N);
         const int kj = j <= N / 2 ? j : j - N;
-        const int c = ki * ki + kj * kj;
-        double wxy;
-        {
-            const double a = iw_s[L + (ki < 0 ? -ki : ki)], b = iw_s[L + (kj < 0 ? -kj : kj)];
-            wxy = sizeof(real) == 4 ? (double) ((float) a * (float) b) : a * b;
-        }
-        const Cplx<real> *rowptr = grid + (size_t) r * L;
+        R.c = ki * ki + kj * kj;
+        const double a = iw_s[L + (ki < 0 ? -ki : ki)], b = iw_s[L + (kj < 0 ? -kj : kj)];
+        R.wxy = sizeof(real) == 4 ? (double) ((float) a * (float) b) : a * b;
+        R.ptr = grid + (size_t) r * L;
         // pairs must start on a 2-element boundary of the slab: skip z=0 when the row starts odd
-        const int zfirst = (int) ((((size_t) r * L) + base_odd) & 1);
-        const int npairs = (L - zfirst) >> 1;
-        if (zfirst) k1_single<real>(rowptr, 0, c, wxy, binscale, thr_s, iw_s, mybins, lane);
-        if ((L - zfirst) & 1) k1_single<real>(rowptr, L - 1, c, wxy, binscale, thr_s, iw_s, mybins, lane);
-        const int nfull_groups = (npairs / 32) / U;
-        const int nsteps = (npairs + 31) / 32;
-        int g = 0;
+        R.zfirst = (int) ((((size_t) r * L) + base_odd) & 1);
+        R.npairs = (L - R.zfirst) >> 1;
+        R.nfull = (R.npairs / 32) / U;              // groups of U steps that lie entirely inside the row
+        return R;
+    };
+
+    int r = blockIdx.x * nwarps + warp;
+    Pair<real> v[U];
+    Row cur;
+    if (r < nrows) {
+        cur = setup(r);
+        if (cur.nfull > 0) pair_load<real, U, false>(v, cur.ptr, lane, cur.npairs, cur.zfirst);
+    }
+    while (r < nrows) {
+        // the unpaired first / last mode of the row
+        if (cur.zfirst) k1_single<real>(cur.ptr, 0, cur.c, cur.wxy, binscale, thr_s, iw_s, mybins, lane);
+        if ((L - cur.zfirst) & 1) k1_single<real>(cur.ptr, L - 1, cur.c, cur.wxy, binscale, thr_s, iw_s, mybins, lane);
+        const int rn = r + stride;
+        Row nxt = cur;
+        int ba[U], bb[U];
+        double pa[U], x[U];
 #pragma unroll 1
-        for (; g < nfull_groups; g++)
-            k1_pair_group<real, U, false>(rowptr, lane + g * 32 * U, npairs, zfirst, c, wxy, binscale, nrbins, thr_s, iw_s, mybins, lane, c == 0);
+        for (int g = 0; g < cur.nfull; g++) {
+            pair_phaseA<real, U, false>(v, lane + g * 32 * U, cur.npairs, cur.zfirst, cur.c, cur.wxy, binscale, thr_s, iw_s, cur.c == 0, ba, bb, pa, x);
+            // v is free again: put the next group's loads in flight before the shuffle-heavy phases
+            if (g + 1 < cur.nfull) {
+                pair_load<real, U, false>(v, cur.ptr, lane + (g + 1) * 32 * U, cur.npairs, cur.zfirst);
+            } else if (rn < nrows) {
+                nxt = setup(rn);
+                if (nxt.nfull > 0) pair_load<real, U, false>(v, nxt.ptr, lane, nxt.npairs, nxt.zfirst);
+            }
+            pair_phaseBC<U, false>(ba, bb, pa, x, mybins, lane);
+        }
+        if (cur.nfull == 0 && rn < nrows) {          // rows shorter than one full group: nothing was prefetched
+            nxt = setup(rn);
+            if (nxt.nfull > 0) pair_load<real, U, false>(v, nxt.ptr, lane, nxt.npairs, nxt.zfirst);
+        }
+        // the rest of the row goes one (masked) step at a time
+        const int nsteps = (cur.npairs + 31) / 32;
 #pragma unroll 1
-        for (int st = g * U; st < nsteps; st++)
-            k1_pair_group<real, 1, true>(rowptr, lane + st * 32, npairs, zfirst, c, wxy, binscale, nrbins, thr_s, iw_s, mybins, lane, c == 0);
+        for (int st = cur.nfull * U; st < nsteps; st++) {
+            Pair<real> v1[1];
+            int ba1[1], bb1[1];
+            double pa1[1], x1[1];
+            pair_load<real, 1, true>(v1, cur.ptr, lane + st * 32, cur.npairs, cur.zfirst);
+            pair_phaseA<real, 1, true>(v1, lane + st * 32, cur.npairs, cur.zfirst, cur.c, cur.wxy, binscale, thr_s, iw_s, cur.c == 0, ba1, bb1, pa1, x1);
+            pair_phaseBC<1, true>(ba1, bb1, pa1, x1, mybins, lane);
+        }
+        r = rn;
+        cur = nxt;
     }
     __syncthreads();
     double *out = partial + (size_t) blockIdx.x * nrbins;

@@ -97,6 +97,96 @@ template <int U> __global__ void read128_rows(const D2 *p, int nrows, int rowlen
     if (s == 123.456) out[0] = s;
 }
 
+__device__ __forceinline__ void pf_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// rows, NOT persistent: CTA b handles rows [b*RPC, (b+1)*RPC), one warp per row at a time
+template <int U> __global__ void scale128_rows_np(D2 *p, int nrows, int rowlen, int rpc, double f)
+{
+    const int nw = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r1 = min(nrows, (blockIdx.x + 1) * rpc);
+    for (int r = blockIdx.x * rpc + w; r < r1; r += nw) {
+        D2 *row = p + (size_t) r * rowlen;
+        for (int z0 = lane; z0 + 32 * (U - 1) < rowlen; z0 += 32 * U) {
+            D2 v[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) v[u] = ld128rw(row + z0 + 32 * u);
+#pragma unroll
+            for (int u = 0; u < U; u++) { v[u].a *= f; v[u].b *= f; st128(row + z0 + 32 * u, v[u]); }
+        }
+    }
+}
+// persistent rows with an L2 prefetch DIST groups ahead
+template <int U, int DIST> __global__ void scale128_rows_pf(D2 *p, int nrows, int rowlen, double f)
+{
+    const int nw = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = blockIdx.x * nw + w; r < nrows; r += gridDim.x * nw) {
+        D2 *row = p + (size_t) r * rowlen;
+        for (int z0 = lane; z0 + 32 * (U - 1) < rowlen; z0 += 32 * U) {
+            D2 v[U];
+            if ((lane & 7) == 0) {
+#pragma unroll
+                for (int u = 0; u < U; u++) pf_l2(row + z0 + 32 * (u + U * DIST));
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) v[u] = ld128rw(row + z0 + 32 * u);
+#pragma unroll
+            for (int u = 0; u < U; u++) { v[u].a *= f; v[u].b *= f; st128(row + z0 + 32 * u, v[u]); }
+        }
+    }
+}
+template <int U, int DIST> __global__ void read128_rows_pf(const D2 *p, int nrows, int rowlen, double *out)
+{
+    double s = 0;
+    const int nw = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = blockIdx.x * nw + w; r < nrows; r += gridDim.x * nw) {
+        const D2 *row = p + (size_t) r * rowlen;
+        for (int z0 = lane; z0 + 32 * (U - 1) < rowlen; z0 += 32 * U) {
+            D2 v[U];
+            if ((lane & 7) == 0) {
+#pragma unroll
+                for (int u = 0; u < U; u++) pf_l2(row + z0 + 32 * (u + U * DIST));
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) v[u] = ld128(row + z0 + 32 * u);
+#pragma unroll
+            for (int u = 0; u < U; u++) s += v[u].a + v[u].b;
+        }
+    }
+    if (s == 123.456) out[0] = s;
+}
+
+// CTA-cooperative rows: the whole CTA sweeps RPI consecutive rows per iteration; warp w takes the w-th
+// 32*U-element segment of the (contiguous) RPI-row block -> CTA-wide accesses are contiguous
+template <int U> __global__ void scale128_ctarows(D2 *p, size_t nelem, double f, int persistent)
+{
+    const size_t per_cta = (size_t) blockDim.x * U;            // elements per CTA iteration
+    const size_t ntiles = (nelem + per_cta - 1) / per_cta;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (size_t t = blockIdx.x; t < ntiles; t += persistent ? gridDim.x : ntiles) {
+        const size_t base = t * per_cta + (size_t) w * 32 * U + lane;
+        D2 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) if (base + 32 * u < nelem) v[u] = ld128rw(p + base + 32 * u);
+#pragma unroll
+        for (int u = 0; u < U; u++) if (base + 32 * u < nelem) { v[u].a *= f; v[u].b *= f; st128(p + base + 32 * u, v[u]); }
+    }
+}
+template <int U> __global__ void read128_ctarows(const D2 *p, size_t nelem, double *out, int persistent)
+{
+    double s = 0;
+    const size_t per_cta = (size_t) blockDim.x * U;
+    const size_t ntiles = (nelem + per_cta - 1) / per_cta;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (size_t t = blockIdx.x; t < ntiles; t += persistent ? gridDim.x : ntiles) {
+        const size_t base = t * per_cta + (size_t) w * 32 * U + lane;
+        D2 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) if (base + 32 * u < nelem) v[u] = ld128(p + base + 32 * u); else { v[u].a = 0; v[u].b = 0; }
+#pragma unroll
+        for (int u = 0; u < U; u++) s += v[u].a + v[u].b;
+    }
+    if (s == 123.456) out[0] = s;
+}
+
 template <class F> static void timeit(const char *name, double bytes, F f)
 {
     cudaEvent_t a, b;
@@ -135,6 +225,23 @@ int main(int argc, char **argv)
         snprintf(nm, 96, "scale256 flat U4 grid=%d x %d", g, t); timeit(nm, 2 * bytes, [&] { scale256<4><<<g, t>>>((D4 *) p, n / 2, 1.0); });
         snprintf(nm, 96, "scale128 rows U4 grid=%d x %d", g, t); timeit(nm, 2 * bytes, [&] { scale128_rows<4><<<g, t>>>((D2 *) p, N * N, L, 1.0); });
         snprintf(nm, 96, "scale128 rows U8 grid=%d x %d", g, t); timeit(nm, 2 * bytes, [&] { scale128_rows<8><<<g, t>>>((D2 *) p, N * N, L, 1.0); });
+    }
+    timeit("read128 rows U8 pf1 148x512", bytes, [&] { read128_rows_pf<8, 1><<<148, 512>>>((D2 *) p, N * N, L, out); });
+    timeit("read128 rows U8 pf2 148x512", bytes, [&] { read128_rows_pf<8, 2><<<148, 512>>>((D2 *) p, N * N, L, out); });
+    timeit("read128 rows U8 pf4 148x512", bytes, [&] { read128_rows_pf<8, 4><<<148, 512>>>((D2 *) p, N * N, L, out); });
+    timeit("scale128 rows U4 pf2 592x256", 2 * bytes, [&] { scale128_rows_pf<4, 2><<<592, 256>>>((D2 *) p, N * N, L, 1.0); });
+    timeit("scale128 rows U4 pf4 592x256", 2 * bytes, [&] { scale128_rows_pf<4, 4><<<592, 256>>>((D2 *) p, N * N, L, 1.0); });
+    timeit("scale128 cta-contig U4 persistent 592x256", 2 * bytes, [&] { scale128_ctarows<4><<<592, 256>>>((D2 *) p, n, 1.0, 1); });
+    timeit("scale128 cta-contig U8 persistent 296x256", 2 * bytes, [&] { scale128_ctarows<8><<<296, 256>>>((D2 *) p, n, 1.0, 1); });
+    timeit("scale128 cta-contig U4 persistent 1184x256", 2 * bytes, [&] { scale128_ctarows<4><<<1184, 256>>>((D2 *) p, n, 1.0, 1); });
+    timeit("scale128 cta-contig U4 one-tile-per-CTA x256", 2 * bytes, [&] { scale128_ctarows<4><<<(unsigned) ((n + 1023) / 1024), 256>>>((D2 *) p, n, 1.0, 0); });
+    timeit("read128 cta-contig U8 persistent 148x512", bytes, [&] { read128_ctarows<8><<<148, 512>>>((D2 *) p, n, out, 1); });
+    timeit("read128 cta-contig U8 persistent 296x512", bytes, [&] { read128_ctarows<8><<<296, 512>>>((D2 *) p, n, out, 1); });
+    timeit("read128 cta-contig U8 one-tile-per-CTA x512", bytes, [&] { read128_ctarows<8><<<(unsigned) ((n + 4095) / 4096), 512>>>((D2 *) p, n, out, 0); });
+    for (int rpc : {8, 16, 64, 256}) {
+        char nm[96];
+        snprintf(nm, 96, "scale128 rows U4 non-persistent rpc=%d x256", rpc);
+        timeit(nm, 2 * bytes, [&] { scale128_rows_np<4><<<(N * N + rpc - 1) / rpc, 256>>>((D2 *) p, N * N, L, rpc, 1.0); });
     }
     // big grids (not persistent): one CTA per 64 KB
     {

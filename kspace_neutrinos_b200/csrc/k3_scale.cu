@@ -25,7 +25,6 @@
 namespace ksn {
 
 constexpr int K3_MAX_CELLS = 16384;
-constexpr int K3_UNROLL = 4;
 constexpr int K3_THREADS = 256;
 
 template <typename real> struct C2;
@@ -139,6 +138,91 @@ k3_scale_kernel(C2<real> *__restrict__ grid, int nrows, int rows_per_cta, int N,
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// TMA variant (default for double/float grids): the CTA's block of rows is brought into shared memory by ONE bulk
+// asynchronous copy (cp.async.bulk, completion on an mbarrier) issued before anything else; while it is in flight every
+// thread computes the scale factors of its modes (they depend on geometry only), then scales in shared memory and one
+// bulk store writes the block back.  In-flight bytes are bounded by shared memory (~32 KB per CTA, 5-6 CTAs per SM),
+// not by registers.
+constexpr int K3_EPT = 9;                  // modes per thread
+constexpr int K3_TMA_THREADS = 128;        // <= 1152 modes (one 2048^3 row) per CTA: many small CTAs keep L1 for the tables
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
+
+template <typename real, bool ONE_ROW>
+__global__ void __launch_bounds__(K3_TMA_THREADS, 8)
+k3_scale_tma_kernel(C2<real> *__restrict__ grid, int nrows, int rows_per_cta, int N, long long plane0,
+                    const double *__restrict__ tab, const K3Params prm)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bar;
+    C2<real> *buf = (C2<real> *) smem_raw;
+    const K3Seg *seg = (const K3Seg *) tab;
+    const unsigned short *cellv = (const unsigned short *) (seg + prm.n + 1);
+    const int L = N / 2 + 1;
+    const int row0 = blockIdx.x * rows_per_cta;
+    const int nr = min(rows_per_cta, nrows - row0);
+    const int nel = nr * L;
+    const unsigned bytes = (unsigned) nel * (unsigned) sizeof(C2<real>);
+    C2<real> *base = grid + (size_t) row0 * L;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(buf)), "l"(base), "r"(bytes), "r"(smem_u32(&bar)) : "memory");
+    }
+    // factors while the copy is in flight
+    auto row_c = [&](int r) {                // kx^2 + ky^2 of grid row r
+        const int pl = r / N, j = r - pl * N;
+        const long long gi = plane0 + pl;
+        const int ki = gi <= N / 2 ? (int) gi : (int) (gi - N);
+        const int kj = j <= N / 2 ? j : j - N;
+        return ki * ki + kj * kj;
+    };
+    const int c0 = row_c(row0);              // CTA-uniform: the only row when ONE_ROW
+    double smth[K3_EPT];
+#pragma unroll
+    for (int k = 0; k < K3_EPT; k++) {
+        const int e = threadIdx.x + K3_TMA_THREADS * k;
+        smth[k] = 1.0;
+        if (e < nel) {
+            int k2i;
+            if (ONE_ROW) {
+                k2i = c0 + e * e;
+            } else {
+                const int rl = e / L, z = e - rl * L;
+                k2i = row_c(row0 + rl) + z * z;
+            }
+            if (k2i > 0) smth[k] = k3_factor<real>(k2i, seg, cellv, prm);     // F(0,0,0) keeps factor 1
+        }
+    }
+    __syncthreads();                       // the barrier was initialised before anyone polls it
+    {
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(&bar)) : "memory");
+    }
+#pragma unroll
+    for (int k = 0; k < K3_EPT; k++) {
+        const int e = threadIdx.x + K3_TMA_THREADS * k;
+        if (e < nel) {
+            C2<real> v = buf[e];
+            v.re = (real) ((double) v.re * smth[k]);
+            v.im = (real) ((double) v.im * smth[k]);
+            buf[e] = v;
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the bulk store
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(base), "r"(smem_u32(buf)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the read
+    }
+}
+
 static size_t k3_tab_doubles(int n, int cells) { return (size_t) 4 * (n + 1) + ((size_t) cells * sizeof(unsigned short) + 7) / 8; }
 static K3Params g_k3prm;
 
@@ -197,6 +281,25 @@ int k3_launch(void *dgrid, int real_bytes, int dims, long long plane0_global, lo
     if (nrows == 0) return KSN_OK;
     constexpr int U = 4;
     const int L = dims / 2 + 1;
+    if (real_bytes == 8 && !getenv("KSN_K3_NOTMA") && L <= K3_TMA_THREADS * K3_EPT) {   // bulk copies need 16-byte granules: double grids
+        // ~16 KB of grid per CTA (at least one row): one row at PMGRID=2048, 7 CTAs per SM inside a 132 KB carve-out
+        const size_t row_bytes = (size_t) L * 2 * real_bytes;
+        int rpc = (int) ((size_t) K3_TMA_THREADS * K3_EPT / L);
+        while (rpc > 1 && rpc * row_bytes > 18432) rpc--;
+        const size_t smem = rpc * row_bytes + 128;
+        const int nct = (nrows + rpc - 1) / rpc;
+        auto go = [&](auto kern) -> int {
+            KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 58));   // ~132 of 228 KB: L1 keeps the tables
+            kern<<<nct, K3_TMA_THREADS, smem, c.stream>>>((C2<double> *) dgrid, nrows, rpc, dims, plane0_global, c.d_k3tab, g_k3prm);
+            return KSN_OK;
+        };
+        const int rcl = rpc == 1 ? go(k3_scale_tma_kernel<double, true>) : go(k3_scale_tma_kernel<double, false>);
+        if (rcl) return rcl;
+        c.launches++;
+        KSN_CUDA(cudaGetLastError());
+        return KSN_OK;
+    }
     // one CTA per ~1024 modes: a single row for large grids, several short rows otherwise
     const int rows_per_cta = L >= K3_THREADS * U ? 1 : (K3_THREADS * U) / L;
     const int ctas = (nrows + rows_per_cta - 1) / rows_per_cta;

@@ -134,6 +134,9 @@ typedef struct ksn_delta_nu_args {
 /* out: nspecies*nk doubles, species-major.  n_evals (may be NULL): integrand evaluations. */
 int ksn_delta_nu_integrate(const ksn_delta_nu_args *args, double *out, unsigned long long *n_evals);
 
+/* integrand evaluations of the most recent ksn_delta_nu_integrate call (fslength table included) */
+unsigned long long ksn_last_k2_evals(void);
+
 /* Tabulate 1/(a H(a)) for the device integrand.  hub(a, user) is called on the host at
  * n uniform points in log a over [loga_lo, loga_hi]. */
 typedef double (*ksn_hubble_fn)(double a, void *user);

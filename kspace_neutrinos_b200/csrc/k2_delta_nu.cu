@@ -77,7 +77,16 @@ __device__ __forceinline__ double bessel_j0_d(double x)
 __device__ double Jfrac_high_d(double x, double qc, double nufrac_low, const double *__restrict__ enq)
 {
     double integ = 0;
-    const double j0 = bessel_j0_d(qc * x), cs = cos(qc * x), x2 = x * x;
+    const double arg = qc * x, x2 = x * x;
+    double sn, cs;
+    sincos(arg, &sn, &cs);
+    double j0;                                   // gsl_sf_bessel_j0: Taylor series below 0.5, sin(x)/x above
+    if (fabs(arg) < 0.5) {
+        const double y = arg * arg;
+        j0 = 1.0 + y * (-1.0 / 6.0 + y * (1.0 / 120.0 + y * (-1.0 / 5040.0 + y * (1.0 / 362880.0 + y * (-1.0 / 39916800.0 + y * (1.0 / 6227020800.0))))));
+    } else {
+        j0 = sn / arg;
+    }
     const double qj = qc * j0;
 #pragma unroll
     for (int n = 1; n < 20; n++) {
@@ -114,6 +123,14 @@ __device__ __forceinline__ double cspline_eval_d(const double *xa, const double 
     const double b_i = (dy / dx) - dx * (c_ip1 + 2.0 * c_i) / 3.0;
     const double d_i = (c_ip1 - c_i) / (3.0 * dx);
     return y_lo + delx * (b_i + delx * (c_i + delx * d_i));
+}
+
+// Polynomial coefficients of segment i exactly as gsl cspline_eval derives them at every call; done once instead.
+__device__ __forceinline__ void cspline_segment(const double *xa, const double *ya, const double *ca, int i, double &b, double &d)
+{
+    const double dx = xa[i + 1] - xa[i], dy = ya[i + 1] - ya[i];
+    b = (dy / dx) - dx * (ca[i + 1] + 2.0 * ca[i]) / 3.0;
+    d = (ca[i + 1] - ca[i]) / (3.0 * dx);
 }
 
 // LDL^T factors of the natural-spline system for knots xa[0..n): alpha[i], gamma[i], i < n-2
@@ -172,7 +189,8 @@ __device__ __forceinline__ double rescale_error_d(double err, double result_abs,
 {
     err = fabs(err);
     if (result_asc != 0 && err != 0) {
-        const double scale = pow((200 * err / result_asc), 1.5);
+        const double t = 200 * err / result_asc;
+        const double scale = t * sqrt(t);                 // pow(t, 1.5)
         err = scale < 1 ? result_asc * scale : result_asc;
     }
     if (result_abs > DBL_MIN / (50 * DBL_EPSILON)) {
@@ -354,7 +372,8 @@ __global__ void fs_knots_kernel(double loga0, double loga, int Nfs, double *__re
 constexpr int FS_WARM = 64;
 __global__ void __launch_bounds__(256)
 k2_prep_splines_kernel(const double *__restrict__ fsscales, const double *__restrict__ fslengths, int Nfs,
-                       double *__restrict__ fs_c, double *__restrict__ alpha, double *__restrict__ gamma,
+                       double *__restrict__ fs_c, double *__restrict__ fs_b, double *__restrict__ fs_d,
+                       double *__restrict__ alpha, double *__restrict__ gamma,
                        const double *__restrict__ scalefact, int Na, double *__restrict__ dt_alpha, double *__restrict__ dt_gamma)
 {
     if (blockIdx.x == 1) {
@@ -369,6 +388,7 @@ k2_prep_splines_kernel(const double *__restrict__ fsscales, const double *__rest
             spline_factor_seq(fsscales, Nfs, alpha, gamma);
             for (int i = 0; i < M; i++) fs_c[i + 1] = spline_rhs(fsscales, fslengths, i);
             spline_solve_seq(Nfs, alpha, gamma, fs_c);
+            for (int i = 0; i < Nfs - 1; i++) cspline_segment(fsscales, fslengths, fs_c, i, fs_b[i], fs_d[i]);
         }
         return;
     }
@@ -415,6 +435,8 @@ k2_prep_splines_kernel(const double *__restrict__ fsscales, const double *__rest
     }
     __syncthreads();
     for (int i = lo; i < hi; i++) z[i] = zkeep[i - lo];
+    __syncthreads();
+    for (int i = t; i < Nfs - 1; i += T) cspline_segment(fsscales, fslengths, fs_c, i, fs_b[i], fs_d[i]);
 }
 
 // ---------------------------------------------------------------- the per-k integral
@@ -424,7 +446,7 @@ struct K2Dev {
     double mnubykT[3], qc[3], relerr[3];
     int integrate[3];
     const double *scalefact, *delta_tot, *wavenum, *delta_nu_init;   // device
-    const double *fsscales, *fslengths, *fs_c, *dt_alpha, *dt_gamma; // device
+    const double *fsscales, *fslengths, *fs_c, *fs_b, *fs_d, *dt_alpha, *dt_gamma; // device
     double *out;
     int *status;
     unsigned long long *evals;
@@ -434,7 +456,7 @@ struct K2Dev {
 struct DeltaNuIntegrand {
     // get_delta_nu_int, delta_tot_table.c:492-500
     const K2Dev *P;
-    const double *sx, *sy, *sc;   // shared: knots, delta_tot row, spline c
+    const double *sx, *sy, *sc, *sb, *sd;   // shared: knots, delta_tot row, spline c and per-segment b, d
     double k, mnubykT, qc, fs_x0, fs_inv_dx;
     const double *enq;            // shared: (-1)^(n+1) exp(-n qc), n = 1..19
     __device__ double operator()(double logai) const
@@ -445,11 +467,13 @@ struct DeltaNuIntegrand {
         i = max(0, min(i, p.Nfs - 2));
         while (i > 0 && logai < __ldg(p.fsscales + i)) i--;
         while (i < p.Nfs - 2 && logai >= __ldg(p.fsscales + i + 1)) i++;
-        const double fsl = cspline_eval_d(p.fsscales, p.fslengths, p.fs_c, i, logai);
+        const double dfs = logai - __ldg(p.fsscales + i);
+        const double fsl = __ldg(p.fslengths + i) + dfs * (__ldg(p.fs_b + i) + dfs * (__ldg(p.fs_c + i) + dfs * __ldg(p.fs_d + i)));
         double dtot;
         if (p.Na > 2) {
             const int m = bsearch_d(sx, p.Na, logai);
-            dtot = cspline_eval_d(sx, sy, sc, m, logai);
+            const double dt = logai - sx[m];
+            dtot = sy[m] + dt * (sb[m] + dt * (sc[m] + dt * sd[m]));
         } else {
             dtot = sy[0] + (logai - sx[0]) / (sx[1] - sx[0]) * (sy[1] - sy[0]);
         }
@@ -458,12 +482,12 @@ struct DeltaNuIntegrand {
     }
 };
 
-__global__ void __launch_bounds__(K2_THREADS)
+__global__ void __launch_bounds__(K2_THREADS, 6)
 k2_delta_nu_kernel(const __grid_constant__ K2Dev p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ QagShared S;
-    double *sx = (double *) smem_raw, *sy = sx + p.Na, *sc = sy + p.Na;
+    double *sx = (double *) smem_raw, *sy = sx + p.Na, *sc = sy + p.Na, *sb = sc + p.Na, *sd = sb + p.Na;
     __shared__ double enq_s[19];
     const int ik = blockIdx.x, sp = blockIdx.y;
     if (threadIdx.x < 19) {
@@ -488,9 +512,11 @@ k2_delta_nu_kernel(const __grid_constant__ K2Dev p)
             __syncthreads();
             if (threadIdx.x == 0) spline_solve_seq(p.Na, p.dt_alpha, p.dt_gamma, sc);
             __syncthreads();
+            for (int i = threadIdx.x; i < p.Na - 1; i += blockDim.x) cspline_segment(sx, sy, sc, i, sb[i], sd[i]);
+            __syncthreads();
         }
         DeltaNuIntegrand f;
-        f.P = &p; f.sx = sx; f.sy = sy; f.sc = sc;
+        f.P = &p; f.sx = sx; f.sy = sy; f.sc = sc; f.sb = sb; f.sd = sd;
         f.k = k; f.mnubykT = mnubykT; f.qc = p.qc[sp]; f.enq = enq_s;
         f.fs_x0 = p.loga0;
         f.fs_inv_dx = (p.Nfs - 1.) / (p.loga - p.loga0);
@@ -522,6 +548,9 @@ struct Bump {
 }  // namespace ksn
 
 using namespace ksn;
+
+static unsigned long long g_last_evals = 0;
+extern "C" unsigned long long ksn_last_k2_evals(void) { return g_last_evals; }
 
 extern "C" int ksn_set_background(ksn_hubble_fn hub, void *user, double loga_lo, double loga_hi, int n)
 {
@@ -591,7 +620,7 @@ extern "C" int ksn_delta_nu_integrate(const ksn_delta_nu_args *A, double *out, u
 
     // one pinned staging block -> one device block
     const size_t n_in = (size_t) Na + (size_t) nk * A->namax + 2 * (size_t) nk;
-    const size_t dev_doubles = n_in + 3 * (size_t) Nfs + 2 * (size_t) Nfs + 2 * (size_t) Na + (size_t) ns * nk + 8;
+    const size_t dev_doubles = n_in + 3 * (size_t) Nfs + 4 * (size_t) Nfs + 2 * (size_t) Na + (size_t) ns * nk + 16;
     const size_t dev_bytes = dev_doubles * sizeof(double) + ((size_t) ns * nk + Nfs) * sizeof(int) + 256;
     rc = ensure_device_buffer((void **) &c.d_k2, &c.k2_cap, dev_bytes);
     if (rc) return rc;
@@ -609,6 +638,7 @@ extern "C" int ksn_delta_nu_integrate(const ksn_delta_nu_args *A, double *out, u
     double *d_in = bp.take<double>(n_in);
     double *d_fsscales = bp.take<double>(Nfs), *d_fslengths = bp.take<double>(Nfs), *d_fsc = bp.take<double>(Nfs);
     double *d_sa = bp.take<double>(Nfs), *d_sg = bp.take<double>(Nfs);
+    double *d_fsb = bp.take<double>(Nfs), *d_fsd = bp.take<double>(Nfs);
     double *d_dta = bp.take<double>(Na), *d_dtg = bp.take<double>(Na);
     double *d_out = bp.take<double>((size_t) ns * nk);
     unsigned long long *d_evals = bp.take<unsigned long long>(1);
@@ -626,7 +656,7 @@ extern "C" int ksn_delta_nu_integrate(const ksn_delta_nu_args *A, double *out, u
                                                                         d_fslengths, d_status + (size_t) ns * nk, d_evals);
     c.launches += 2;
     if (any_integral) {
-        k2_prep_splines_kernel<<<2, 256, 0, c.stream>>>(d_fsscales, d_fslengths, Nfs, d_fsc, d_sa, d_sg, d_in, Na, d_dta, d_dtg);
+        k2_prep_splines_kernel<<<2, 256, 0, c.stream>>>(d_fsscales, d_fslengths, Nfs, d_fsc, d_fsb, d_fsd, d_sa, d_sg, d_in, Na, d_dta, d_dtg);
         c.launches++;
     }
     K2Dev p;
@@ -639,9 +669,9 @@ extern "C" int ksn_delta_nu_integrate(const ksn_delta_nu_args *A, double *out, u
     }
     p.scalefact = d_in; p.delta_tot = d_in + Na; p.wavenum = d_in + Na + (size_t) nk * A->namax;
     p.delta_nu_init = p.wavenum + nk;
-    p.fsscales = d_fsscales; p.fslengths = d_fslengths; p.fs_c = d_fsc; p.dt_alpha = d_dta; p.dt_gamma = d_dtg;
+    p.fsscales = d_fsscales; p.fslengths = d_fslengths; p.fs_c = d_fsc; p.fs_b = d_fsb; p.fs_d = d_fsd; p.dt_alpha = d_dta; p.dt_gamma = d_dtg;
     p.out = d_out; p.status = d_status; p.evals = d_evals; p.bg = bg;
-    k2_delta_nu_kernel<<<dim3(nk, ns), K2_THREADS, 3 * (size_t) Na * sizeof(double), c.stream>>>(p);
+    k2_delta_nu_kernel<<<dim3(nk, ns), K2_THREADS, 5 * (size_t) Na * sizeof(double), c.stream>>>(p);
     c.launches++;
     KSN_CUDA(cudaGetLastError());
     double *h_out = h + n_in;
@@ -654,6 +684,7 @@ extern "C" int ksn_delta_nu_integrate(const ksn_delta_nu_args *A, double *out, u
     KSN_CUDA(cudaStreamSynchronize(c.stream));
     phase_collect();
     memcpy(out, h_out, sizeof(double) * ns * nk);
+    g_last_evals = *h_evals;
     if (n_evals) *n_evals = *h_evals;
     for (size_t i = 0; i < (size_t) ns * nk + Nfs; i++)
         if (h_status[i])

@@ -151,6 +151,16 @@ __device__ __forceinline__ void k1_group(const Cplx<real> *__restrict__ rowptr, 
     }
 }
 
+// Fast-path weight: the CIC deconvolution weight (iwx iwy iwz)^4 (powerspectrum.c:20-24,68) times the Hermitian
+// multiplicity factorises into a per-row scalar (iwx iwy)^4 and a per-z table m_z iwz^4 (m = 1 for kz = 0 and the
+// Nyquist plane, 2 otherwise): one multiply per mode; differs from the reference's rounding order by ~4e-16.
+template <typename real>
+__device__ __forceinline__ double pair_power(real re, real im, double w)
+{
+    const double a = (double) re, b = (double) im;
+    return fma(b, b, a * a) * w;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Fast path (power only): every lane owns TWO consecutive modes, fetched with one 256-bit load
 // (sm_100a LDG.256), so a warp step covers 64 modes with one segmented scan.  The two modes of a
@@ -211,10 +221,8 @@ __device__ __forceinline__ void pair_phaseA(Pair<real> (&v)[U], int q0, int npai
         const int k2a = c + z * z, k2b = k2a + 2 * z + 1;
         ba[u] = bin_of(k2a, binscale, thr_s);
         bb[u] = bin_of(k2b, binscale, thr_s);
-        Cplx<real> e0, e1;
-        e0.re = v[u].re0; e0.im = v[u].im0; e1.re = v[u].re1; e1.im = v[u].im1;
-        pa[u] = mode_power(e0, wxy, iw_s[z]);
-        const double pb = mode_power(e1, wxy, iw_s[z + 1]);
+        pa[u] = pair_power<real>(v[u].re0, v[u].im0, wxy * iw_s[z]);
+        const double pb = pair_power<real>(v[u].re1, v[u].im1, wxy * iw_s[z + 1]);
         if (MASKED && q0 + 32 * u >= npairs) { ba[u] = 0x7fffffff; bb[u] = 0x7fffffff; }
         x[u] = fma(pa[u], __hiloint2double(ba[u] == bb[u] ? 0x3ff00000 : 0, 0), pb);
     }
@@ -264,7 +272,7 @@ __device__ __forceinline__ void k1_single(const Cplx<real> *__restrict__ rowptr,
         const int k2 = c + z * z;
         if (k2 > 0) {
             const Cplx<real> e = ld_stream(rowptr + z);
-            mybins[bin_of(k2, binscale, thr_s)] += mode_power(e, wxy, iw_s[z]);
+            mybins[bin_of(k2, binscale, thr_s)] += pair_power<real>(e.re, e.im, wxy * iw_s[z]);
         }
     }
     __syncwarp();
@@ -285,9 +293,11 @@ k1_pair_kernel(const Cplx<real> *__restrict__ grid, int nrows, int N, int nrbins
     double *iw_s = (double *) smem_raw;                       // 2L: z table (with multiplicity) | plain table
     double *bins_s = iw_s + 2 * L;                            // nwarps * nrbins
     uint2 *thr_s = (uint2 *) (bins_s + (size_t) nwarps * nrbins);   // nrbins+1 pairs {thr[b], thr[b+1]}
-    const double root2_4 = sizeof(real) == 4 ? (double) 1.189207115002721f : 1.189207115002721;
-    for (int i = threadIdx.x; i < L; i += blockDim.x) iw_s[L + i] = iw[i];
-    for (int i = threadIdx.x; i < L; i += blockDim.x) iw_s[i] = (i == 0 || i == nyq) ? iw[i] : iw[i] * root2_4;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) iw_s[L + i] = iw[i];              // plain 1-D window: x/y factors
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {                                 // m_z * iwz^4
+        const double w2 = iw[i] * iw[i];
+        iw_s[i] = ((i == 0 || i == nyq) ? 1.0 : 2.0) * (w2 * w2);
+    }
     for (int i = threadIdx.x; i <= nrbins; i += blockDim.x)
         thr_s[i] = make_uint2(i < nrbins ? thr[i] : 0xffffffffu, i + 1 < nrbins ? thr[i + 1] : 0xffffffffu);
     for (int i = threadIdx.x; i < nwarps * nrbins; i += blockDim.x) bins_s[i] = 0.0;
@@ -307,7 +317,8 @@ k1_pair_kernel(const Cplx<real> *__restrict__ grid, int nrows, int N, int nrbins
         const int kj = j <= N / 2 ? j : j - N;
         R.c = ki * ki + kj * kj;
         const double a = iw_s[L + (ki < 0 ? -ki : ki)], b = iw_s[L + (kj < 0 ? -kj : kj)];
-        R.wxy = sizeof(real) == 4 ? (double) ((float) a * (float) b) : a * b;
+        const double t = a * b, t2 = t * t;
+        R.wxy = t2 * t2;                            // (iwx iwy)^4
         R.ptr = grid + (size_t) r * L;
         // pairs must start on a 2-element boundary of the slab: skip z=0 when the row starts odd
         R.zfirst = (int) ((((size_t) r * L) + base_odd) & 1);

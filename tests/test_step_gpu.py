@@ -64,3 +64,61 @@ def test_add_nu_power_matches_oracle_port(gpu):
             assert (m.dtot.ia, m.dtot.nk) == (ia, nk)
             np.testing.assert_allclose(dnu, np.array([m.dtot.delta_nu_last[i] for i in range(nk)]), rtol=tol)
             np.testing.assert_allclose(gg, cur, rtol=tol, atol=0)
+
+
+def test_config1_256_cube_transfer_at_a_0p1(gpu):
+    """BASELINE.json configs[1]: PMGRID=256^3 double, 3 x 0.1 eV, CAMB ics_transfer_0.1.dat (TimeTransfer = 0.1), against the
+    oracle port on the same bytes: three PM steps (init, kept row, dropped row)."""
+    import os
+    o = refs.orc()
+    n = 256
+    tfile = os.path.join(refs.GOLDEN, "camb_ics_transfer_0.1.dat")
+    g = refs.random_grid(n, seed=256)
+    times = (0.1, 0.12, 0.1205)
+    got = _run(gpu, "add_nu_power_to_rhogrid_f64", g, times, True, masses=(0.1, 0.1, 0.1), time_transfer=0.1, transfer=tfile)
+    m = refs.orc_module(n, masses=(0.1, 0.1, 0.1), time_transfer=0.1, transfer=tfile)
+    cur = g.copy()
+    for (ia, nk, gg, dnu), a in zip(got, times):
+        assert o.orc_add_nu_power_to_rhogrid(C.byref(m), a, refs.BOX, cur.ctypes.data_as(C.c_void_p), 1, n, 0, n) == 0
+        assert (m.dtot.ia, m.dtot.nk) == (ia, nk)
+        np.testing.assert_allclose(dnu, np.array([m.dtot.delta_nu_last[i] for i in range(nk)]), rtol=1e-10)
+        np.testing.assert_allclose(gg, cur, rtol=1e-10, atol=0)
+
+
+def test_full_size_properties_1024(gpu):
+    """At a BASELINE size the CPU oracle cannot sweep in test time (1024^3, 8.6 GB): properties that do not need it.
+    One whole step on a device-resident synthetic grid: mode counts add up to N^3-1; the k=0 element is untouched;
+    every other mode is scaled by a factor in (1, 1 + prefac] that depends on |k| only (checked on Hermitian-equivalent
+    and permuted wave vectors)."""
+    from kspace_neutrinos_b200 import host
+    n = 1024
+    slab = host.Slab(0, n)
+    grid = host.DeviceGrid(n, slab)
+    grid.fill_synthetic(seed=7, slope=-1.0)
+    sim = host.KspaceNeutrinos(host.Cosmology(transfer_file=host.default_transfer_file(), mnu=(0.1, 0.1, 0.1)), n)
+    L = n // 2 + 1
+
+    def rows(i, js):      # a few rows of plane i, copied back
+        out = {}
+        for j in js:
+            buf = np.empty((L, 2))
+            off = ((i * n + j) * L) * 16
+            capi.check(gpu.ksn_memcpy_d2h(buf.ctypes.data_as(C.c_void_p), C.c_void_p(grid.ptr.value + off), buf.nbytes))
+            out[j] = buf
+        return out
+    probes = [(0, (0, 3, n - 3)), (3, (0,)), (5, (7,)), (7, (5,)), (n - 5, (n - 7,))]
+    before = {i: rows(i, js) for i, js in probes}
+    sim.add_nu_power_to_rhogrid(0.01, grid.ptr, slab)
+    sim.add_nu_power_to_rhogrid(0.02, grid.ptr, slab)
+    after = {i: rows(i, js) for i, js in probes}
+    grid.free()
+    assert sim.state.nk > 400 and sim.state.ia == 2
+    f = {(i, j): after[i][j][:, 0] / before[i][j][:, 0] for i, js in probes for j in js}
+    assert f[(0, 0)][0] == 1.0                                      # F(0,0,0) untouched
+    for key, v in f.items():
+        vv = v[1:] if key == (0, 0) else v
+        assert np.all(vv > 1.0) and np.all(vv < 1.2)
+    np.testing.assert_allclose(f[(0, 3)], f[(0, n - 3)], rtol=1e-13)   # (0, 3, z) and (0, -3, z): same |k|
+    np.testing.assert_allclose(f[(0, 3)], f[(3, 0)], rtol=1e-13)       # (0, 3, z) and (3, 0, z)
+    np.testing.assert_allclose(f[(5, 7)], f[(7, 5)], rtol=1e-13)       # (5, 7, z) and (7, 5, z)
+    np.testing.assert_allclose(f[(5, 7)], f[(n - 5, n - 7)], rtol=1e-13)

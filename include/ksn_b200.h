@@ -136,6 +136,8 @@ int ksn_delta_nu_integrate(const ksn_delta_nu_args *args, double *out, unsigned 
 
 /* integrand evaluations of the most recent ksn_delta_nu_integrate call (fslength table included) */
 unsigned long long ksn_last_k2_evals(void);
+/* largest number of 61-point rule applications any single k bin needed in that call (the kernel's critical path) */
+unsigned ksn_last_k2_max_passes(void);
 
 /* Tabulate 1/(a H(a)) for the device integrand.  hub(a, user) is called on the host at
  * n uniform points in log a over [loga_lo, loga_hi]. */

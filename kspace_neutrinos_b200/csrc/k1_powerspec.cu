@@ -278,13 +278,12 @@ __device__ __forceinline__ void k1_single(const Cplx<real> *__restrict__ rowptr,
     __syncwarp();
 }
 
-template <typename real>
-__global__ void __launch_bounds__(K1_MAX_WARPS * 32, 1)
+template <typename real, int MAXW, int U>
+__global__ void __launch_bounds__(MAXW * 32, 1)
 k1_pair_kernel(const Cplx<real> *__restrict__ grid, int nrows, int N, int nrbins, long long plane0,
                float binscale, const unsigned *__restrict__ thr, const double *__restrict__ iw,
                double *__restrict__ partial, int accumulate)
 {
-    constexpr int U = 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int L = N / 2 + 1;
     const int nyq = N / 2;
@@ -479,7 +478,10 @@ static int k1_launch_t(const void *dgrid, int dims, int nrbins, long long plane0
     constexpr int NV = FULL ? 3 : 1;
     if (nplanes * dims > 0x7fffffffLL) return set_error(KSN_EINVAL, "K1: %lld rows in one slab", nplanes * dims);
     const int nrows = (int) (nplanes * dims);
-    int nwarps = K1_MAX_WARPS;
+    // experiment knob: KSN_K1_CFG = "<max warps><unroll>" in {164, 204, 242, 244, 162}
+    const char *cfg = FULL ? nullptr : getenv("KSN_K1_CFG");
+    const int cfgv = cfg ? atoi(cfg) : 164;
+    int nwarps = FULL ? K1_MAX_WARPS : cfgv / 10;
     while (nwarps > 1 && k1_smem_bytes(dims, nrbins, nwarps, NV) > c.smem_optin) nwarps--;
     const size_t smem = k1_smem_bytes(dims, nrbins, nwarps, NV);
     if (smem > c.smem_optin)
@@ -498,7 +500,11 @@ static int k1_launch_t(const void *dgrid, int dims, int nrbins, long long plane0
         return KSN_OK;
     };
     if (FULL || getenv("KSN_K1_NOPAIR")) rc = launch(k1_bin_kernel<real, FULL>);
-    else rc = launch(k1_pair_kernel<real>);
+    else if (cfgv == 204) rc = launch(k1_pair_kernel<real, 20, 4>);
+    else if (cfgv == 242) rc = launch(k1_pair_kernel<real, 24, 2>);
+    else if (cfgv == 244) rc = launch(k1_pair_kernel<real, 24, 4>);
+    else if (cfgv == 162) rc = launch(k1_pair_kernel<real, 16, 2>);
+    else rc = launch(k1_pair_kernel<real, 16, 4>);
     if (rc) return rc;
     *ctas_out = ctas;
     *stride_out = NV * nrbins;

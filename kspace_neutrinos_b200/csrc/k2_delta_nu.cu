@@ -526,7 +526,7 @@ k2_delta_nu_kernel(const __grid_constant__ K2Dev p)
     }
     if (threadIdx.x == 0) {
         p.out[(size_t) sp * p.nk + ik] = dnu;
-        p.status[(size_t) sp * p.nk + ik] = st;
+        p.status[(size_t) sp * p.nk + ik] = st | ((int) passes << 8);     // low byte: GSL-style status, rest: 61-point passes
         if (p.evals && passes) atomicAdd(p.evals, 61ull * passes);
     }
 }
@@ -550,6 +550,8 @@ struct Bump {
 using namespace ksn;
 
 static unsigned long long g_last_evals = 0;
+static unsigned g_max_passes = 0;
+extern "C" unsigned ksn_last_k2_max_passes(void) { return g_max_passes; }
 extern "C" unsigned long long ksn_last_k2_evals(void) { return g_last_evals; }
 
 extern "C" int ksn_set_background(ksn_hubble_fn hub, void *user, double loga_lo, double loga_hi, int n)
@@ -686,9 +688,13 @@ extern "C" int ksn_delta_nu_integrate(const ksn_delta_nu_args *A, double *out, u
     memcpy(out, h_out, sizeof(double) * ns * nk);
     g_last_evals = *h_evals;
     if (n_evals) *n_evals = *h_evals;
-    for (size_t i = 0; i < (size_t) ns * nk + Nfs; i++)
-        if (h_status[i])
+    g_max_passes = 0;
+    for (size_t i = 0; i < (size_t) ns * nk + Nfs; i++) {
+        const int st = i < (size_t) ns * nk ? (h_status[i] & 0xff) : h_status[i];
+        if (i < (size_t) ns * nk && (h_status[i] >> 8) > (int) g_max_passes) g_max_passes = (unsigned) (h_status[i] >> 8);
+        if (st)
             return set_error(KSN_EQUAD, "quadrature %zu (%s) failed with GSL-style code %d at a=%g",
-                             i, i < (size_t) ns * nk ? "delta_nu" : "fslength", h_status[i], A->a);
+                             i, i < (size_t) ns * nk ? "delta_nu" : "fslength", st, A->a);
+    }
     return KSN_OK;
 }

@@ -257,12 +257,16 @@ int k3_upload_table(int dims, double boxsize, const double *logkk, const double 
         return set_error(KSN_EINVAL, "K3: table knots closer than %g in log2(k^2) are not supported", (hi - lo) / K3_MAX_CELLS * 1.05);
     const double scale = cells / (hi - lo);
     unsigned short *cell = (unsigned short *) (seg + nbins + 1);
-    int s = 0;
-    for (int k = 0; k < cells; k++) {
-        // last knot at or below the lower edge of cell k, minus a guard for the float log2 on the device
-        const double edge = exp2(lo + (k - 0.02) / scale);
-        while (s + 1 < nbins && seg[s + 1].K2 <= edge) s++;
-        cell[k] = (unsigned short) s;
+    // cell[k] = last knot at or below the lower edge of cell k, minus a guard (0.02 cell) for the float log2 on the
+    // device.  One log2 per knot: knot i starts to count from cell ceil((log2 K2_i - lo) * scale + 0.02).
+    {
+        int k = 0;
+        for (int i = 1; i < nbins; i++) {
+            int first = (int) ceil((log2(seg[i].K2) - lo) * scale + 0.02);
+            if (first > cells) first = cells;
+            for (; k < first; k++) cell[k] = (unsigned short) (i - 1);
+        }
+        for (; k < cells; k++) cell[k] = (unsigned short) (nbins - 1);
     }
     g_k3prm.n = nbins;
     g_k3prm.cells = cells;

@@ -308,7 +308,7 @@ def ours(args):
             traffic = json.load(f).get(f"k3_{n}")
     except (OSError, ValueError):
         pass
-    roofline = {"bound": "hbm", "kernel": "k3_scale_kernel<double> (read-modify-write, 32 B per stored mode)",
+    roofline = {"bound": "hbm", "kernel": "k3_scale_tma_kernel<double> (read-modify-write, 32 B per stored mode)",
                 "achieved": 32.0 * local_modes / (k3_launch_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                 "frac": 32.0 * local_modes / (k3_launch_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
                 "k1": {"kernel": "k1_pair_kernel<double> (read-only, 16 B per stored mode)",

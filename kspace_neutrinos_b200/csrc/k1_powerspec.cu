@@ -447,15 +447,17 @@ template <typename real>
 __global__ void k1_final_kernel(const double *__restrict__ partial, int ctas, int nv, int nrbins,
                                 const Cplx<real> *origin, double *__restrict__ red)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per output value: lane l adds the partials of CTAs l, l+32, ... in that order, then a fixed xor tree
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i < nv * nrbins) {
         double s = 0.0;
-#pragma unroll 8
-        for (int c = 0; c < ctas; c++) s += partial[(size_t) c * nv * nrbins + i];   // fixed CTA order
+        for (int c = lane; c < ctas; c += 32) s += partial[(size_t) c * nv * nrbins + i];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
         const int which = i / nrbins, b = i - which * nrbins;
-        red[which == 0 ? b : which * nrbins + 1 + b] = s;
+        if (lane == 0) red[which == 0 ? b : which * nrbins + 1 + b] = s;
     }
-    if (i == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         double m2 = 0.0;
         if (origin) {   // powerspectrum.c:45-47: only the rank holding plane 0
             const double re = (double) origin->re, im = (double) origin->im;
@@ -526,7 +528,7 @@ int k1_finish(int real_bytes, int dims, int nrbins, bool full, int ctas, int str
     (void) dims; (void) stride;
     Ctx &c = ctx();
     const int nv = full ? 3 : 1;
-    const int threads = 128, blocks = (nv * nrbins + threads - 1) / threads;
+    const int threads = 256, blocks = (nv * nrbins * 32 + threads - 1) / threads;
     if (real_bytes == 8)
         k1_final_kernel<double><<<blocks, threads, 0, c.stream>>>(c.d_partial, ctas, nv, nrbins, (const Cplx<double> *) origin_elem, c.d_red);
     else

@@ -133,3 +133,22 @@ def test_linearity_large(gpu):
     # every mode except (0,0,0) was multiplied by 1.5 -> P grows by 2.25 relative to the unchanged |F(0)|^2
     np.testing.assert_allclose(p2[:n1], 2.25 * p1[:n1], rtol=1e-12)
     np.testing.assert_array_equal(k1, k2)
+
+
+def test_odd_aligned_device_pointer(gpu):
+    """A device slab that starts on an odd 16-byte boundary (the 256-bit pair loads must re-align per row)."""
+    from kspace_neutrinos_b200 import capi
+    n, nrbins = 64, 32
+    g = refs.random_grid(n, seed=21)
+    ptr = C.c_void_p()
+    capi.check(gpu.ksn_device_malloc(C.byref(ptr), g.nbytes + 64))
+    shifted = C.c_void_p(ptr.value + 16)
+    capi.check(gpu.ksn_memcpy_h2d(shifted, g.ctypes.data_as(C.c_void_p), g.nbytes))
+    a = _sums(gpu, g, nrbins, 0, n, pointer=shifted)
+    a = _sums(gpu, g, nrbins, 0, n, pointer=shifted)         # second call: the pair kernel
+    d = refs.DeviceBuffer(gpu, g)
+    b = _sums(gpu, g, nrbins, 0, n, pointer=d.ptr)
+    d.free()
+    gpu.ksn_device_free(ptr)
+    assert np.array_equal(a[2], b[2]) and a[3] == b[3]
+    np.testing.assert_allclose(a[0], b[0], rtol=1e-13)

@@ -122,3 +122,77 @@ def test_full_size_properties_1024(gpu):
     np.testing.assert_allclose(f[(0, 3)], f[(3, 0)], rtol=1e-13)       # (0, 3, z) and (3, 0, z)
     np.testing.assert_allclose(f[(5, 7)], f[(7, 5)], rtol=1e-13)       # (5, 7, z) and (7, 5, z)
     np.testing.assert_allclose(f[(5, 7)], f[(n - 5, n - 7)], rtol=1e-13)
+
+
+def test_compute_neutrino_power_from_cdm_matches_reference(gpu):
+    """The MP-Gadget style entry (interface_common.c:106-123): host supplies P(k); empty bins are dropped; only K2 runs
+    on the GPU.  Against the reference sources where available, else against the oracle port's integrator."""
+    n = 64
+    kk, delta_nu, delta_tot = refs.load_golden_state()
+    nk_in = n // 2
+    keff = np.ascontiguousarray(kk[::9][:nk_in])
+    rng = np.random.default_rng(1)
+    P = (1e5 * (keff / keff[0]) ** -0.7) ** 2
+    nmodes = np.ones(nk_in, dtype=np.int64)
+    nmodes[[3, 17]] = 0                                        # two empty bins
+    nm = nmodes.ctypes.data_as(C.POINTER(C.c_long))
+
+    def run(libh):
+        refs.init_module(libh, n, masses=(0.15, 0.15, 0.15))
+        out = []
+        for a in (0.01, 0.03, 0.0305, 0.2):
+            d = libh.compute_neutrino_power_from_cdm(a, refs.dptr(keff), refs.dptr(P), nm, nk_in, 0)
+            out.append((d.nbins, d.norm, np.array([d.logkk[i] for i in range(d.nbins)]), np.array([d.delta_ratio[i] for i in range(d.nbins)])))
+            libh.free_d_pow(C.byref(d))
+        return out
+    got = run(gpu)
+    ref = refs.ref_lib(True)
+    if ref is not None:
+        want = run(ref)
+    else:
+        o = refs.orc()
+        m = refs.orc_module(n, masses=(0.15, 0.15, 0.15))
+        keep = nmodes > 0
+        kz, dz = np.ascontiguousarray(keff[keep]), np.ascontiguousarray(np.sqrt(P[keep]))
+        want = []
+        for a in (0.01, 0.03, 0.0305, 0.2):
+            dn = np.zeros(len(kz))
+            assert o.orc_get_delta_nu_update(C.byref(m.dtot), a, len(kz), refs.dptr(kz), refs.dptr(dz), refs.dptr(dn), m.t_logk, m.t_tnu, m.nt) == 0
+            nop = o.orc_omega_nu_nopart(C.byref(m.cosmo), a)
+            hyb = o.orc_omega_nu(C.byref(m.cosmo), a) - nop
+            want.append((len(kz), nop / (m.dtot.Omeganonu / a ** 3 + hyb), np.log(kz), dn / dz))
+    for (nb_g, norm_g, lk_g, r_g), (nb_w, norm_w, lk_w, r_w) in zip(got, want):
+        assert nb_g == nb_w == nk_in - 2
+        assert norm_g == pytest.approx(norm_w, rel=1e-12)
+        np.testing.assert_allclose(lk_g, lk_w, rtol=1e-14)
+        np.testing.assert_allclose(r_g, r_w, rtol=1e-10)
+
+
+def test_total_power_path_and_output_files(gpu, tmp_path):
+    """compute_total_power_spectrum + save_total_power (interface_gadget.c:114-144,196-224) and save_neutrino_power:
+    file contents against the oracle's numbers through the same '%g' formatting."""
+    o = refs.orc()
+    n = 32
+    g = refs.random_grid(n, seed=8)
+    refs.init_module(gpu, n, masses=(0.15, 0.15, 0.15))
+    d = refs.DeviceBuffer(gpu, g)
+    gpu.add_nu_power_to_rhogrid_f64(0.01, refs.BOX, d.ptr, n, 0, n, 0)
+    assert gpu.save_neutrino_power(0.01, 7, str(tmp_path).encode()) == 0
+    lines = open(tmp_path / "powerspec_nu_007.txt").read().split("\n")
+    assert lines[0] == "# k P_nu(k)" and lines[1] == "# a = 0.01"
+    dt = capi.global_delta_tot_table()
+    assert lines[2] == f"# nbins = {dt.nk}"
+    k0, p0 = lines[3].split()
+    assert k0 == "%g" % dt.wavenum[0] and p0 == "%g" % (dt.delta_nu_last[0] ** 2)
+    # total power of the (already corrected) grid, no-neutrino path
+    gpu.compute_total_power_spectrum_f64(0.01, refs.BOX, d.ptr, n, 0, n, 0)
+    cur = d.download(g)
+    d.free()
+    assert gpu.save_total_power(0.01, 3, str(tmp_path).encode()) == 0
+    rows = [l.split() for l in open(tmp_path / "powerspec_tot_003.txt").read().strip().split("\n")[3:]]
+    nb = n // 2
+    p, k = np.zeros(nb), np.zeros(nb)
+    c = np.zeros(nb, dtype=np.int64)
+    nret = o.orc_total_powerspectrum(n, cur.ctypes.data_as(C.c_void_p), 1, nb, 0, n, refs.dptr(p), c.ctypes.data_as(capi.c_longlong_p), refs.dptr(k))
+    assert len(rows) == nret
+    np.testing.assert_allclose([float(r[0]) for r in rows], k[:nret] * 2 * np.pi / refs.BOX, rtol=6e-6)    # %g keeps 6 significant digits

@@ -143,6 +143,9 @@ unsigned ksn_last_k2_max_passes(void);
  * n uniform points in log a over [loga_lo, loga_hi]. */
 typedef double (*ksn_hubble_fn)(double a, void *user);
 int ksn_set_background(ksn_hubble_fn hub, void *user, double loga_lo, double loga_hi, int n);
+/* how the last table came out: cells whose 4-point interpolant missed the host function (kinks in H(a), e.g. the
+ * spline/series switch of Omega_nu, omega_nu_single.c:180-199) and the refined patches that cover them */
+int ksn_background_info(int *npatch, int *flagged_cells);
 /* device fslength (same table), for tests: light * int_{logai}^{logaf} dloga /(a^2 H) */
 int ksn_fslength_device(const double *logai, int n, double logaf, double light, double *out);
 

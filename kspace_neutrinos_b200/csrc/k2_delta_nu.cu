@@ -35,23 +35,48 @@ constexpr int QAG_LIMIT = 200;      // GSL_VAL, kspace_neutrino_const.h:19
 
 enum { Q_OK = 0, Q_EROUND = 18, Q_ESING = 21, Q_EMAXITER = 11, Q_EFAILED = 5 };
 
-struct BgTable {
-    const double *g;   // 1/(a H(a)) at x_i = lo + i*h
-    int n;
-    double lo, h, inv_h;
+// A host Hubble rate is not smooth everywhere: the reference's own Omega_nu(a) switches from a spline table to a series at
+// a = 100 kT_nu/m_nu (omega_nu_single.c:180-199), which leaves a kink in H(a).  A 4-point stencil that straddles a kink is
+// only first-order accurate there (measured: 1e-10 pointwise, enough to flip adaptive-quadrature decisions against the
+// CPU path).  ksn_set_background() therefore checks every cell of the uniform table against the host function and covers
+// the cells that fail with PATCHES: sub-tables BG_SUB times finer, searched first.
+constexpr int BG_MAX_PATCH = 4;
+constexpr int BG_SUB = 4096;            // sub-cells per coarse cell inside a patch
+constexpr int BG_MAX_PATCH_CELLS = 48;  // coarse cells covered by all patches together
+
+struct BgPatch {
+    double lo, hi;     // covers lo <= x < hi
+    double x0, inv_h;  // sub-node j sits at x0 + j / inv_h; x0 = lo - one sub-cell
+    int off, n;        // first sub-node in g[], count
 };
 
-__device__ __forceinline__ double bg_eval(const BgTable &t, double x)
+struct BgTable {
+    const double *g;   // 1/(a H(a)) at x_i = lo + i*h, followed by the patch sub-tables
+    int n;
+    double lo, h, inv_h;
+    int npatch;
+    BgPatch patch[BG_MAX_PATCH];
+};
+
+__device__ __forceinline__ double bg_lagrange(const double *__restrict__ g, int n, double s)
 {
-    const double s = (x - t.lo) * t.inv_h;
     int i = (int) floor(s);
-    i = max(1, min(i, t.n - 3));
+    i = max(1, min(i, n - 3));
     const double u = s - i, um1 = u - 1.0, up1 = u + 1.0, um2 = u - 2.0;
     const double w0 = -u * um1 * um2 * (1.0 / 6.0);
     const double w1 = up1 * um1 * um2 * 0.5;
     const double w2 = -up1 * u * um2 * 0.5;
     const double w3 = up1 * u * um1 * (1.0 / 6.0);
-    return w0 * __ldg(t.g + i - 1) + w1 * __ldg(t.g + i) + w2 * __ldg(t.g + i + 1) + w3 * __ldg(t.g + i + 2);
+    return w0 * __ldg(g + i - 1) + w1 * __ldg(g + i) + w2 * __ldg(g + i + 1) + w3 * __ldg(g + i + 2);
+}
+
+__device__ __forceinline__ double bg_eval(const BgTable &t, double x)
+{
+#pragma unroll
+    for (int p = 0; p < BG_MAX_PATCH; p++)
+        if (p < t.npatch && x >= t.patch[p].lo && x < t.patch[p].hi)
+            return bg_lagrange(t.g + t.patch[p].off, t.patch[p].n, (x - t.patch[p].x0) * t.patch[p].inv_h);
+    return bg_lagrange(t.g, t.n, (x - t.lo) * t.inv_h);
 }
 
 // ---------------------------------------------------------------- specialJ (delta_tot_table.c:417-463)
@@ -531,11 +556,16 @@ k2_delta_nu_kernel(const __grid_constant__ K2Dev p)
     }
 }
 
+static BgPatch g_bg_patch[BG_MAX_PATCH];
+static int g_bg_npatch = 0, g_bg_flagged = 0;
+
 static BgTable bg_table()
 {
     Ctx &c = ctx();
     BgTable t;
     t.g = c.d_bg; t.n = c.bg_n; t.lo = c.bg_lo; t.h = c.bg_h; t.inv_h = 1.0 / c.bg_h;
+    t.npatch = g_bg_npatch;
+    for (int p = 0; p < BG_MAX_PATCH; p++) t.patch[p] = g_bg_patch[p];
     return t;
 }
 
@@ -554,6 +584,22 @@ static unsigned g_max_passes = 0;
 extern "C" unsigned ksn_last_k2_max_passes(void) { return g_max_passes; }
 extern "C" unsigned long long ksn_last_k2_evals(void) { return g_last_evals; }
 
+// host mirror of bg_lagrange (same formula), used to validate the table against the host function
+static double bg_lagrange_host(const double *g, int n, double s)
+{
+    int i = (int) floor(s);
+    i = i < 1 ? 1 : (i > n - 3 ? n - 3 : i);
+    const double u = s - i, um1 = u - 1.0, up1 = u + 1.0, um2 = u - 2.0;
+    return -u * um1 * um2 * (1.0 / 6.0) * g[i - 1] + up1 * um1 * um2 * 0.5 * g[i] - up1 * u * um2 * 0.5 * g[i + 1] + up1 * u * um1 * (1.0 / 6.0) * g[i + 2];
+}
+
+extern "C" int ksn_background_info(int *npatch, int *flagged_cells)
+{
+    if (npatch) *npatch = g_bg_npatch;
+    if (flagged_cells) *flagged_cells = g_bg_flagged;
+    return KSN_OK;
+}
+
 extern "C" int ksn_set_background(ksn_hubble_fn hub, void *user, double loga_lo, double loga_hi, int n)
 {
     int rc = ensure_init();
@@ -561,14 +607,55 @@ extern "C" int ksn_set_background(ksn_hubble_fn hub, void *user, double loga_lo,
     if (!hub || !(loga_hi > loga_lo) || n < 16) return set_error(KSN_EINVAL, "ksn_set_background: bad arguments");
     Ctx &c = ctx();
     const double h = (loga_hi - loga_lo) / (n - 1);
-    double *tab = (double *) malloc(sizeof(double) * n);
-    for (int i = 0; i < n; i++) {
-        const double a = exp(loga_lo + i * h);
-        tab[i] = 1.0 / (a * hub(a, user));
+    auto sample = [&](double x) { const double a = exp(x); return 1.0 / (a * hub(a, user)); };
+    const size_t cap = (size_t) n + (size_t) BG_MAX_PATCH_CELLS * BG_SUB + 4 * BG_MAX_PATCH;
+    double *tab = (double *) malloc(sizeof(double) * cap);
+    unsigned char *bad = (unsigned char *) calloc(n, 1);
+    if (!tab || !bad) { free(tab); free(bad); return set_error(KSN_ENOMEM, "ksn_set_background: out of host memory"); }
+    for (int i = 0; i < n; i++) tab[i] = sample(loga_lo + i * h);
+    // validate every cell whose stencil is centred (the integrand never leaves [lo+2h, hi-2h]) at its midpoint
+    const bool patches_on = !getenv("KSN_BG_NOPATCH");
+    int flagged = 0;
+    for (int i = 1; patches_on && i < n - 2; i++) {
+        const double want = sample(loga_lo + (i + 0.5) * h), got = bg_lagrange_host(tab, n, i + 0.5);
+        // 1e-13: above the ~1e-14 the interpolant loses at the knots of a cubic-spline Omega_nu table (third-derivative
+        // jumps), far below the ~6e-9 it loses at a slope discontinuity
+        if (!(fabs(got - want) <= 1e-13 * fabs(want))) { bad[i] = 1; flagged++; }
     }
+    // cells next to a failing one share its stencil nodes: cover them too, then merge into ranges
+    int npatch = 0, cells = 0;
+    size_t used = n;
+    bool overflow = false;
+    if (flagged) {
+        unsigned char *cover = (unsigned char *) calloc(n, 1);
+        for (int i = 1; i < n - 2; i++)
+            if (bad[i]) for (int d = -2; d <= 2; d++) if (i + d >= 1 && i + d < n - 2) cover[i + d] = 1;
+        for (int i = 1; i < n - 2 && !overflow; i++) {
+            if (!cover[i]) continue;
+            int j = i;
+            while (j + 1 < n - 2 && cover[j + 1]) j++;
+            const int nc = j - i + 1;
+            if (npatch == BG_MAX_PATCH || cells + nc > BG_MAX_PATCH_CELLS) { overflow = true; break; }
+            BgPatch &P = g_bg_patch[npatch];
+            const double hs = h / BG_SUB;
+            P.lo = loga_lo + i * h; P.hi = loga_lo + (j + 1) * h;
+            P.x0 = P.lo - hs; P.inv_h = 1.0 / hs;
+            P.off = (int) used; P.n = nc * BG_SUB + 3;
+            for (int k = 0; k < P.n; k++) tab[used + k] = sample(P.x0 + k * hs);
+            used += P.n;
+            cells += nc;
+            npatch++;
+            i = j;
+        }
+        free(cover);
+    }
+    free(bad);
+    if (overflow) { npatch = 0; used = n; }   // a host function that is rough everywhere: plain table (first-order near its kinks)
+    g_bg_npatch = npatch;
+    g_bg_flagged = flagged;
     if (c.d_bg) { cudaFree(c.d_bg); c.d_bg = nullptr; }
-    cudaError_t e = cudaMalloc((void **) &c.d_bg, sizeof(double) * n);
-    if (e == cudaSuccess) e = cudaMemcpy(c.d_bg, tab, sizeof(double) * n, cudaMemcpyHostToDevice);
+    cudaError_t e = cudaMalloc((void **) &c.d_bg, sizeof(double) * used);
+    if (e == cudaSuccess) e = cudaMemcpy(c.d_bg, tab, sizeof(double) * used, cudaMemcpyHostToDevice);
     free(tab);
     KSN_CUDA(e);
     c.bg_n = n; c.bg_lo = loga_lo; c.bg_hi = loga_hi; c.bg_h = h;

@@ -12,6 +12,7 @@
  * GSL objects of the reference do not exist here. */
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -282,7 +283,9 @@ void ksn_ensure_background(double a_lo, double a_hi)
     /* margin of a few table cells on both sides for the 4-point stencil */
     const double lo = fmin(a_lo, bgc.valid ? bgc.a_lo : a_lo), hi = fmax(a_hi, bgc.valid ? bgc.a_hi : a_hi);
     const double xlo = log(lo) - 0.01, xhi = log(hi) + 0.01;
-    const int rc = ksn_set_background(hubble_cb, NULL, xlo, xhi, 16384);
+    const char *env = getenv("KSN_BG_POINTS");                  /* experiment knob: table resolution */
+    const int npts = env && atoi(env) >= 64 ? atoi(env) : 16384;
+    const int rc = ksn_set_background(hubble_cb, NULL, xlo, xhi, npts);
     if (rc) ksn_fatal_device(rc, "ksn_set_background");
     bgc.valid = 1;
     bgc.a_lo = lo;

@@ -201,6 +201,7 @@ def golden_delta_cdm(libh, om, delta_nu, delta_tot):
 
 def set_background(libh, om):
     """Install the flat-LCDM + neutrino + photon Hubble rate of the reference's tests on either library."""
+    _cache[("background", id(libh))] = om      # the library keeps a POINTER to it: it must outlive the caller's locals
     if hasattr(libh, "ksn_ref_set_background"):
         libh.ksn_ref_set_background(C.byref(om), OMEGA0, UNIT_TIME)
     else:

@@ -40,6 +40,32 @@ def test_fslength_device_matches_host_and_kat(gpu, state):
     gpu.ksn_invalidate_background()
 
 
+@pytest.mark.parametrize("masses,nkinks", [((0.15, 0.15, 0.15), 1), ((0.2, 0.1, 0.3), 3)])
+def test_background_table_patches_the_kinks_of_hubble(gpu, masses, nkinks):
+    """H(a) has a slope discontinuity where Omega_nu switches from its spline table to the non-relativistic series
+    (omega_nu_single.c:180-199, a = 100 kT/m per distinct mass).  The device table must find each one, cover it with a
+    refined patch, and then reproduce the host's fslength ACROSS the kink to rounding (a plain 4-point table is off by
+    ~1e-11 there, which is what flipped adaptive-quadrature decisions against the CPU path in long runs)."""
+    om = refs.make_omnu(gpu, masses)
+    refs.set_background(gpu, om)
+    hub = capi.HUBBLE_FN(lambda a, _u: gpu.hubble_function(a))
+    capi.check(gpu.ksn_set_background(hub, None, math.log(0.01) - 0.01, 0.01, 16384))
+    npatch, flagged = C.c_int(), C.c_int()
+    capi.check(gpu.ksn_background_info(C.byref(npatch), C.byref(flagged)))
+    assert npatch.value == nkinks and flagged.value == 3 * nkinks       # a kink spoils the three cells whose stencil straddles it
+    kT = 8.61734e-5 * ((4 / 11.) ** (1 / 3.) * 1.00328) * refs.T_CMB0
+    worst = 0.0
+    for m in set(masses):
+        a_sw = 100 * kT / m
+        lo = np.array([math.log(a_sw) - d for d in (0.3, 0.02, 1e-3, 1e-5)])
+        out = np.zeros(len(lo))
+        capi.check(gpu.ksn_fslength_device(refs.dptr(lo), len(lo), math.log(a_sw) + 0.01, 299792., refs.dptr(out)))
+        for i in range(len(lo)):
+            worst = max(worst, abs(out[i] / gpu.fslength(lo[i], math.log(a_sw) + 0.01, 299792.) - 1))
+    assert worst < 2e-14, worst
+    gpu.ksn_invalidate_background()
+
+
 def _resume(libh, om, st, time):
     d = refs.new_delta_tot(libh, om, len(st["kk"]))
     libh.read_all_nu_state(C.byref(d), os.path.join(refs.GOLDEN, "delta_tot_nu.txt").encode())

@@ -196,3 +196,37 @@ def test_total_power_path_and_output_files(gpu, tmp_path):
     nret = o.orc_total_powerspectrum(n, cur.ctypes.data_as(C.c_void_p), 1, nb, 0, n, refs.dptr(p), c.ctypes.data_as(capi.c_longlong_p), refs.dptr(k))
     assert len(rows) == nret
     np.testing.assert_allclose([float(r[0]) for r in rows], k[:nret] * 2 * np.pi / refs.BOX, rtol=6e-6)    # %g keeps 6 significant digits
+
+
+@pytest.mark.parametrize("hybrid,masses", [(False, (0.1, 0.1, 0.1)), (True, (0.2, 0.1, 0.3))])
+def test_hundred_step_run_tracks_oracle(gpu, hybrid, masses):
+    """A whole simulated run, a = 0.01 ... 1.0 in 110 PM steps (kept and dropped rows, the history growing to ~100 rows, the
+    hybrid switch-on at a = 0.333): after EVERY step delta_nu and the row bookkeeping must agree with the CPU oracle to the
+    north-star tolerance.  ~10^5 adaptive-quadrature decisions are replayed; one flipped decision would show up as ~1e-7."""
+    o = refs.orc()
+    n = 32
+    g = refs.random_grid(n, seed=77)
+    refs.init_module(gpu, n, masses=masses, hybrid=hybrid)
+    dt = capi.global_delta_tot_table()
+    m = refs.orc_module(n, masses=masses, hybrid=hybrid)
+    dev = refs.DeviceBuffer(gpu, g)
+    cur = g.copy()
+    worst = 0.0
+    # kept rows every 0.0105 (namax = 101 rows is never exceeded: the reference has no bound check), plus dropped in-between steps
+    times = [0.01]
+    for i in range(1, 95):
+        times.append(0.01 + 0.0105 * i)
+        if i % 6 == 2:
+            times.append(0.01 + 0.0105 * i + 0.004)
+    for a in times:
+        gpu.add_nu_power_to_rhogrid_f64(a, refs.BOX, dev.ptr, n, 0, n, 0)
+        assert o.orc_add_nu_power_to_rhogrid(C.byref(m), a, refs.BOX, cur.ctypes.data_as(C.c_void_p), 1, n, 0, n) == 0
+        assert (dt.ia, dt.nk) == (m.dtot.ia, m.dtot.nk)
+        got = np.array([dt.delta_nu_last[i] for i in range(dt.nk)])
+        want = np.array([m.dtot.delta_nu_last[i] for i in range(dt.nk)])
+        worst = max(worst, float(np.max(np.abs(got / want - 1))))
+    final = dev.download(g)
+    dev.free()
+    assert dt.ia > 90
+    assert worst < 1e-10, worst
+    np.testing.assert_allclose(final, cur, rtol=1e-9, atol=0)       # 110 multiplicative steps accumulate rounding

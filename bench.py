@@ -311,7 +311,7 @@ def ours(args):
     roofline = {"bound": "hbm", "kernel": "k3_scale_tma_kernel<double> (read-modify-write, 32 B per stored mode)",
                 "achieved": 32.0 * local_modes / (k3_launch_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                 "frac": 32.0 * local_modes / (k3_launch_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
-                "k1": {"kernel": "k1_pair_kernel<double> (read-only, 16 B per stored mode)",
+                "k1": {"kernel": L.ksn_last_k1_kernel().decode() + " (read-only, 16 B per stored mode)",
                        "achieved": 16.0 * local_modes / (k1_launch_ms * 1e-3) / 1e9,
                        "frac": 16.0 * local_modes / (k1_launch_ms * 1e-3) / 1e9 / peak},
                 "step": {"achieved": 48.0 * local_modes / (step_ms * 1e-3) / 1e9,

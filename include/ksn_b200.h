@@ -134,6 +134,8 @@ typedef struct ksn_delta_nu_args {
 /* out: nspecies*nk doubles, species-major.  n_evals (may be NULL): integrand evaluations. */
 int ksn_delta_nu_integrate(const ksn_delta_nu_args *args, double *out, unsigned long long *n_evals);
 
+/* which K1 kernel (and tile configuration) the most recent power-spectrum sweep launched */
+const char *ksn_last_k1_kernel(void);
 /* integrand evaluations of the most recent ksn_delta_nu_integrate call (fslength table included) */
 unsigned long long ksn_last_k2_evals(void);
 /* largest number of 61-point rule applications any single k bin needed in that call (the kernel's critical path) */

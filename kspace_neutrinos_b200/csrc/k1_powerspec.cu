@@ -26,6 +26,7 @@
 #include "ksn_internal.cuh"
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -380,6 +381,266 @@ k1_pair_kernel(const Cplx<real> *__restrict__ grid, int nrows, int N, int nrbins
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Tile path (default for power-only sweeps of a double grid).  The pair kernel above is ISSUE-bound (ncu: 67 warp
+// instructions per 32 modes, most of them the per-step shuffle scans).  Here the work is laid out so that little but the
+// arithmetic is left:
+//  * a row is cut into tiles of 32*C modes (C = 4q+1); one TMA bulk copy (cp.async.bulk, completion on an mbarrier)
+//    brings a tile into the warp's own shared-memory ring (S stages per warp) -- no load instructions, bytes in flight
+//    bounded by shared memory, not registers;
+//  * lane l walks the C CONSECUTIVE modes [l*C, (l+1)*C) of the tile (odd C => the 32 lanes' 16-byte reads fall in
+//    distinct bank groups): k^2 advances by an integer add, the bin changes only when k^2 crosses the next host-built
+//    threshold, and a run of equal bins is a private FMA chain.  A finished run is PUSHED (one store, no read) onto a
+//    queue that lives in the chunk's own, already consumed, shared-memory slots -- so a lane that closes a run does
+//    not stall the other 31 on a read-modify-write;
+//  * after the walk the queues are drained into the warp-private bin array.  Bins are monotone along a row, so the
+//    queued runs of different lanes hit disjoint bins (plain read-modify-write, fixed order), except the FIRST run of a
+//    lane, which may share its bin with the runs of the lanes before it: those 32 partial sums are combined by one
+//    segmented warp scan per tile.
+constexpr int K1T_MAXW = 16;
+
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+
+__global__ void __launch_bounds__(K1T_MAXW * 32, 1)
+k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbins, long long plane0, float binscale,
+               const unsigned *__restrict__ thr, const double *__restrict__ iw, double *__restrict__ partial, int accumulate,
+               int C, int T, int S, int stage_bytes, unsigned k2_single, int log2N)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int L = N / 2 + 1, nyq = N / 2;
+    const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int TE = 32 * C;                                     // modes per tile
+    const int nwz = T * TE + 8;                                // z-weight table, zero past the row end
+    unsigned char *sp = smem_raw;
+    unsigned char *stages = sp;                   sp += (size_t) W * S * stage_bytes;
+    double *iwz_s = (double *) sp;                sp += (size_t) nwz * sizeof(double);
+    double *bins_s = (double *) sp;               sp += (size_t) W * nrbins * sizeof(double);
+    unsigned long long *bars = (unsigned long long *) sp;  sp += (size_t) W * S * sizeof(unsigned long long);
+    unsigned *thr_s = (unsigned *) sp;                      // nrbins + 3
+    for (int i = threadIdx.x; i < nwz; i += blockDim.x) {      // m_z * iwz^4 (Hermitian multiplicity folded in)
+        double v = 0.0;
+        if (i < L) { const double w2 = iw[i] * iw[i]; v = ((i == 0 || i == nyq) ? 1.0 : 2.0) * (w2 * w2); }
+        iwz_s[i] = v;
+    }
+    for (int i = threadIdx.x; i < nrbins + 3; i += blockDim.x) thr_s[i] = i < nrbins ? thr[i] : 0xffffffffu;
+    for (int i = threadIdx.x; i < W * nrbins; i += blockDim.x) bins_s[i] = 0.0;
+    // the stages start as zeros: modes past a row's end are walked like any other (weight 0), so they must be finite
+    for (int i = threadIdx.x; i < W * S * stage_bytes / 16; i += blockDim.x) ((double2 *) stages)[i] = make_double2(0.0, 0.0);
+    if (lane == 0) {
+        for (int s = 0; s < S; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bars + warp * S + s)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    const long long first = (long long) blockIdx.x * W + warp, stride = (long long) gridDim.x * W;
+    const int dr = (int) (stride / T), dt = (int) (stride - (long long) dr * T);     // a step of `stride` tiles in (row, tile-of-row)
+    unsigned char *mystage = stages + (size_t) warp * S * stage_bytes;
+    const unsigned bar0 = smem_addr(bars + warp * S);
+    double *mybins = bins_s + (size_t) warp * nrbins;
+    const unsigned le_mask = 0xffffffffu >> (31 - lane);
+
+    auto issue = [&](int r, int t, int s) {         // lane 0: bulk copy of tile t of row r into stage s
+        const int z0 = t * TE, len = min(TE, L - z0);
+        const unsigned bytes = (unsigned) len * 16u;
+        const unsigned bar = bar0 + 8u * s, dst = smem_addr(mystage + (size_t) s * stage_bytes);
+        const Cplx<double> *src = grid + (size_t) r * L + z0;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+    };
+    // consumer position (r, t) and producer position (ri, ti) = S tiles ahead
+    int r = (int) (first / T), t = (int) (first - (long long) r * T);
+    int ri = r, ti = t;
+    for (int s = 0; s < S; s++) {
+        if (lane == 0 && ri < nrows) issue(ri, ti, s);
+        ri += dr; ti += dt;
+        if (ti >= T) { ti -= T; ri++; }
+    }
+
+    unsigned phases = 0;
+    int s = 0;
+    while (r < nrows) {
+        // row geometry (warp-uniform); the two window loads are consumed only when the runs are drained
+        const int pl = log2N >= 0 ? r >> log2N : r / N, j = r - pl * N;
+        const long long gi = plane0 + pl;
+        const int ki = gi <= N / 2 ? (int) gi : (int) (gi - N);
+        const int kj = j <= N / 2 ? j : j - N;
+        const int c = ki * ki + kj * kj;
+        const double wa = __ldg(iw + (ki < 0 ? -ki : ki)), wb = __ldg(iw + (kj < 0 ? -kj : kj));
+        const int z0 = t * TE, zl = z0 + lane * C;             // first z of the tile / of this lane's chunk
+        unsigned k2 = (unsigned) c + (unsigned) zl * (unsigned) zl, dz = 2u * (unsigned) zl + 1u;
+        int b = max((int) (binscale * fast_log2((float) k2)), 0);      // within one bin of the truth
+        b = min(b, nrbins - 1);
+        b += (k2 >= thr_s[b + 1]) - (k2 < thr_s[b]);
+        const int fbin = b;
+        unsigned nxt = thr_s[b + 1];
+        const unsigned n2_0 = thr_s[b + 2], n3_0 = thr_s[b + 3];
+        // bin of the chunk's last mode: a lane that closes more than K1T_RUNS-1 runs cannot use the register window below
+        const unsigned k2e = (unsigned) c + (unsigned) (zl + C - 1) * (unsigned) (zl + C - 1);
+        int be = min(max((int) (binscale * fast_log2((float) k2e)), 0), nrbins - 1);
+        be += (k2e >= thr_s[be + 1]) - (k2e < thr_s[be]);
+        const bool narrow = __all_sync(0xffffffffu, be - fbin <= 3);
+        Cplx<double> *chunk = (Cplx<double> *) (mystage + (size_t) s * stage_bytes) + lane * C;
+        const double *wz = iwz_s + zl;
+        mbar_wait(bar0 + 8u * s, (phases >> s) & 1u);
+        phases ^= 1u << s;
+        if (c == 0 && zl == 0) { chunk[0].re = 0; chunk[0].im = 0; }   // F(0,0,0): the mean, not a mode
+        const double q1 = wa * wb, q2 = q1 * q1, wxy = q2 * q2;        // (iwx iwy)^4, applied once per run
+
+        double acc = 0.0, facc;
+        Cplx<double> vc[4];
+        double wc[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { vc[u] = chunk[u]; wc[u] = wz[u]; }
+        if (narrow && (unsigned) c + (unsigned) z0 * (unsigned) z0 >= k2_single) {
+            // FAST tile: one mode crosses at most one bin threshold (so run i of a lane is bin fbin+i) and no lane closes
+            // more than three runs (so the thresholds it will meet sit in three registers): the walk has no branch and no
+            // dependent load.  The running sum is stored every mode; the store slot advances when a bin closes.  The
+            // queue lives in the chunk's own, already consumed, slots.
+            double *q = (double *) chunk;
+            unsigned n2 = n2_0, n3 = n3_0;
+            auto step = [&](const Cplx<double> &v, double w) {
+                const double pp = fma(v.im, v.im, v.re * v.re);
+                const bool ch = k2 >= nxt;
+                *q = acc;
+                q += ch;
+                nxt = ch ? n2 : nxt;
+                n2 = ch ? n3 : n2;
+                n3 = ch ? 0xffffffffu : n3;
+                acc = ch ? 0.0 : acc;
+                acc = fma(pp, w, acc);
+                k2 += dz;
+                dz += 2u;
+            };
+#pragma unroll 2
+            for (int e = 0; e + 4 < C; e += 4) {           // C = 4q+1: q blocks of four, then one mode
+                Cplx<double> vn[4];
+                double wn[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) { vn[u] = chunk[e + 4 + u]; wn[u] = wz[e + 4 + u]; }
+#pragma unroll
+                for (int u = 0; u < 4; u++) step(vc[u], wc[u]);
+#pragma unroll
+                for (int u = 0; u < 4; u++) { vc[u] = vn[u]; wc[u] = wn[u]; }
+            }
+            step(vc[0], wc[0]);
+            *q = acc;                                       // the open run
+            const int cnt = (int) (q - (double *) chunk) + 1;
+            const int maxcnt = __reduce_max_sync(0xffffffffu, cnt);
+            const double *qq = (const double *) chunk;
+            for (int i = 1; i < maxcnt; i++)
+                if (i < cnt) mybins[fbin + i] = fma(qq[i], wxy, mybins[fbin + i]);
+            facc = qq[0];
+        } else {
+            // GENERAL tile (the low-k corner, where bins are narrower than a step in k^2): finished runs go straight to the bins
+            facc = 0.0;
+            auto step = [&](const Cplx<double> &v, double w) {
+                const double pp = fma(v.im, v.im, v.re * v.re);
+                if (k2 >= nxt) {
+                    if (b == fbin) facc = acc; else mybins[b] = fma(acc, wxy, mybins[b]);
+                    acc = 0.0;
+                    do { b++; nxt = thr_s[b + 1]; } while (k2 >= nxt);
+                }
+                acc = fma(pp, w, acc);
+                k2 += dz;
+                dz += 2u;
+            };
+#pragma unroll 1
+            for (int e = 0; e + 4 < C; e += 4) {
+                Cplx<double> vn[4];
+                double wn[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) { vn[u] = chunk[e + 4 + u]; wn[u] = wz[e + 4 + u]; }
+#pragma unroll
+                for (int u = 0; u < 4; u++) step(vc[u], wc[u]);
+#pragma unroll
+                for (int u = 0; u < 4; u++) { vc[u] = vn[u]; wc[u] = wn[u]; }
+            }
+            step(vc[0], wc[0]);
+            if (b == fbin) facc = acc; else mybins[b] = fma(acc, wxy, mybins[b]);
+        }
+        // A lane's FIRST run may share its bin with the runs of the lanes before it (everything else above hit bins no
+        // other lane touches, because bins are monotone along a row): one segmented scan over the 32 first runs.
+        {
+            double v1[1] = { facc };
+            const unsigned tails = segmented_sum<1>(fbin, v1, lane, le_mask);
+            __syncwarp();
+            if ((tails >> lane) & 1u) mybins[fbin] = fma(v1[0], wxy, mybins[fbin]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the queue was written through the generic proxy
+        __syncwarp();                                                  // every lane is done with the stage and with the bins
+        if (lane == 0 && ri < nrows) issue(ri, ti, s);
+        ri += dr; ti += dt;
+        if (ti >= T) { ti -= T; ri++; }
+        r += dr; t += dt;
+        if (t >= T) { t -= T; r++; }
+        s = s + 1 == S ? 0 : s + 1;
+    }
+    __syncthreads();
+    double *out = partial + (size_t) blockIdx.x * nrbins;
+    for (int i = threadIdx.x; i < nrbins; i += blockDim.x) {
+        double sum = 0.0;
+        for (int w = 0; w < W; w++) sum += bins_s[(size_t) w * nrbins + i];
+        out[i] = accumulate ? out[i] + sum : sum;
+    }
+}
+
+static unsigned g_k1_k2_single = 0xffffffffu;
+static char g_k1_last[96] = "none";
+
+struct K1TileCfg { int W, C, S, T, stage_bytes; size_t smem, inflight; };
+
+static size_t k1_tile_smem(int L, int nrbins, int W, int C, int S, int *T_out, int *stage_out)
+{
+    const int TE = 32 * C, T = (L + TE - 1) / TE;
+    const int stage = (int) ((((size_t) TE + 8) * 16 + 127) & ~(size_t) 127);
+    if (T_out) *T_out = T;
+    if (stage_out) *stage_out = stage;
+    return (size_t) W * S * stage + ((size_t) T * TE + 8) * 8 + (size_t) W * nrbins * 8 + (size_t) W * S * 8 + (size_t) (nrbins + 3) * 4 + 128;
+}
+
+// Pick (warps, chunk, stages): as many bytes in flight as shared memory allows (capped: ~128 KB per SM saturates HBM),
+// little of a row's last tile wasted, at least 4 warps.  KSN_K1_TILE="W,C,S" overrides.
+static bool k1_tile_config(int L, int nrbins, size_t budget, K1TileCfg *best)
+{
+    best->W = 0;
+    double best_score = -1;
+    int fw = 0, fc = 0, fs = 0;
+    const char *env = getenv("KSN_K1_TILE");
+    if (env && sscanf(env, "%d,%d,%d", &fw, &fc, &fs) != 3) fw = 0;
+    for (int W = 4; W <= K1T_MAXW; W++)
+        for (int C = 1; C <= 65; C += 4)
+            for (int S = 1; S <= 4; S++) {
+                if (fw ? (W != fw || C != fc || S != fs) : S < 2) continue;
+                int T, stage;
+                const size_t smem = k1_tile_smem(L, nrbins, W, C, S, &T, &stage);
+                if (smem > budget) continue;
+                const int TE = 32 * C;
+                if (T > 1 && C < 5) continue;                             // tiny tiles only for tiny rows
+                const double eff = (double) L / ((double) T * TE);        // lane slots that carry a mode
+                const size_t inflight = (size_t) W * S * TE * 16;
+                const double fl = inflight < (size_t) 131072 ? (double) inflight : 131072.0;
+                double score = eff * fl;
+                if (W >= 8) score *= 1.05;                                // enough warps to hide the shared-memory latency
+                if (TE * 16 >= 4096) score *= 1.05;                       // bulk copies of at least 4 KB
+                if (score > best_score) {
+                    best_score = score;
+                    best->W = W; best->C = C; best->S = S; best->T = T; best->stage_bytes = stage; best->smem = smem; best->inflight = inflight;
+                }
+            }
+    return best->W > 0;
+}
+
 template <typename real, bool FULL>
 __global__ void __launch_bounds__(K1_MAX_WARPS * 32, 1)
 k1_bin_kernel(const Cplx<real> *__restrict__ grid, int nrows, int N, int nrbins, long long plane0,
@@ -501,6 +762,23 @@ static int k1_launch_t(const void *dgrid, int dims, int nrbins, long long plane0
         KSN_CUDA(cudaGetLastError());
         return KSN_OK;
     };
+    K1TileCfg tc;
+    if (!FULL && sizeof(real) == 8 && !getenv("KSN_K1_PAIR") && !getenv("KSN_K1_NOPAIR") && ((uintptr_t) dgrid & 15) == 0 &&
+        k1_tile_config(dims / 2 + 1, nrbins, c.smem_optin, &tc)) {
+        int log2N = -1;
+        if ((dims & (dims - 1)) == 0) { log2N = 0; while ((1 << log2N) < dims) log2N++; }
+        KSN_CUDA(cudaFuncSetAttribute(k1_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc.smem));
+        k1_tile_kernel<<<ctas, tc.W * 32, tc.smem, c.stream>>>((const Cplx<double> *) dgrid, nrows, dims, nrbins, plane0, binscale,
+                                                              c.d_thr, c.d_iw, c.d_partial, accumulate ? 1 : 0, tc.C, tc.T, tc.S, tc.stage_bytes,
+                                                              g_k1_k2_single, log2N);
+        c.launches++;
+        KSN_CUDA(cudaGetLastError());
+        snprintf(g_k1_last, sizeof g_k1_last, "k1_tile_kernel (%d warps x %d modes per lane, %d stages, %d tiles per row)", tc.W, tc.C, tc.S, tc.T);
+        *ctas_out = ctas;
+        *stride_out = NV * nrbins;
+        return KSN_OK;
+    }
+    snprintf(g_k1_last, sizeof g_k1_last, "%s<%s>", FULL || getenv("KSN_K1_NOPAIR") ? "k1_bin_kernel" : "k1_pair_kernel", sizeof(real) == 8 ? "double" : "float");
     if (FULL || getenv("KSN_K1_NOPAIR")) rc = launch(k1_bin_kernel<real, FULL>);
     else if (cfgv == 204) rc = launch(k1_pair_kernel<real, 20, 4>);
     else if (cfgv == 242) rc = launch(k1_pair_kernel<real, 24, 2>);
@@ -540,6 +818,14 @@ int k1_finish(int real_bytes, int dims, int nrbins, bool full, int ctas, int str
 
 static int k1_upload_tables(int dims, int nrbins, const unsigned int *thresholds, const double *invwin)
 {
+    // From which k^2 on can one step along z (k^2 -> k^2 + 2z+1 <= k^2 + 2 sqrt(k^2) + 1) cross at most ONE bin threshold?
+    // J = one past the last pair of thresholds closer than such a step; a tile that starts at or above thr[J] is "fast".
+    {
+        int J = 0;
+        for (int j = 0; j + 1 < nrbins; j++)
+            if ((double) thresholds[j + 1] - (double) thresholds[j] < 2.0 * sqrt((double) thresholds[j + 1]) + 2.0) J = j + 2;
+        g_k1_k2_single = J < nrbins ? thresholds[J] : 0xffffffffu;
+    }
     Ctx &c = ctx();
     const int L = dims / 2 + 1;
     int rc = ensure_device_buffer((void **) &c.d_thr, &c.thr_cap, (size_t) nrbins * sizeof(unsigned));
@@ -658,6 +944,8 @@ int k1_sums(const void *dgrid, const void *hgrid, int real_bytes, int dims, int 
 }  // namespace ksn
 
 using namespace ksn;
+
+extern "C" const char *ksn_last_k1_kernel(void) { return g_k1_last; }
 
 extern "C" int ksn_powerspectrum_sums(const void *grid, int real_bytes, int dims, int nrbins,
                                       long long startslab, long long nslab,

@@ -152,3 +152,41 @@ def test_odd_aligned_device_pointer(gpu):
     gpu.ksn_device_free(ptr)
     assert np.array_equal(a[2], b[2]) and a[3] == b[3]
     np.testing.assert_allclose(a[0], b[0], rtol=1e-13)
+
+
+@pytest.mark.parametrize("n,start,nslab,tile", [(64, 0, 64, None), (128, 3, 77, None), (256, 0, 256, None), (256, 100, 31, "8,5,2"),
+                                                (256, 0, 256, "4,9,3"), (512, 0, 64, None), (512, 200, 48, "6,17,2")])
+def test_tile_pair_and_full_kernels_agree(gpu, n, start, nslab, tile, monkeypatch):
+    """The three K1 kernels (k1_bin_kernel: all three sums, first call per geometry; k1_pair_kernel: 256-bit loads +
+    segmented scans; k1_tile_kernel: TMA tiles + per-lane sequential walk, fast and general tiles) sum the same modes in
+    different orders: same power sums to rounding, on whole grids, ragged slabs and forced tile shapes."""
+    from kspace_neutrinos_b200 import capi
+    nrbins = n // 2
+    g = refs.random_grid(n, seed=n + start)[start:start + nslab].copy()
+    d = refs.DeviceBuffer(gpu, g)
+    monkeypatch.setenv("KSN_NO_GEOM_CACHE", "1")
+    full = _sums(gpu, g, nrbins, start, nslab, pointer=d.ptr)
+    assert b"k1_bin_kernel" in gpu.ksn_last_k1_kernel()
+    monkeypatch.delenv("KSN_NO_GEOM_CACHE")
+    _sums(gpu, g, nrbins, start, nslab, pointer=d.ptr)              # fills the geometry cache
+    monkeypatch.setenv("KSN_K1_PAIR", "1")
+    pair = _sums(gpu, g, nrbins, start, nslab, pointer=d.ptr)
+    assert b"k1_pair_kernel" in gpu.ksn_last_k1_kernel()
+    monkeypatch.delenv("KSN_K1_PAIR")
+    if tile:
+        monkeypatch.setenv("KSN_K1_TILE", tile)
+    tl = _sums(gpu, g, nrbins, start, nslab, pointer=d.ptr)
+    name = gpu.ksn_last_k1_kernel()
+    assert b"k1_tile_kernel" in name, name
+    if tile:
+        w, c, s = tile.split(",")
+        assert f"({w} warps x {c} modes per lane, {s} stages".encode() in name, name
+    tl2 = _sums(gpu, g, nrbins, start, nslab, pointer=d.ptr)
+    d.free()
+    assert np.array_equal(tl[0], tl2[0])                             # run-to-run bitwise
+    assert np.array_equal(full[2], tl[2]) and np.array_equal(full[2], pair[2])
+    live = full[0] != 0
+    assert np.array_equal(live, tl[0] != 0) and np.array_equal(live, pair[0] != 0)
+    np.testing.assert_allclose(tl[0][live], full[0][live], rtol=2e-13)
+    np.testing.assert_allclose(pair[0][live], full[0][live], rtol=2e-13)
+    assert tl[3] == full[3] == pair[3]

@@ -391,14 +391,17 @@ k1_pair_kernel(const Cplx<real> *__restrict__ grid, int nrows, int N, int nrbins
 //    bounded by shared memory, not registers;
 //  * lane l walks the C CONSECUTIVE modes [l*C, (l+1)*C) of the tile (odd C => the 32 lanes' 16-byte reads fall in
 //    distinct bank groups): k^2 advances by an integer add, the bin changes only when k^2 crosses the next host-built
-//    threshold, and a run of equal bins is a private FMA chain.  A finished run is PUSHED (one store, no read) onto a
-//    queue that lives in the chunk's own, already consumed, shared-memory slots -- so a lane that closes a run does
-//    not stall the other 31 on a read-modify-write;
+//    threshold, and a run of equal bins is a private FMA chain.  The z-window weights of a lane's chunk are the same for
+//    every row, so (C known at compile time) they stay in registers;
+//  * FAST tiles (one mode crosses at most one threshold; no lane closes more than three runs -- all but the low-k corner):
+//    the walk has no branch and no dependent load; a finished run is pushed by one predicated store onto a small queue
+//    (run i of a lane is bin fbin+i);  GENERAL tiles update the bins from inside the walk;
 //  * after the walk the queues are drained into the warp-private bin array.  Bins are monotone along a row, so the
 //    queued runs of different lanes hit disjoint bins (plain read-modify-write, fixed order), except the FIRST run of a
 //    lane, which may share its bin with the runs of the lanes before it: those 32 partial sums are combined by one
 //    segmented warp scan per tile.
 constexpr int K1T_MAXW = 16;
+constexpr int K1T_QRUNS = 4;              // queue slots per lane: three closed runs and the open one
 
 __device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
 
@@ -410,12 +413,29 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
 }
 
-__global__ void __launch_bounds__(K1T_MAXW * 32, 1)
+// queue accesses bypass the compiler's alias analysis on purpose (no "memory" clobber): the queue is a region of its
+// own, and the walk's loads must stay free to move ahead of these stores
+__device__ __forceinline__ void queue_push_if(bool ch, unsigned addr, double v)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.shared.f64 [%1], %2;\n\t}" ::"r"((unsigned) ch), "r"(addr), "d"(v));
+}
+__device__ __forceinline__ void queue_put(unsigned addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v)); }
+__device__ __forceinline__ double queue_get(unsigned addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+// CT > 0: modes per lane known at compile time (walk fully unrolled, weights in registers); CT == 0: run-time C.
+template <int CT>
+__global__ void __launch_bounds__((CT == 5 || CT == 9 ? K1T_MAXW : 8) * 32, 1)
 k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbins, long long plane0, float binscale,
                const unsigned *__restrict__ thr, const double *__restrict__ iw, double *__restrict__ partial, int accumulate,
-               int C, int T, int S, int stage_bytes, unsigned k2_single, int log2N)
+               int Crt, int T, int S, int stage_bytes, unsigned k2_single, int log2N)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int C = CT > 0 ? CT : Crt;
     const int L = N / 2 + 1, nyq = N / 2;
     const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int TE = 32 * C;                                     // modes per tile
@@ -424,6 +444,7 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
     unsigned char *stages = sp;                   sp += (size_t) W * S * stage_bytes;
     double *iwz_s = (double *) sp;                sp += (size_t) nwz * sizeof(double);
     double *bins_s = (double *) sp;               sp += (size_t) W * nrbins * sizeof(double);
+    double *queue_s = (double *) sp;              sp += (size_t) W * K1T_QRUNS * 32 * sizeof(double);
     unsigned long long *bars = (unsigned long long *) sp;  sp += (size_t) W * S * sizeof(unsigned long long);
     unsigned *thr_s = (unsigned *) sp;                      // nrbins + 3
     for (int i = threadIdx.x; i < nwz; i += blockDim.x) {      // m_z * iwz^4 (Hermitian multiplicity folded in)
@@ -439,7 +460,7 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
         for (int s = 0; s < S; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bars + warp * S + s)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zeros above, before any bulk copy lands on them
     __syncthreads();
 
     const long long first = (long long) blockIdx.x * W + warp, stride = (long long) gridDim.x * W;
@@ -447,6 +468,7 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
     unsigned char *mystage = stages + (size_t) warp * S * stage_bytes;
     const unsigned bar0 = smem_addr(bars + warp * S);
     double *mybins = bins_s + (size_t) warp * nrbins;
+    const unsigned q0 = smem_addr(queue_s + (size_t) warp * K1T_QRUNS * 32 + lane);   // run i of this lane: q0 + 256 i
     const unsigned le_mask = 0xffffffffu >> (31 - lane);
 
     auto issue = [&](int r, int t, int s) {         // lane 0: bulk copy of tile t of row r into stage s
@@ -467,6 +489,8 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
         if (ti >= T) { ti -= T; ri++; }
     }
 
+    double wreg[CT > 0 ? CT : 1];
+    int t_loaded = -1;
     unsigned phases = 0;
     int s = 0;
     while (r < nrows) {
@@ -484,36 +508,32 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
         b += (k2 >= thr_s[b + 1]) - (k2 < thr_s[b]);
         const int fbin = b;
         unsigned nxt = thr_s[b + 1];
-        const unsigned n2_0 = thr_s[b + 2], n3_0 = thr_s[b + 3];
-        // bin of the chunk's last mode: a lane that closes more than K1T_RUNS-1 runs cannot use the register window below
+        unsigned n2 = thr_s[b + 2], n3 = thr_s[b + 3];
+        // bin of the chunk's last mode: a lane that would close more than three runs cannot use the register window
         const unsigned k2e = (unsigned) c + (unsigned) (zl + C - 1) * (unsigned) (zl + C - 1);
         int be = min(max((int) (binscale * fast_log2((float) k2e)), 0), nrbins - 1);
         be += (k2e >= thr_s[be + 1]) - (k2e < thr_s[be]);
-        const bool narrow = __all_sync(0xffffffffu, be - fbin <= 3);
-        Cplx<double> *chunk = (Cplx<double> *) (mystage + (size_t) s * stage_bytes) + lane * C;
+        const bool fast = __all_sync(0xffffffffu, be - fbin <= K1T_QRUNS - 1) && (unsigned) c + (unsigned) z0 * (unsigned) z0 >= k2_single;
+        const Cplx<double> *chunk = (const Cplx<double> *) (mystage + (size_t) s * stage_bytes) + lane * C;
         const double *wz = iwz_s + zl;
+        if (CT > 0 && t != t_loaded) {             // (a warp keeps the same tile-of-row whenever T divides its stride)
+#pragma unroll
+            for (int e = 0; e < (CT > 0 ? CT : 1); e++) wreg[e] = wz[e];
+            t_loaded = t;
+        }
+        const double worigin = (c == 0 && zl == 0) ? 0.0 : 1.0;        // F(0,0,0) is the mean, not a mode: weight 0
         mbar_wait(bar0 + 8u * s, (phases >> s) & 1u);
         phases ^= 1u << s;
-        if (c == 0 && zl == 0) { chunk[0].re = 0; chunk[0].im = 0; }   // F(0,0,0): the mean, not a mode
         const double q1 = wa * wb, q2 = q1 * q1, wxy = q2 * q2;        // (iwx iwy)^4, applied once per run
 
         double acc = 0.0, facc;
-        Cplx<double> vc[4];
-        double wc[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) { vc[u] = chunk[u]; wc[u] = wz[u]; }
-        if (narrow && (unsigned) c + (unsigned) z0 * (unsigned) z0 >= k2_single) {
-            // FAST tile: one mode crosses at most one bin threshold (so run i of a lane is bin fbin+i) and no lane closes
-            // more than three runs (so the thresholds it will meet sit in three registers): the walk has no branch and no
-            // dependent load.  The running sum is stored every mode; the store slot advances when a bin closes.  The
-            // queue lives in the chunk's own, already consumed, slots.
-            double *q = (double *) chunk;
-            unsigned n2 = n2_0, n3 = n3_0;
-            auto step = [&](const Cplx<double> &v, double w) {
+        if (fast) {
+            unsigned qa = q0;
+            auto step = [&](const Cplx<double> v, double w) {
                 const double pp = fma(v.im, v.im, v.re * v.re);
                 const bool ch = k2 >= nxt;
-                *q = acc;
-                q += ch;
+                queue_push_if(ch, qa, acc);
+                qa += ch ? 256u : 0u;
                 nxt = ch ? n2 : nxt;
                 n2 = ch ? n3 : n2;
                 n3 = ch ? 0xffffffffu : n3;
@@ -522,29 +542,42 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
                 k2 += dz;
                 dz += 2u;
             };
+            if (CT > 0) {
+                step(chunk[0], wreg[0] * worigin);
+#pragma unroll
+                for (int e = 1; e < (CT > 0 ? CT : 1); e++) step(chunk[e], wreg[e]);
+            } else {
+                Cplx<double> vc[4];
+                double wc[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) { vc[u] = chunk[u]; wc[u] = wz[u]; }
+                wc[0] *= worigin;
 #pragma unroll 2
-            for (int e = 0; e + 4 < C; e += 4) {           // C = 4q+1: q blocks of four, then one mode
-                Cplx<double> vn[4];
-                double wn[4];
+                for (int e = 0; e + 4 < C; e += 4) {           // C = 4q+1: q blocks of four, then one mode
+                    Cplx<double> vn[4];
+                    double wn[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) { vn[u] = chunk[e + 4 + u]; wn[u] = wz[e + 4 + u]; }
+                    for (int u = 0; u < 4; u++) { vn[u] = chunk[e + 4 + u]; wn[u] = wz[e + 4 + u]; }
 #pragma unroll
-                for (int u = 0; u < 4; u++) step(vc[u], wc[u]);
+                    for (int u = 0; u < 4; u++) step(vc[u], wc[u]);
 #pragma unroll
-                for (int u = 0; u < 4; u++) { vc[u] = vn[u]; wc[u] = wn[u]; }
+                    for (int u = 0; u < 4; u++) { vc[u] = vn[u]; wc[u] = wn[u]; }
+                }
+                step(vc[0], wc[0]);
             }
-            step(vc[0], wc[0]);
-            *q = acc;                                       // the open run
-            const int cnt = (int) (q - (double *) chunk) + 1;
+            queue_put(qa, acc);                                 // the open run
+            // the stage is consumed: put the next bulk copy in flight before the bookkeeping below
+            __syncwarp();
+            if (lane == 0 && ri < nrows) issue(ri, ti, s);
+            const int cnt = (int) ((qa - q0) >> 8) + 1;
             const int maxcnt = __reduce_max_sync(0xffffffffu, cnt);
-            const double *qq = (const double *) chunk;
             for (int i = 1; i < maxcnt; i++)
-                if (i < cnt) mybins[fbin + i] = fma(qq[i], wxy, mybins[fbin + i]);
-            facc = qq[0];
+                if (i < cnt) mybins[fbin + i] = fma(queue_get(q0 + 256u * i), wxy, mybins[fbin + i]);
+            facc = queue_get(q0);
         } else {
             // GENERAL tile (the low-k corner, where bins are narrower than a step in k^2): finished runs go straight to the bins
             facc = 0.0;
-            auto step = [&](const Cplx<double> &v, double w) {
+            auto step = [&](const Cplx<double> v, double w) {
                 const double pp = fma(v.im, v.im, v.re * v.re);
                 if (k2 >= nxt) {
                     if (b == fbin) facc = acc; else mybins[b] = fma(acc, wxy, mybins[b]);
@@ -555,19 +588,12 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
                 k2 += dz;
                 dz += 2u;
             };
+            step(chunk[0], wz[0] * worigin);
 #pragma unroll 1
-            for (int e = 0; e + 4 < C; e += 4) {
-                Cplx<double> vn[4];
-                double wn[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) { vn[u] = chunk[e + 4 + u]; wn[u] = wz[e + 4 + u]; }
-#pragma unroll
-                for (int u = 0; u < 4; u++) step(vc[u], wc[u]);
-#pragma unroll
-                for (int u = 0; u < 4; u++) { vc[u] = vn[u]; wc[u] = wn[u]; }
-            }
-            step(vc[0], wc[0]);
+            for (int e = 1; e < C; e++) step(chunk[e], wz[e]);
             if (b == fbin) facc = acc; else mybins[b] = fma(acc, wxy, mybins[b]);
+            __syncwarp();
+            if (lane == 0 && ri < nrows) issue(ri, ti, s);
         }
         // A lane's FIRST run may share its bin with the runs of the lanes before it (everything else above hit bins no
         // other lane touches, because bins are monotone along a row): one segmented scan over the 32 first runs.
@@ -577,9 +603,7 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
             __syncwarp();
             if ((tails >> lane) & 1u) mybins[fbin] = fma(v1[0], wxy, mybins[fbin]);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the queue was written through the generic proxy
-        __syncwarp();                                                  // every lane is done with the stage and with the bins
-        if (lane == 0 && ri < nrows) issue(ri, ti, s);
+        __syncwarp();                                                  // every lane is done with the bins
         ri += dr; ti += dt;
         if (ti >= T) { ti -= T; ri++; }
         r += dr; t += dt;
@@ -606,8 +630,11 @@ static size_t k1_tile_smem(int L, int nrbins, int W, int C, int S, int *T_out, i
     const int stage = (int) ((((size_t) TE + 8) * 16 + 127) & ~(size_t) 127);
     if (T_out) *T_out = T;
     if (stage_out) *stage_out = stage;
-    return (size_t) W * S * stage + ((size_t) T * TE + 8) * 8 + (size_t) W * nrbins * 8 + (size_t) W * S * 8 + (size_t) (nrbins + 3) * 4 + 128;
+    return (size_t) W * S * stage + ((size_t) T * TE + 8) * 8 + (size_t) W * nrbins * 8 + (size_t) W * K1T_QRUNS * 32 * 8 +
+           (size_t) W * S * 8 + (size_t) (nrbins + 3) * 4 + 128;
 }
+
+static int k1_tile_max_warps(int C) { return (C == 5 || C == 9) ? K1T_MAXW : 8; }      // the kernels' launch bounds
 
 // Pick (warps, chunk, stages): as many bytes in flight as shared memory allows (capped: ~128 KB per SM saturates HBM),
 // little of a row's last tile wasted, at least 4 warps.  KSN_K1_TILE="W,C,S" overrides.
@@ -618,8 +645,8 @@ static bool k1_tile_config(int L, int nrbins, size_t budget, K1TileCfg *best)
     int fw = 0, fc = 0, fs = 0;
     const char *env = getenv("KSN_K1_TILE");
     if (env && sscanf(env, "%d,%d,%d", &fw, &fc, &fs) != 3) fw = 0;
-    for (int W = 4; W <= K1T_MAXW; W++)
-        for (int C = 1; C <= 65; C += 4)
+    for (int C = 1; C <= 65; C += 4)
+        for (int W = 4; W <= k1_tile_max_warps(C); W++)
             for (int S = 1; S <= 4; S++) {
                 if (fw ? (W != fw || C != fc || S != fs) : S < 2) continue;
                 int T, stage;
@@ -633,6 +660,7 @@ static bool k1_tile_config(int L, int nrbins, size_t budget, K1TileCfg *best)
                 double score = eff * fl;
                 if (W >= 8) score *= 1.05;                                // enough warps to hide the shared-memory latency
                 if (TE * 16 >= 4096) score *= 1.05;                       // bulk copies of at least 4 KB
+                if (C <= 17) score *= 1.05;                               // compile-time chunk: weights in registers
                 if (score > best_score) {
                     best_score = score;
                     best->W = W; best->C = C; best->S = S; best->T = T; best->stage_bytes = stage; best->smem = smem; best->inflight = inflight;
@@ -767,10 +795,22 @@ static int k1_launch_t(const void *dgrid, int dims, int nrbins, long long plane0
         k1_tile_config(dims / 2 + 1, nrbins, c.smem_optin, &tc)) {
         int log2N = -1;
         if ((dims & (dims - 1)) == 0) { log2N = 0; while ((1 << log2N) < dims) log2N++; }
-        KSN_CUDA(cudaFuncSetAttribute(k1_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc.smem));
-        k1_tile_kernel<<<ctas, tc.W * 32, tc.smem, c.stream>>>((const Cplx<double> *) dgrid, nrows, dims, nrbins, plane0, binscale,
-                                                              c.d_thr, c.d_iw, c.d_partial, accumulate ? 1 : 0, tc.C, tc.T, tc.S, tc.stage_bytes,
-                                                              g_k1_k2_single, log2N);
+        auto go = [&](auto kern) -> int {
+            KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc.smem));
+            kern<<<ctas, tc.W * 32, tc.smem, c.stream>>>((const Cplx<double> *) dgrid, nrows, dims, nrbins, plane0, binscale,
+                                                         c.d_thr, c.d_iw, c.d_partial, accumulate ? 1 : 0, tc.C, tc.T, tc.S, tc.stage_bytes,
+                                                         g_k1_k2_single, log2N);
+            return KSN_OK;
+        };
+        int rct;
+        switch (tc.C) {
+        case 5: rct = go(k1_tile_kernel<5>); break;
+        case 9: rct = go(k1_tile_kernel<9>); break;
+        case 13: rct = go(k1_tile_kernel<13>); break;
+        case 17: rct = go(k1_tile_kernel<17>); break;
+        default: rct = go(k1_tile_kernel<0>); break;
+        }
+        if (rct) return rct;
         c.launches++;
         KSN_CUDA(cudaGetLastError());
         snprintf(g_k1_last, sizeof g_k1_last, "k1_tile_kernel (%d warps x %d modes per lane, %d stages, %d tiles per row)", tc.W, tc.C, tc.S, tc.T);

@@ -636,9 +636,11 @@ static size_t k1_tile_smem(int L, int nrbins, int W, int C, int S, int *T_out, i
 
 static int k1_tile_max_warps(int C) { return (C == 5 || C == 9) ? K1T_MAXW : 8; }      // the kernels' launch bounds
 
-// Pick (warps, chunk, stages): as many bytes in flight as shared memory allows (capped: ~128 KB per SM saturates HBM),
-// little of a row's last tile wasted, at least 4 warps.  KSN_K1_TILE="W,C,S" overrides.
-static bool k1_tile_config(int L, int nrbins, size_t budget, K1TileCfg *best)
+// Pick (warps, chunk, stages).  The walk is bound by per-warp latency, not by issue slots or (yet) by HBM, so throughput
+// goes as warps x C/(C+10) (the per-tile bookkeeping costs about ten modes' worth) -- fitted to probes at 1024^3, 2048^3
+// and 4096^3 slabs (tools/k1_tile_probe.py); shared memory (bins: 8 nrbins bytes per warp) decides how many warps fit.
+// KSN_K1_TILE="W,C,S" overrides.
+static bool k1_tile_config(int L, int nrbins, size_t budget, int ctas, K1TileCfg *best)
 {
     best->W = 0;
     double best_score = -1;
@@ -655,15 +657,13 @@ static bool k1_tile_config(int L, int nrbins, size_t budget, K1TileCfg *best)
                 const int TE = 32 * C;
                 if (T > 1 && C < 5) continue;                             // tiny tiles only for tiny rows
                 const double eff = (double) L / ((double) T * TE);        // lane slots that carry a mode
-                const size_t inflight = (size_t) W * S * TE * 16;
-                const double fl = inflight < (size_t) 131072 ? (double) inflight : 131072.0;
-                double score = eff * fl;
-                if (W >= 8) score *= 1.05;                                // enough warps to hide the shared-memory latency
-                if (TE * 16 >= 4096) score *= 1.05;                       // bulk copies of at least 4 KB
-                if (C <= 17) score *= 1.05;                               // compile-time chunk: weights in registers
+                const bool compile_time = C == 5 || C == 9 || C == 13 || C == 17;
+                double score = W * (C / (C + 10.0)) * eff * (compile_time ? 1.0 : 0.88) * (1.0 + 0.01 * S);
+                if (((long long) ctas * W) % T) score *= 0.97;            // the warp's tile-of-row changes every tile: weights reloaded
                 if (score > best_score) {
                     best_score = score;
-                    best->W = W; best->C = C; best->S = S; best->T = T; best->stage_bytes = stage; best->smem = smem; best->inflight = inflight;
+                    best->W = W; best->C = C; best->S = S; best->T = T; best->stage_bytes = stage; best->smem = smem;
+                    best->inflight = (size_t) W * S * TE * 16;
                 }
             }
     return best->W > 0;
@@ -792,7 +792,7 @@ static int k1_launch_t(const void *dgrid, int dims, int nrbins, long long plane0
     };
     K1TileCfg tc;
     if (!FULL && sizeof(real) == 8 && !getenv("KSN_K1_PAIR") && !getenv("KSN_K1_NOPAIR") && ((uintptr_t) dgrid & 15) == 0 &&
-        k1_tile_config(dims / 2 + 1, nrbins, c.smem_optin, &tc)) {
+        k1_tile_config(dims / 2 + 1, nrbins, c.smem_optin, c.num_sms, &tc)) {
         int log2N = -1;
         if ((dims & (dims - 1)) == 0) { log2N = 0; while ((1 << log2N) < dims) log2N++; }
         auto go = [&](auto kern) -> int {

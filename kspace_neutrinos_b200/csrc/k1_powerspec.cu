@@ -26,6 +26,7 @@
 #include "ksn_internal.cuh"
 
 #include <math.h>
+#include <type_traits>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -401,7 +402,8 @@ k1_pair_kernel(const Cplx<real> *__restrict__ grid, int nrows, int N, int nrbins
 //    lane, which may share its bin with the runs of the lanes before it: those 32 partial sums are combined by one
 //    segmented warp scan per tile.
 constexpr int K1T_MAXW = 16;
-constexpr int K1T_QRUNS = 4;              // queue slots per lane: three closed runs and the open one
+constexpr int K1T_QRUNS = 8;              // queue slots per lane: up to seven closed runs and the open one
+constexpr int K1_WZ_PAD = 32 * 65 + 16;   // zeros behind the z-weight table
 
 __device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
 
@@ -436,22 +438,16 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int C = CT > 0 ? CT : Crt;
-    const int L = N / 2 + 1, nyq = N / 2;
+    const int L = N / 2 + 1;
     const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int TE = 32 * C;                                     // modes per tile
-    const int nwz = T * TE + 8;                                // z-weight table, zero past the row end
+    const double *__restrict__ iwz_g = iw + L;                 // m_z * iwz^4 (Hermitian multiplicity folded in), zeros past the row end
     unsigned char *sp = smem_raw;
     unsigned char *stages = sp;                   sp += (size_t) W * S * stage_bytes;
-    double *iwz_s = (double *) sp;                sp += (size_t) nwz * sizeof(double);
     double *bins_s = (double *) sp;               sp += (size_t) W * nrbins * sizeof(double);
     double *queue_s = (double *) sp;              sp += (size_t) W * K1T_QRUNS * 32 * sizeof(double);
     unsigned long long *bars = (unsigned long long *) sp;  sp += (size_t) W * S * sizeof(unsigned long long);
-    unsigned *thr_s = (unsigned *) sp;                      // nrbins + 3
-    for (int i = threadIdx.x; i < nwz; i += blockDim.x) {      // m_z * iwz^4 (Hermitian multiplicity folded in)
-        double v = 0.0;
-        if (i < L) { const double w2 = iw[i] * iw[i]; v = ((i == 0 || i == nyq) ? 1.0 : 2.0) * (w2 * w2); }
-        iwz_s[i] = v;
-    }
+    unsigned *thr_s = (unsigned *) sp;                      // nrbins + 3, padded with "never"
     for (int i = threadIdx.x; i < nrbins + 3; i += blockDim.x) thr_s[i] = i < nrbins ? thr[i] : 0xffffffffu;
     for (int i = threadIdx.x; i < W * nrbins; i += blockDim.x) bins_s[i] = 0.0;
     // the stages start as zeros: modes past a row's end are walked like any other (weight 0), so they must be finite
@@ -489,6 +485,17 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
         if (ti >= T) { ti -= T; ri++; }
     }
 
+    // A lane's FIRST run may share its bin with the runs of the lanes before it (everything else hits bins no other lane
+    // touches, because bins are monotone along a row): one segmented scan over the 32 first runs per tile.  The scan of
+    // tile k is issued together with the set-up arithmetic of tile k+1, so that the two latency chains overlap.
+    int p_fbin = 0x7fffffff;               // previous tile's first-run bin / sum / row factor (none yet)
+    double p_facc = 0.0, p_wxy = 0.0;
+    auto merge_first_runs = [&]() {
+        double v1[1] = { p_facc };
+        const unsigned tails = segmented_sum<1>(p_fbin, v1, lane, le_mask);
+        if (((tails >> lane) & 1u) && p_fbin != 0x7fffffff) mybins[p_fbin] = fma(v1[0], p_wxy, mybins[p_fbin]);
+        __syncwarp();
+    };
     double wreg[CT > 0 ? CT : 1];
     int t_loaded = -1;
     unsigned phases = 0;
@@ -508,17 +515,18 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
         b += (k2 >= thr_s[b + 1]) - (k2 < thr_s[b]);
         const int fbin = b;
         unsigned nxt = thr_s[b + 1];
-        unsigned n2 = thr_s[b + 2], n3 = thr_s[b + 3];
         // bin of the chunk's last mode: a lane that would close more than three runs cannot use the register window
         const unsigned k2e = (unsigned) c + (unsigned) (zl + C - 1) * (unsigned) (zl + C - 1);
         int be = min(max((int) (binscale * fast_log2((float) k2e)), 0), nrbins - 1);
         be += (k2e >= thr_s[be + 1]) - (k2e < thr_s[be]);
-        const bool fast = __all_sync(0xffffffffu, be - fbin <= K1T_QRUNS - 1) && (unsigned) c + (unsigned) z0 * (unsigned) z0 >= k2_single;
+        const int spread = __reduce_max_sync(0xffffffffu, be - fbin);      // most runs any lane will close in this tile
+        const bool single = (unsigned) c + (unsigned) z0 * (unsigned) z0 >= k2_single;
+        merge_first_runs();                                            // of the previous tile
         const Cplx<double> *chunk = (const Cplx<double> *) (mystage + (size_t) s * stage_bytes) + lane * C;
-        const double *wz = iwz_s + zl;
+        const double *wz = iwz_g + zl;
         if (CT > 0 && t != t_loaded) {             // (a warp keeps the same tile-of-row whenever T divides its stride)
 #pragma unroll
-            for (int e = 0; e < (CT > 0 ? CT : 1); e++) wreg[e] = wz[e];
+            for (int e = 0; e < (CT > 0 ? CT : 1); e++) wreg[e] = __ldg(wz + e);
             t_loaded = t;
         }
         const double worigin = (c == 0 && zl == 0) ? 0.0 : 1.0;        // F(0,0,0) is the mean, not a mode: weight 0
@@ -527,16 +535,25 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
         const double q1 = wa * wb, q2 = q1 * q1, wxy = q2 * q2;        // (iwx iwy)^4, applied once per run
 
         double acc = 0.0, facc;
-        if (fast) {
+        // FAST tiles: one mode crosses at most one bin threshold (so run i of a lane is bin fbin+i) and no lane closes more
+        // than R-1 runs (so the thresholds it will meet sit in R-1 registers): the walk has no branch and no dependent
+        // load; a closed run is pushed onto the lane's queue by one predicated store.  R = 4 for most tiles, 8 near the
+        // k_x = k_y = 0 axis where bins are narrow along z.
+        auto fast_walk = [&](auto RT) {
+            constexpr int R = decltype(RT)::value;
+            unsigned nx[R - 1];
+            nx[0] = nxt;
+#pragma unroll
+            for (int i = 1; i < R - 1; i++) nx[i] = thr_s[min(b + 1 + i, nrbins + 2)];
             unsigned qa = q0;
             auto step = [&](const Cplx<double> v, double w) {
                 const double pp = fma(v.im, v.im, v.re * v.re);
-                const bool ch = k2 >= nxt;
+                const bool ch = k2 >= nx[0];
                 queue_push_if(ch, qa, acc);
                 qa += ch ? 256u : 0u;
-                nxt = ch ? n2 : nxt;
-                n2 = ch ? n3 : n2;
-                n3 = ch ? 0xffffffffu : n3;
+#pragma unroll
+                for (int i = 0; i < R - 2; i++) nx[i] = ch ? nx[i + 1] : nx[i];
+                nx[R - 2] = ch ? 0xffffffffu : nx[R - 2];
                 acc = ch ? 0.0 : acc;
                 acc = fma(pp, w, acc);
                 k2 += dz;
@@ -550,14 +567,14 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
                 Cplx<double> vc[4];
                 double wc[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) { vc[u] = chunk[u]; wc[u] = wz[u]; }
+                for (int u = 0; u < 4; u++) { vc[u] = chunk[u]; wc[u] = __ldg(wz + u); }
                 wc[0] *= worigin;
 #pragma unroll 2
                 for (int e = 0; e + 4 < C; e += 4) {           // C = 4q+1: q blocks of four, then one mode
                     Cplx<double> vn[4];
                     double wn[4];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) { vn[u] = chunk[e + 4 + u]; wn[u] = wz[e + 4 + u]; }
+                    for (int u = 0; u < 4; u++) { vn[u] = chunk[e + 4 + u]; wn[u] = __ldg(wz + e + 4 + u); }
 #pragma unroll
                     for (int u = 0; u < 4; u++) step(vc[u], wc[u]);
 #pragma unroll
@@ -569,11 +586,21 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
             // the stage is consumed: put the next bulk copy in flight before the bookkeeping below
             __syncwarp();
             if (lane == 0 && ri < nrows) issue(ri, ti, s);
-            const int cnt = (int) ((qa - q0) >> 8) + 1;
-            const int maxcnt = __reduce_max_sync(0xffffffffu, cnt);
-            for (int i = 1; i < maxcnt; i++)
-                if (i < cnt) mybins[fbin + i] = fma(queue_get(q0 + 256u * i), wxy, mybins[fbin + i]);
+            // drain: run i >= 1 of this lane is bin fbin+i, and nobody else's (loads first, then the updates)
+            const int closed = (int) ((qa - q0) >> 8);
+            double g[R - 1], m[R - 1];
+#pragma unroll
+            for (int i = 1; i < R; i++)
+                if (i <= closed) { g[i - 1] = queue_get(q0 + 256u * i); m[i - 1] = mybins[fbin + i]; }
+#pragma unroll
+            for (int i = 1; i < R; i++)
+                if (i <= closed) mybins[fbin + i] = fma(g[i - 1], wxy, m[i - 1]);
             facc = queue_get(q0);
+        };
+        if (single && spread <= 3) {
+            fast_walk(std::integral_constant<int, 4>());
+        } else if (single && spread <= K1T_QRUNS - 1) {
+            fast_walk(std::integral_constant<int, K1T_QRUNS>());
         } else {
             // GENERAL tile (the low-k corner, where bins are narrower than a step in k^2): finished runs go straight to the bins
             facc = 0.0;
@@ -588,28 +615,22 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
                 k2 += dz;
                 dz += 2u;
             };
-            step(chunk[0], wz[0] * worigin);
+            step(chunk[0], __ldg(wz) * worigin);
 #pragma unroll 1
-            for (int e = 1; e < C; e++) step(chunk[e], wz[e]);
+            for (int e = 1; e < C; e++) step(chunk[e], __ldg(wz + e));
             if (b == fbin) facc = acc; else mybins[b] = fma(acc, wxy, mybins[b]);
             __syncwarp();
             if (lane == 0 && ri < nrows) issue(ri, ti, s);
         }
-        // A lane's FIRST run may share its bin with the runs of the lanes before it (everything else above hit bins no
-        // other lane touches, because bins are monotone along a row): one segmented scan over the 32 first runs.
-        {
-            double v1[1] = { facc };
-            const unsigned tails = segmented_sum<1>(fbin, v1, lane, le_mask);
-            __syncwarp();
-            if ((tails >> lane) & 1u) mybins[fbin] = fma(v1[0], wxy, mybins[fbin]);
-        }
         __syncwarp();                                                  // every lane is done with the bins
+        p_fbin = fbin; p_facc = facc; p_wxy = wxy;                     // merged at the top of the next tile
         ri += dr; ti += dt;
         if (ti >= T) { ti -= T; ri++; }
         r += dr; t += dt;
         if (t >= T) { t -= T; r++; }
         s = s + 1 == S ? 0 : s + 1;
     }
+    merge_first_runs();                                                // of the last tile
     __syncthreads();
     double *out = partial + (size_t) blockIdx.x * nrbins;
     for (int i = threadIdx.x; i < nrbins; i += blockDim.x) {
@@ -630,8 +651,8 @@ static size_t k1_tile_smem(int L, int nrbins, int W, int C, int S, int *T_out, i
     const int stage = (int) ((((size_t) TE + 8) * 16 + 127) & ~(size_t) 127);
     if (T_out) *T_out = T;
     if (stage_out) *stage_out = stage;
-    return (size_t) W * S * stage + ((size_t) T * TE + 8) * 8 + (size_t) W * nrbins * 8 + (size_t) W * K1T_QRUNS * 32 * 8 +
-           (size_t) W * S * 8 + (size_t) (nrbins + 3) * 4 + 128;
+    return (size_t) W * S * stage + (size_t) W * nrbins * 8 + (size_t) W * K1T_QRUNS * 32 * 8 + (size_t) W * S * 8 +
+           (size_t) (nrbins + 3 + K1T_QRUNS) * 4 + 128;
 }
 
 static int k1_tile_max_warps(int C) { return (C == 5 || C == 9) ? K1T_MAXW : 8; }      // the kernels' launch bounds
@@ -870,8 +891,21 @@ static int k1_upload_tables(int dims, int nrbins, const unsigned int *thresholds
     const int L = dims / 2 + 1;
     int rc = ensure_device_buffer((void **) &c.d_thr, &c.thr_cap, (size_t) nrbins * sizeof(unsigned));
     if (rc) return rc;
-    rc = ensure_device_buffer((void **) &c.d_iw, &c.iw_cap, (size_t) L * sizeof(double));
+    // d_iw = [ iw[0..L) | m_z iw[z]^4 for z in [0, L), then K1_WZ_PAD zeros (lanes walk past the row end with weight 0) ]
+    rc = ensure_device_buffer((void **) &c.d_iw, &c.iw_cap, (size_t) (2 * L + K1_WZ_PAD) * sizeof(double));
     if (rc) return rc;
+    {
+        double *wz = (double *) calloc((size_t) L + K1_WZ_PAD, sizeof(double));
+        if (!wz) return set_error(KSN_ENOMEM, "K1: out of host memory");
+        for (int z = 0; z < L; z++) {
+            const double w2 = invwin[z] * invwin[z];
+            wz[z] = ((z == 0 || z == dims / 2) ? 1.0 : 2.0) * (w2 * w2);      // Hermitian multiplicity folded in
+        }
+        const cudaError_t e = cudaMemcpyAsync(c.d_iw + L, wz, ((size_t) L + K1_WZ_PAD) * sizeof(double), cudaMemcpyHostToDevice, c.stream);
+        if (e == cudaSuccess) cudaStreamSynchronize(c.stream);
+        free(wz);
+        KSN_CUDA(e);
+    }
     KSN_CUDA(cudaMemcpyAsync(c.d_thr, thresholds, (size_t) nrbins * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
     KSN_CUDA(cudaMemcpyAsync(c.d_iw, invwin, (size_t) L * sizeof(double), cudaMemcpyHostToDevice, c.stream));
     rc = ensure_device_buffer((void **) &c.d_red, &c.red_cap, (size_t) (3 * nrbins + 1) * sizeof(double));

@@ -8,7 +8,7 @@ from kspace_neutrinos_b200 import capi
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 cfgs = sys.argv[2:] or ["auto"]
 nslab = int(os.environ.get("KSN_PROBE_NSLAB", n))          # planes of the slab held by this GPU (N=4096: 512 = one of 8 GPUs)
-nrbins = n // 2; nel = nslab * n * (n // 2 + 1)
+nrbins = int(os.environ.get("KSN_PROBE_NRBINS", n // 2)); nel = nslab * n * (n // 2 + 1)
 L = capi.lib(); capi.check(L.ksn_init(-1)); L.ksn_set_quiet(1)
 ptr = C.c_void_p(); capi.check(L.ksn_device_malloc(C.byref(ptr), nel * 16))
 capi.check(L.ksn_fill_synthetic_grid(ptr, 8, n, 0, nslab, 1, -1.0))

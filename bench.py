@@ -305,7 +305,9 @@ def ours(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(f"k3_{n}")
+            traffic = json.load(f).get(f"k3_{n}")            # one launch over the whole grid (ncu, N=1)
+        if traffic is not None:
+            traffic = traffic * local_modes / modes_total   # a launch on this rank's slab
     except (OSError, ValueError):
         pass
     roofline = {"bound": "hbm", "kernel": "k3_scale_tma_kernel<double> (read-modify-write, 32 B per stored mode)",

@@ -190,3 +190,51 @@ def test_tile_pair_and_full_kernels_agree(gpu, n, start, nslab, tile, monkeypatc
     np.testing.assert_allclose(tl[0][live], full[0][live], rtol=2e-13)
     np.testing.assert_allclose(pair[0][live], full[0][live], rtol=2e-13)
     assert tl[3] == full[3] == pair[3]
+
+
+def test_host_grid_staged_in_chunks_matches_device_grid(gpu):
+    """A host-resident slab larger than one 256 MB staging chunk: K1 runs on each chunk as it lands and accumulates
+    into the same per-CTA partials; the sums must equal the device-resident sweep of the same bytes."""
+    from kspace_neutrinos_b200 import capi
+    n, nrbins, nslab = 512, 256, 320                  # 320 planes x 2.1 MB = 673 MB -> 3 chunks
+    nbytes = nslab * n * (n // 2 + 1) * 16
+    ptr = C.c_void_p()
+    capi.check(gpu.ksn_device_malloc(C.byref(ptr), nbytes))
+    capi.check(gpu.ksn_fill_synthetic_grid(ptr, 8, n, 100, nslab, 7, -1.0))
+    host = np.empty((nslab, n, n // 2 + 1, 2))
+    capi.check(gpu.ksn_memcpy_d2h(host.ctypes.data_as(C.c_void_p), ptr, nbytes))
+    _sums(gpu, host, nrbins, 100, nslab, pointer=ptr)                 # geometry
+    dev = _sums(gpu, host, nrbins, 100, nslab, pointer=ptr)
+    hst = _sums(gpu, host, nrbins, 100, nslab, pointer=host.ctypes.data_as(C.c_void_p))
+    gpu.ksn_device_free(ptr)
+    assert np.array_equal(dev[2], hst[2])
+    live = dev[0] != 0
+    np.testing.assert_allclose(hst[0][live], dev[0][live], rtol=1e-13)
+
+
+def test_full_size_slabs_kernels_agree(gpu):
+    """At the PMGRID of BASELINE configs 4 and 5 (2048, 4096), on slabs as one of 8 GPUs would hold them (a few planes
+    here): the tile kernel against the scan-based kernel, and the multiplicity-weighted mode count of the slab."""
+    from kspace_neutrinos_b200 import capi
+    import os
+    for n, start, nslab in ((2048, 1000, 24), (4096, 2040, 12), (4096, 0, 6)):
+        nrbins = n // 2
+        nbytes = nslab * n * (n // 2 + 1) * 16
+        ptr = C.c_void_p()
+        capi.check(gpu.ksn_device_malloc(C.byref(ptr), nbytes))
+        capi.check(gpu.ksn_fill_synthetic_grid(ptr, 8, n, start, nslab, 11, -1.0))
+        shape = np.empty((nslab, n, 1, 1))
+        first = _sums(gpu, shape, nrbins, start, nslab, pointer=ptr)
+        tile = _sums(gpu, shape, nrbins, start, nslab, pointer=ptr)
+        assert b"k1_tile_kernel" in gpu.ksn_last_k1_kernel()
+        os.environ["KSN_K1_PAIR"] = "1"
+        try:
+            pair = _sums(gpu, shape, nrbins, start, nslab, pointer=ptr)
+        finally:
+            del os.environ["KSN_K1_PAIR"]
+        gpu.ksn_device_free(ptr)
+        # every stored mode counted with its Hermitian multiplicity: N per (x, y) pair, minus the mean
+        assert first[2].sum() == nslab * n * n - (1 if start == 0 else 0)
+        live = first[0] != 0
+        np.testing.assert_allclose(tile[0][live], first[0][live], rtol=2e-13)
+        np.testing.assert_allclose(pair[0][live], first[0][live], rtol=2e-13)

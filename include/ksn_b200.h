@@ -110,6 +110,20 @@ int ksn_step_staged(void *hgrid, int real_bytes, int dims, int nrbins, long long
                     const unsigned int *thresholds, const double *invwin, double boxsize,
                     ksn_between_fn between, void *user);
 
+/* ---- K3 fused with the PM Green's function -------------------------------------
+ * A Gadget-style PM step multiplies the same grid, right after the neutrino correction, by the periodic Green's
+ * function with CIC deconvolution (Gadget-2 pm_periodic.c, the loop following the hook of gadget-2/0002
+ * patch:116-125):  G(k) = -exp(-k2*asmth2)/k2 * (iwx iwy iwz)^4, F(0,0,0) = 0, k2 in grid units, iw(q) = 1/sinc(pi q/N),
+ * asmth2 = (2 pi Asmth / BoxSize)^2.  These entries apply (1 + norm*interp) * G in ONE pass, which saves the host's own
+ * read-modify-write traversal (32 B per mode).  invwin: iw[0..dims/2], as for ksn_powerspectrum_sums. */
+int ksn_scale_modes_greens(void *grid, int real_bytes, int dims, long long startslab, long long nslab, double boxsize,
+                           const double *logkk, const double *ratio, int nbins, double norm,
+                           const double *invwin, double asmth2);
+int ksn_step_staged_greens(void *hgrid, int real_bytes, int dims, int nrbins, long long startslab, long long nslab,
+                           const unsigned int *thresholds, const double *invwin, double boxsize,
+                           ksn_between_fn between, void *user, double asmth2);
+
+
 /* ---- K2: linear-response integral (delta_tot_table.c:507-611) ----------------------- */
 typedef struct ksn_delta_nu_args {
     int nk;                    /* k bins */

@@ -229,6 +229,10 @@ int total_powerspectrum_f64(const int dims, void *outfield, const int nrbins, co
 int total_powerspectrum_f32(const int dims, void *outfield, const int nrbins, const int startslab, const int nslab, double *power, long long int *count, double *keffs, const MPI_Comm MYMPI_COMM_WORLD);
 void add_nu_power_to_rhogrid_f64(const double Time, const double BoxSize, void *fft_of_rhogrid, const int pmgrid, int slabstart_y, int nslab_y, MPI_Comm MYMPI_COMM_WORLD);
 void add_nu_power_to_rhogrid_f32(const double Time, const double BoxSize, void *fft_of_rhogrid, const int pmgrid, int slabstart_y, int nslab_y, MPI_Comm MYMPI_COMM_WORLD);
+/* Extension, not in the reference: the neutrino correction and the PM Green's function that follows it in
+ * pmforce_periodic (gadget-2/0002 patch:116-125 context), in one pass over the grid.  asmth2 = (2 pi Asmth / BoxSize)^2. */
+void add_nu_power_and_greens_to_rhogrid_f64(const double Time, const double BoxSize, void *fft_of_rhogrid, const int pmgrid, int slabstart_y, int nslab_y, const double asmth2, MPI_Comm MYMPI_COMM_WORLD);
+void add_nu_power_and_greens_to_rhogrid_f32(const double Time, const double BoxSize, void *fft_of_rhogrid, const int pmgrid, int slabstart_y, int nslab_y, const double asmth2, MPI_Comm MYMPI_COMM_WORLD);
 void compute_total_power_spectrum_f64(const double Time, const double BoxSize, void *fft_of_rhogrid, const int pmgrid, int slabstart_y, int nslab_y, MPI_Comm MYMPI_COMM_WORLD);
 void compute_total_power_spectrum_f32(const double Time, const double BoxSize, void *fft_of_rhogrid, const int pmgrid, int slabstart_y, int nslab_y, MPI_Comm MYMPI_COMM_WORLD);
 
@@ -243,6 +247,8 @@ void compute_total_power_spectrum_f32(const double Time, const double BoxSize, v
 /* interface_gadget.h:48 */
 #define compute_total_power_spectrum(Time, BoxSize, grid, pmgrid, slabstart_y, nslab_y, comm) \
     compute_total_power_spectrum_f64(Time, BoxSize, (fftw_complex *) (grid), pmgrid, slabstart_y, nslab_y, comm)
+#define add_nu_power_and_greens_to_rhogrid(Time, BoxSize, grid, pmgrid, slabstart_y, nslab_y, asmth2, comm) \
+    add_nu_power_and_greens_to_rhogrid_f64(Time, BoxSize, (fftw_complex *) (grid), pmgrid, slabstart_y, nslab_y, asmth2, comm)
 #else
 #define total_powerspectrum(dims, outfield, nrbins, startslab, nslab, power, count, keffs, comm) \
     total_powerspectrum_f32(dims, (fftw_complex *) (outfield), nrbins, startslab, nslab, power, count, keffs, comm)
@@ -250,6 +256,8 @@ void compute_total_power_spectrum_f32(const double Time, const double BoxSize, v
     add_nu_power_to_rhogrid_f32(Time, BoxSize, (fftw_complex *) (grid), pmgrid, slabstart_y, nslab_y, comm)
 #define compute_total_power_spectrum(Time, BoxSize, grid, pmgrid, slabstart_y, nslab_y, comm) \
     compute_total_power_spectrum_f32(Time, BoxSize, (fftw_complex *) (grid), pmgrid, slabstart_y, nslab_y, comm)
+#define add_nu_power_and_greens_to_rhogrid(Time, BoxSize, grid, pmgrid, slabstart_y, nslab_y, asmth2, comm) \
+    add_nu_power_and_greens_to_rhogrid_f32(Time, BoxSize, (fftw_complex *) (grid), pmgrid, slabstart_y, nslab_y, asmth2, comm)
 #endif
 #endif
 

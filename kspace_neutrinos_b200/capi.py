@@ -103,8 +103,12 @@ PROTOTYPES = {
                                          C.POINTER(C.c_uint), c_double_p, c_double_p, c_double_p, c_longlong_p, c_double_p]),
     "ksn_scale_modes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.c_double,
                                   c_double_p, c_double_p, C.c_int, C.c_double]),
+    "ksn_scale_modes_greens": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.c_double,
+                                        c_double_p, c_double_p, C.c_int, C.c_double, c_double_p, C.c_double]),
     "ksn_step_staged": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_longlong,
                                   C.POINTER(C.c_uint), c_double_p, C.c_double, C.c_void_p, C.c_void_p]),
+    "ksn_step_staged_greens": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_longlong,
+                                         C.POINTER(C.c_uint), c_double_p, C.c_double, C.c_void_p, C.c_void_p, C.c_double]),
     "ksn_delta_nu_integrate": (C.c_int, [C.POINTER(DeltaNuArgs), c_double_p, C.POINTER(C.c_ulonglong)]),
     "ksn_last_k1_kernel": (C.c_char_p, []),
     "ksn_last_k2_evals": (C.c_ulonglong, []),
@@ -171,6 +175,8 @@ for _name in ("total_powerspectrum", "total_powerspectrum_f64", "total_powerspec
 for _name in ("add_nu_power_to_rhogrid", "add_nu_power_to_rhogrid_f64", "add_nu_power_to_rhogrid_f32",
               "compute_total_power_spectrum", "compute_total_power_spectrum_f64", "compute_total_power_spectrum_f32"):
     PROTOTYPES[_name] = (None, [C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int])
+for _name in ("add_nu_power_and_greens_to_rhogrid_f64", "add_nu_power_and_greens_to_rhogrid_f32"):
+    PROTOTYPES[_name] = (None, [C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int])
 # helpers exported for stand-alone use (src/ksn_host.h)
 PROTOTYPES["ksn_set_default_hubble"] = (None, [C.POINTER(OmegaNu), C.c_double, C.c_double])
 PROTOTYPES["ksn_set_quiet"] = (None, [C.c_int])

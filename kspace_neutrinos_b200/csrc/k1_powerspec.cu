@@ -403,7 +403,6 @@ k1_pair_kernel(const Cplx<real> *__restrict__ grid, int nrows, int N, int nrbins
 //    segmented warp scan per tile.
 constexpr int K1T_MAXW = 16;
 constexpr int K1T_QRUNS = 8;              // queue slots per lane: up to seven closed runs and the open one
-constexpr int K1_WZ_PAD = 32 * 65 + 16;   // zeros behind the z-weight table
 
 __device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
 

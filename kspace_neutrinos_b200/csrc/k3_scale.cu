@@ -62,6 +62,30 @@ __device__ __forceinline__ float fast_log2(float x)
 // per-knot record
 struct __align__(16) K3Seg { double K2, inv, A, B; };
 
+// Optional second factor: the periodic PM Green's function with CIC deconvolution that a Gadget-style PM step applies
+// to the same grid right after the neutrino correction (Gadget-2 pm_periodic.c, the loop that follows the hook of
+// gadget-2/0002 patch:116-125):  G(k) = -exp(-k2*asmth2)/k2 * (iwx iwy iwz)^4,  G(0) = 0,  iw(q) = 1/sinc(pi q/N).
+// Fusing it into K3 saves the host's own read-modify-write pass over the grid (32 B per mode).
+struct K3Greens {
+    int on;
+    double asmth2;
+    const double *iw;   // device: 1-D inverse CIC window, q = 0..N/2 (the table K1 uses)
+};
+
+__device__ __forceinline__ double k3_greens(const K3Greens &gr, int k2i, double wxy4, int z)
+{
+    const double w = __ldg(gr.iw + z), w2 = w * w;
+    const double k2 = (double) k2i;
+    return -exp(-k2 * gr.asmth2) / k2 * (wxy4 * (w2 * w2));
+}
+
+__device__ __forceinline__ double k3_row_window4(const K3Greens &gr, int ki, int kj)
+{
+    const double a = __ldg(gr.iw + (ki < 0 ? -ki : ki)), b = __ldg(gr.iw + (kj < 0 ? -kj : kj));
+    const double q = a * b, q2 = q * q;
+    return q2 * q2;
+}
+
 struct K3Params {
     int n;            // knots
     int cells;        // lookup cells in log2(k2); the host sizes them so that no cell holds two knots
@@ -100,7 +124,7 @@ __device__ __forceinline__ double k3_factor(int k2i, const K3Seg *__restrict__ s
 template <typename real, int U>
 __global__ void __launch_bounds__(K3_THREADS)
 k3_scale_kernel(C2<real> *__restrict__ grid, int nrows, int rows_per_cta, int N, long long plane0,
-                const double *__restrict__ tab, const K3Params prm)
+                const double *__restrict__ tab, const K3Params prm, const K3Greens gr)
 {
     const K3Seg *seg = (const K3Seg *) tab;
     const unsigned short *cellv = (const unsigned short *) (seg + prm.n + 1);
@@ -128,8 +152,9 @@ k3_scale_kernel(C2<real> *__restrict__ grid, int nrows, int rows_per_cta, int N,
             const int ki = gi <= N / 2 ? (int) gi : (int) (gi - N);
             const int kj = j <= N / 2 ? j : j - N;
             const int k2i = ki * ki + kj * kj + z * z;
-            if (k2i == 0) continue;                              // F(0,0,0) is skipped (interface_gadget.c:174)
-            const double smth = k3_factor<real>(k2i, seg, cellv, prm);
+            if (k2i == 0 && !gr.on) continue;                    // F(0,0,0) is skipped (interface_gadget.c:174)
+            double smth = k2i > 0 ? k3_factor<real>(k2i, seg, cellv, prm) : 0.0;
+            if (gr.on && k2i > 0) smth *= k3_greens(gr, k2i, k3_row_window4(gr, ki, kj), z);   // the mean is zeroed
             C2<real> o;
             o.re = (real) ((double) v[u].re * smth);
             o.im = (real) ((double) v[u].im * smth);
@@ -152,7 +177,7 @@ __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned) 
 template <typename real, bool ONE_ROW>
 __global__ void __launch_bounds__(K3_TMA_THREADS, 8)
 k3_scale_tma_kernel(C2<real> *__restrict__ grid, int nrows, int rows_per_cta, int N, long long plane0,
-                    const double *__restrict__ tab, const K3Params prm)
+                    const double *__restrict__ tab, const K3Params prm, const K3Greens gr)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
@@ -173,28 +198,40 @@ k3_scale_tma_kernel(C2<real> *__restrict__ grid, int nrows, int rows_per_cta, in
                      ::"r"(smem_u32(buf)), "l"(base), "r"(bytes), "r"(smem_u32(&bar)) : "memory");
     }
     // factors while the copy is in flight
-    auto row_c = [&](int r) {                // kx^2 + ky^2 of grid row r
+    auto row_k = [&](int r, int &ki, int &kj) {
         const int pl = r / N, j = r - pl * N;
         const long long gi = plane0 + pl;
-        const int ki = gi <= N / 2 ? (int) gi : (int) (gi - N);
-        const int kj = j <= N / 2 ? j : j - N;
+        ki = gi <= N / 2 ? (int) gi : (int) (gi - N);
+        kj = j <= N / 2 ? j : j - N;
+    };
+    auto row_c = [&](int r) {                // kx^2 + ky^2 of grid row r
+        int ki, kj;
+        row_k(r, ki, kj);
         return ki * ki + kj * kj;
     };
     const int c0 = row_c(row0);              // CTA-uniform: the only row when ONE_ROW
+    double w0 = 1.0;                         // (iwx iwy)^4 of that row, for the Green's function
+    if (gr.on && ONE_ROW) { int ki, kj; row_k(row0, ki, kj); w0 = k3_row_window4(gr, ki, kj); }
     double smth[K3_EPT];
 #pragma unroll
     for (int k = 0; k < K3_EPT; k++) {
         const int e = threadIdx.x + K3_TMA_THREADS * k;
         smth[k] = 1.0;
         if (e < nel) {
-            int k2i;
+            int k2i, z = e;
+            double wxy4 = w0;
             if (ONE_ROW) {
                 k2i = c0 + e * e;
             } else {
-                const int rl = e / L, z = e - rl * L;
-                k2i = row_c(row0 + rl) + z * z;
+                const int rl = e / L;
+                z = e - rl * L;
+                int ki, kj;
+                row_k(row0 + rl, ki, kj);
+                k2i = ki * ki + kj * kj + z * z;
+                if (gr.on) wxy4 = k3_row_window4(gr, ki, kj);
             }
-            if (k2i > 0) smth[k] = k3_factor<real>(k2i, seg, cellv, prm);     // F(0,0,0) keeps factor 1
+            if (k2i > 0) smth[k] = k3_factor<real>(k2i, seg, cellv, prm);     // F(0,0,0) keeps factor 1 ...
+            if (gr.on) smth[k] = k2i > 0 ? smth[k] * k3_greens(gr, k2i, wxy4, z) : 0.0;   // ... or is zeroed with the potential
         }
     }
     __syncthreads();                       // the barrier was initialised before anyone polls it
@@ -276,10 +313,29 @@ int k3_upload_table(int dims, double boxsize, const double *logkk, const double 
     return KSN_OK;
 }
 
+static K3Greens g_k3greens = { 0, 0.0, nullptr };
+
+// Switch the fused Green's function on (invwin: host table iw[0..N/2], as K1 takes it) or off (invwin == nullptr).
+static int k3_set_greens(int dims, const double *invwin, double asmth2)
+{
+    g_k3greens.on = 0;
+    if (!invwin) return KSN_OK;
+    Ctx &c = ctx();
+    const size_t L = (size_t) dims / 2 + 1;
+    int rc = ensure_device_buffer((void **) &c.d_iw, &c.iw_cap, (2 * L + K1_WZ_PAD) * sizeof(double));   // K1's layout: iw | z weights
+    if (rc) return rc;
+    KSN_CUDA(cudaMemcpyAsync(c.d_iw, invwin, L * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    g_k3greens.on = 1;
+    g_k3greens.asmth2 = asmth2;
+    g_k3greens.iw = c.d_iw;
+    return KSN_OK;
+}
+
 int k3_launch(void *dgrid, int real_bytes, int dims, long long plane0_global, long long nplanes, int nknots)
 {
     (void) nknots;
     Ctx &c = ctx();
+    const K3Greens gr = g_k3greens;
     if (nplanes * dims > 0x7fffffffLL) return set_error(KSN_EINVAL, "K3: %lld rows in one slab", nplanes * dims);
     const int nrows = (int) (nplanes * dims);
     if (nrows == 0) return KSN_OK;
@@ -295,7 +351,7 @@ int k3_launch(void *dgrid, int real_bytes, int dims, long long plane0_global, lo
         auto go = [&](auto kern) -> int {
             KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
             KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 58));   // ~132 of 228 KB: L1 keeps the tables
-            kern<<<nct, K3_TMA_THREADS, smem, c.stream>>>((C2<double> *) dgrid, nrows, rpc, dims, plane0_global, c.d_k3tab, g_k3prm);
+            kern<<<nct, K3_TMA_THREADS, smem, c.stream>>>((C2<double> *) dgrid, nrows, rpc, dims, plane0_global, c.d_k3tab, g_k3prm, gr);
             return KSN_OK;
         };
         const int rcl = rpc == 1 ? go(k3_scale_tma_kernel<double, true>) : go(k3_scale_tma_kernel<double, false>);
@@ -308,9 +364,9 @@ int k3_launch(void *dgrid, int real_bytes, int dims, long long plane0_global, lo
     const int rows_per_cta = L >= K3_THREADS * U ? 1 : (K3_THREADS * U) / L;
     const int ctas = (nrows + rows_per_cta - 1) / rows_per_cta;
     if (real_bytes == 8)
-        k3_scale_kernel<double, U><<<ctas, K3_THREADS, 0, c.stream>>>((C2<double> *) dgrid, nrows, rows_per_cta, dims, plane0_global, c.d_k3tab, g_k3prm);
+        k3_scale_kernel<double, U><<<ctas, K3_THREADS, 0, c.stream>>>((C2<double> *) dgrid, nrows, rows_per_cta, dims, plane0_global, c.d_k3tab, g_k3prm, gr);
     else
-        k3_scale_kernel<float, U><<<ctas, K3_THREADS, 0, c.stream>>>((C2<float> *) dgrid, nrows, rows_per_cta, dims, plane0_global, c.d_k3tab, g_k3prm);
+        k3_scale_kernel<float, U><<<ctas, K3_THREADS, 0, c.stream>>>((C2<float> *) dgrid, nrows, rows_per_cta, dims, plane0_global, c.d_k3tab, g_k3prm, gr);
     c.launches++;
     KSN_CUDA(cudaGetLastError());
     return KSN_OK;
@@ -370,8 +426,9 @@ static int check_table(const double *logkk, const double *ratio, int nbins, doub
     return KSN_OK;
 }
 
-extern "C" int ksn_scale_modes(void *grid, int real_bytes, int dims, long long startslab, long long nslab,
-                               double boxsize, const double *logkk, const double *ratio, int nbins, double norm)
+static int scale_modes_impl(void *grid, int real_bytes, int dims, long long startslab, long long nslab,
+                            double boxsize, const double *logkk, const double *ratio, int nbins, double norm,
+                            const double *invwin, double asmth2)
 {
     int rc = ensure_init();
     if (rc) return rc;
@@ -384,6 +441,9 @@ extern "C" int ksn_scale_modes(void *grid, int real_bytes, int dims, long long s
     Ctx &c = ctx();
     rc = k3_upload_table(dims, boxsize, logkk, ratio, nbins, norm);
     if (rc) return rc;
+    rc = k3_set_greens(dims, invwin, asmth2);
+    if (rc) return rc;
+    struct GreensOff { ~GreensOff() { g_k3greens.on = 0; } } greens_off;     // whatever happens below, the switch does not outlive this call
     if (ksn_pointer_is_device(grid)) {
         phase_begin(PH_K3);
         rc = k3_launch(grid, real_bytes, dims, startslab, nslab, nbins);
@@ -405,9 +465,23 @@ extern "C" int ksn_scale_modes(void *grid, int real_bytes, int dims, long long s
     return k3_over_staged_grid(grid, real_bytes, dims, startslab, nslab, nbins);
 }
 
-extern "C" int ksn_step_staged(void *hgrid, int real_bytes, int dims, int nrbins, long long startslab, long long nslab,
-                               const unsigned int *thresholds, const double *invwin, double boxsize,
-                               ksn_between_fn between, void *user)
+extern "C" int ksn_scale_modes(void *grid, int real_bytes, int dims, long long startslab, long long nslab,
+                               double boxsize, const double *logkk, const double *ratio, int nbins, double norm)
+{
+    return scale_modes_impl(grid, real_bytes, dims, startslab, nslab, boxsize, logkk, ratio, nbins, norm, nullptr, 0.0);
+}
+
+extern "C" int ksn_scale_modes_greens(void *grid, int real_bytes, int dims, long long startslab, long long nslab,
+                                      double boxsize, const double *logkk, const double *ratio, int nbins, double norm,
+                                      const double *invwin, double asmth2)
+{
+    if (!invwin || !(asmth2 >= 0)) return set_error(KSN_EINVAL, "ksn_scale_modes_greens: bad arguments");
+    return scale_modes_impl(grid, real_bytes, dims, startslab, nslab, boxsize, logkk, ratio, nbins, norm, invwin, asmth2);
+}
+
+static int step_staged_impl(void *hgrid, int real_bytes, int dims, int nrbins, long long startslab, long long nslab,
+                            const unsigned int *thresholds, const double *invwin, double boxsize,
+                            ksn_between_fn between, void *user, bool greens, double asmth2)
 {
     int rc = ensure_init();
     if (rc) return rc;
@@ -437,6 +511,9 @@ extern "C" int ksn_step_staged(void *hgrid, int real_bytes, int dims, int nrbins
     if (nslab == 0) return KSN_OK;
     rc = k3_upload_table(dims, boxsize, logkk, ratio, nbins, norm);
     if (rc) return rc;
+    rc = k3_set_greens(dims, greens ? invwin : nullptr, asmth2);
+    if (rc) return rc;
+    struct GreensOff { ~GreensOff() { g_k3greens.on = 0; } } greens_off;
     if (on_device) {
         phase_begin(PH_K3);
         rc = k3_launch(hgrid, real_bytes, dims, startslab, nslab, nbins);
@@ -447,4 +524,19 @@ extern "C" int ksn_step_staged(void *hgrid, int real_bytes, int dims, int nrbins
         return KSN_OK;
     }
     return k3_over_staged_grid(hgrid, real_bytes, dims, startslab, nslab, nbins);
+}
+
+extern "C" int ksn_step_staged(void *hgrid, int real_bytes, int dims, int nrbins, long long startslab, long long nslab,
+                               const unsigned int *thresholds, const double *invwin, double boxsize,
+                               ksn_between_fn between, void *user)
+{
+    return step_staged_impl(hgrid, real_bytes, dims, nrbins, startslab, nslab, thresholds, invwin, boxsize, between, user, false, 0.0);
+}
+
+extern "C" int ksn_step_staged_greens(void *hgrid, int real_bytes, int dims, int nrbins, long long startslab, long long nslab,
+                                      const unsigned int *thresholds, const double *invwin, double boxsize,
+                                      ksn_between_fn between, void *user, double asmth2)
+{
+    if (!(asmth2 >= 0)) return set_error(KSN_EINVAL, "ksn_step_staged_greens: bad arguments");
+    return step_staged_impl(hgrid, real_bytes, dims, nrbins, startslab, nslab, thresholds, invwin, boxsize, between, user, true, asmth2);
 }

@@ -11,6 +11,9 @@ struct ncclComm;
 
 namespace ksn {
 
+// c.d_iw holds iw[0..L) followed by K1's z-weight table of L entries and this many zeros
+constexpr int K1_WZ_PAD = 32 * 65 + 16;
+
 enum CommKind { COMM_SINGLE = 0, COMM_NCCL = 1, COMM_HOSTCB = 2 };
 
 // Events used for the optional per-phase timing (ksn_timing_*).

@@ -141,6 +141,11 @@ class KspaceNeutrinos:
         fn = self.lib.add_nu_power_to_rhogrid_f64 if real_bytes == 8 else self.lib.add_nu_power_to_rhogrid_f32
         fn(time, self.cosmo.box_size, grid_ptr, self.pmgrid, slab.start, slab.count, 0)
 
+    def add_nu_power_and_greens_to_rhogrid(self, time: float, grid_ptr, slab: Slab, asmth2: float, real_bytes: int = 8) -> None:
+        """Extension: the same step with the PM Green's function (Gadget-2 pmforce_periodic) fused into the scaling pass."""
+        fn = self.lib.add_nu_power_and_greens_to_rhogrid_f64 if real_bytes == 8 else self.lib.add_nu_power_and_greens_to_rhogrid_f32
+        fn(time, self.cosmo.box_size, grid_ptr, self.pmgrid, slab.start, slab.count, asmth2, 0)
+
     def delta_nu_last(self) -> np.ndarray:
         return np.array([self.state.delta_nu_last[i] for i in range(self.state.nk)])
 

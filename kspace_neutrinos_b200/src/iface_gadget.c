@@ -70,13 +70,15 @@ static int between_passes(void *user, const double *power_sum, const double *kef
     return 0;
 }
 
-static void add_nu_power_any(int real_bytes, const double Time, const double BoxSize, void *grid, const int pmgrid, int slabstart_y, int nslab_y)
+/* asmth2 < 0: the reference's step.  asmth2 >= 0: the same step with the PM Green's function fused into K3. */
+static void add_nu_power_any(int real_bytes, const double Time, const double BoxSize, void *grid, const int pmgrid, int slabstart_y, int nslab_y, double asmth2)
 {
     const unsigned int *thr;
     const double *iw;
     struct step_ctx s = { Time, BoxSize, delta_tot_table.nk_allocated };
     if (ksn_bin_tables(pmgrid, s.nk_allocated, &thr, &iw)) terminate(1, "Could not allocate temporary memory for power spectra\n");
-    const int rc = ksn_step_staged(grid, real_bytes, pmgrid, s.nk_allocated, slabstart_y, nslab_y, thr, iw, BoxSize, between_passes, &s);
+    const int rc = asmth2 < 0 ? ksn_step_staged(grid, real_bytes, pmgrid, s.nk_allocated, slabstart_y, nslab_y, thr, iw, BoxSize, between_passes, &s)
+                              : ksn_step_staged_greens(grid, real_bytes, pmgrid, s.nk_allocated, slabstart_y, nslab_y, thr, iw, BoxSize, between_passes, &s, asmth2);
     if (rc) ksn_fatal_device(rc, "add_nu_power_to_rhogrid");
     message(0, "Done adding neutrinos to grid on all processors\n");
     free_d_pow(&d_pow);
@@ -85,13 +87,30 @@ static void add_nu_power_any(int real_bytes, const double Time, const double Box
 void add_nu_power_to_rhogrid_f64(const double Time, const double BoxSize, void *grid, const int pmgrid, int slabstart_y, int nslab_y, MPI_Comm comm)
 {
     (void) comm;
-    add_nu_power_any(8, Time, BoxSize, grid, pmgrid, slabstart_y, nslab_y);
+    add_nu_power_any(8, Time, BoxSize, grid, pmgrid, slabstart_y, nslab_y, -1.0);
 }
 
 void add_nu_power_to_rhogrid_f32(const double Time, const double BoxSize, void *grid, const int pmgrid, int slabstart_y, int nslab_y, MPI_Comm comm)
 {
     (void) comm;
-    add_nu_power_any(4, Time, BoxSize, grid, pmgrid, slabstart_y, nslab_y);
+    add_nu_power_any(4, Time, BoxSize, grid, pmgrid, slabstart_y, nslab_y, -1.0);
+}
+
+/* Extension: add_nu_power_to_rhogrid followed, in the same pass over the grid, by the multiplication
+ * with the periodic Green's function and CIC deconvolution that Gadget-2's pmforce_periodic performs next
+ * (pm_periodic.c, the loop after the hook of gadget-2/0002 patch:116-125).  asmth2 = (2 pi Asmth / BoxSize)^2, as there. */
+void add_nu_power_and_greens_to_rhogrid_f64(const double Time, const double BoxSize, void *grid, const int pmgrid, int slabstart_y, int nslab_y, const double asmth2, MPI_Comm comm)
+{
+    (void) comm;
+    if (!(asmth2 >= 0)) terminate(1, "add_nu_power_and_greens_to_rhogrid: asmth2 = %g\n", asmth2);
+    add_nu_power_any(8, Time, BoxSize, grid, pmgrid, slabstart_y, nslab_y, asmth2);
+}
+
+void add_nu_power_and_greens_to_rhogrid_f32(const double Time, const double BoxSize, void *grid, const int pmgrid, int slabstart_y, int nslab_y, const double asmth2, MPI_Comm comm)
+{
+    (void) comm;
+    if (!(asmth2 >= 0)) terminate(1, "add_nu_power_and_greens_to_rhogrid: asmth2 = %g\n", asmth2);
+    add_nu_power_any(4, Time, BoxSize, grid, pmgrid, slabstart_y, nslab_y, asmth2);
 }
 
 /* No-neutrino P(k) path (interface_gadget.c:114-144): fills the module's d_pow for save_total_power. */

@@ -175,6 +175,27 @@ def k3_numpy(grid, startslab, box, logkk, ratio, norm):
     return out
 
 
+def greens_numpy(grid, startslab, asmth2):
+    """numpy restatement of the Green's-function loop of Gadget-2's pmforce_periodic (pm_periodic.c, the loop that follows
+    the hook of gadget-2/0002 patch:116-125; Gadget-2 itself is not part of the reference repository): for k2 > 0
+    smth = -exp(-k2*asmth2)/k2, f = sinc(pi k/N) per axis, smth *= (1/(fx fy fz))^4; F(0,0,0) = 0."""
+    nslab, n = grid.shape[0], grid.shape[1]
+    def kvals(idx):
+        return np.where(idx > n // 2, idx - n, idx).astype(np.float64)
+    ky, kx, kz = kvals(np.arange(startslab, startslab + nslab)), kvals(np.arange(n)), np.arange(n // 2 + 1, dtype=np.float64)
+    def sinc(k):
+        f = np.pi * k / n
+        return np.where(k != 0, np.sin(np.where(k != 0, f, 1.0)) / np.where(k != 0, f, 1.0), 1.0)
+    k2 = ky[:, None, None] ** 2 + kx[None, :, None] ** 2 + kz[None, None, :] ** 2
+    ff = 1.0 / (sinc(ky)[:, None, None] * sinc(kx)[None, :, None] * sinc(kz)[None, None, :])
+    live = k2 > 0
+    smth = np.where(live, -np.exp(-k2 * asmth2) / np.where(live, k2, 1.0) * ff * ff * ff * ff, 0.0)
+    out = np.empty_like(grid)
+    out[..., 0] = (grid[..., 0].astype(np.float64) * smth).astype(grid.dtype)
+    out[..., 1] = (grid[..., 1].astype(np.float64) * smth).astype(grid.dtype)
+    return out
+
+
 # ----------------------------------------------------------------------------- integrator fixtures
 def load_golden_state():
     """The arrays delta_tot_table_test.c:setup_delta_pow (:367-452) builds from testdata/:

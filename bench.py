@@ -15,6 +15,7 @@ from __future__ import annotations
 import argparse
 import ctypes as C
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -40,6 +41,7 @@ def parse_args():
     ap.add_argument("--pmgrid", type=int, default=int(os.environ.get("KSN_BENCH_PMGRID", "2048")))
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-greens", action="store_true", help="skip the fused Green's-function side measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-planes", type=int, default=0, help="planes per rank in the CPU sample (0 = auto)")
     return ap.parse_args()
@@ -263,6 +265,41 @@ def ours(args):
     value = modes_total / (step_ms * 1e-3)
     launches = int(tm.launches)
 
+    # ---- what fusing the PM Green's function into K3 saves (one launch each, N=1 only; not part of `value`)
+    greens = None
+    if world == 1 and not args.no_greens:
+        try:
+            import numpy as np
+            thr = C.POINTER(C.c_uint)()
+            iw = capi.c_double_p()
+            L.ksn_bin_tables(n, n // 2, C.byref(thr), C.byref(iw))
+            nk = n // 2                            # as many knots as the step's own table has bins
+            logkk = np.log(np.geomspace(1.0, n * 0.86, nk) * 2 * math.pi / cosmo.box_size)
+            ratio, zero = np.linspace(0.9, 0.1, nk), np.zeros(nk)
+            dp = lambda x: x.ctypes.data_as(capi.c_double_p)    # noqa: E731
+            asmth2 = (2 * math.pi * 1.25 / n) ** 2
+            tg = capi.Timing()
+
+            def one(call):
+                ts = []
+                for _ in range(3):
+                    L.ksn_timing_enable(1)
+                    L.ksn_timing_reset()
+                    capi.check(call())
+                    L.ksn_timing_get(C.byref(tg))
+                    ts.append(tg.k3_ms)
+                L.ksn_timing_enable(0)
+                return statistics.median(ts)
+            k3_plain = one(lambda: L.ksn_scale_modes(grid.ptr, 8, n, slab.start, slab.count, cosmo.box_size, dp(logkk), dp(ratio), nk, 0.01))
+            k3_fused = one(lambda: L.ksn_scale_modes_greens(grid.ptr, 8, n, slab.start, slab.count, cosmo.box_size, dp(logkk), dp(ratio), nk, 0.01, iw, asmth2))
+            g_alone = one(lambda: L.ksn_scale_modes_greens(grid.ptr, 8, n, slab.start, slab.count, cosmo.box_size, dp(logkk), dp(zero), nk, 0.0, iw, asmth2))
+            greens = {"k3_ms": k3_plain, "k3_with_greens_fused_ms": k3_fused, "greens_as_its_own_pass_ms": g_alone,
+                      "saved_ms_per_step": k3_plain + g_alone - k3_fused, "saved_bytes_per_mode": 32,
+                      "note": "K3 fused with the Green's-function multiply of the surrounding Gadget PM step (pm_periodic.c); the host's separate pass disappears"}
+            grid.fill_synthetic()                   # the Green's function was applied nine times: start again from a sane grid
+        except capi.KsnError as exc:
+            greens = {"error": str(exc)}
+
     # ---- end to end: the same call on HOST buffers (pinned), H2D + D2H inside the timed region
     e2e = None
     if not args.no_e2e and args.e2e_steps > 0:
@@ -324,6 +361,8 @@ def ours(args):
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(n, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "wall_ms_per_step": wall_ms / args.steps}
+    if greens is not None:
+        line["greens_fusion"] = greens
     if world == 1 and not args.no_cpu_baseline:
         try:
             v, t_step, info = cpu_throughput(n, 1, args.cpu_planes)

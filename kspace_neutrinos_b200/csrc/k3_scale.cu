@@ -70,20 +70,25 @@ struct K3Greens {
     int on;
     double asmth2;
     const double *iw;   // device: 1-D inverse CIC window, q = 0..N/2 (the table K1 uses)
+    const double *gz;   // device: exp(-z^2 asmth2) * iw[z]^4, z = 0..N/2
 };
 
-__device__ __forceinline__ double k3_greens(const K3Greens &gr, int k2i, double wxy4, int z)
-{
-    const double w = __ldg(gr.iw + z), w2 = w * w;
-    const double k2 = (double) k2i;
-    return -exp(-k2 * gr.asmth2) / k2 * (wxy4 * (w2 * w2));
-}
-
-__device__ __forceinline__ double k3_row_window4(const K3Greens &gr, int ki, int kj)
+// exp(-k2 a) = exp(-(kx^2+ky^2) a) * exp(-kz^2 a): a per-row scalar (with the x-y window) times a per-z table, so that a
+// mode costs one table read, two multiplies and a reciprocal of the integer k2 (float seed + two Newton steps, < 1e-15).
+__device__ __forceinline__ double k3_greens_row(const K3Greens &gr, int ki, int kj)
 {
     const double a = __ldg(gr.iw + (ki < 0 ? -ki : ki)), b = __ldg(gr.iw + (kj < 0 ? -kj : kj));
     const double q = a * b, q2 = q * q;
-    return q2 * q2;
+    return -exp(-(double) (ki * ki + kj * kj) * gr.asmth2) * (q2 * q2);
+}
+
+__device__ __forceinline__ double k3_greens(const K3Greens &gr, int k2i, double rowfac, int z)
+{
+    const double k2 = (double) k2i;
+    double r = (double) __frcp_rn((float) k2i);
+    r = r * fma(-k2, r, 2.0);
+    r = r * fma(-k2, r, 2.0);
+    return rowfac * __ldg(gr.gz + z) * r;
 }
 
 struct K3Params {
@@ -154,7 +159,7 @@ k3_scale_kernel(C2<real> *__restrict__ grid, int nrows, int rows_per_cta, int N,
             const int k2i = ki * ki + kj * kj + z * z;
             if (k2i == 0 && !gr.on) continue;                    // F(0,0,0) is skipped (interface_gadget.c:174)
             double smth = k2i > 0 ? k3_factor<real>(k2i, seg, cellv, prm) : 0.0;
-            if (gr.on && k2i > 0) smth *= k3_greens(gr, k2i, k3_row_window4(gr, ki, kj), z);   // the mean is zeroed
+            if (gr.on && k2i > 0) smth *= k3_greens(gr, k2i, k3_greens_row(gr, ki, kj), z);   // the mean is zeroed
             C2<real> o;
             o.re = (real) ((double) v[u].re * smth);
             o.im = (real) ((double) v[u].im * smth);
@@ -210,8 +215,8 @@ k3_scale_tma_kernel(C2<real> *__restrict__ grid, int nrows, int rows_per_cta, in
         return ki * ki + kj * kj;
     };
     const int c0 = row_c(row0);              // CTA-uniform: the only row when ONE_ROW
-    double w0 = 1.0;                         // (iwx iwy)^4 of that row, for the Green's function
-    if (gr.on && ONE_ROW) { int ki, kj; row_k(row0, ki, kj); w0 = k3_row_window4(gr, ki, kj); }
+    double w0 = 1.0;                         // -exp(-(kx^2+ky^2) asmth2) (iwx iwy)^4 of that row, for the Green's function
+    if (gr.on && ONE_ROW) { int ki, kj; row_k(row0, ki, kj); w0 = k3_greens_row(gr, ki, kj); }
     double smth[K3_EPT];
 #pragma unroll
     for (int k = 0; k < K3_EPT; k++) {
@@ -228,7 +233,7 @@ k3_scale_tma_kernel(C2<real> *__restrict__ grid, int nrows, int rows_per_cta, in
                 int ki, kj;
                 row_k(row0 + rl, ki, kj);
                 k2i = ki * ki + kj * kj + z * z;
-                if (gr.on) wxy4 = k3_row_window4(gr, ki, kj);
+                if (gr.on) wxy4 = k3_greens_row(gr, ki, kj);
             }
             if (k2i > 0) smth[k] = k3_factor<real>(k2i, seg, cellv, prm);     // F(0,0,0) keeps factor 1 ...
             if (gr.on) smth[k] = k2i > 0 ? smth[k] * k3_greens(gr, k2i, wxy4, z) : 0.0;   // ... or is zeroed with the potential
@@ -313,7 +318,7 @@ int k3_upload_table(int dims, double boxsize, const double *logkk, const double 
     return KSN_OK;
 }
 
-static K3Greens g_k3greens = { 0, 0.0, nullptr };
+static K3Greens g_k3greens = { 0, 0.0, nullptr, nullptr };
 
 // Switch the fused Green's function on (invwin: host table iw[0..N/2], as K1 takes it) or off (invwin == nullptr).
 static int k3_set_greens(int dims, const double *invwin, double asmth2)
@@ -324,10 +329,25 @@ static int k3_set_greens(int dims, const double *invwin, double asmth2)
     const size_t L = (size_t) dims / 2 + 1;
     int rc = ensure_device_buffer((void **) &c.d_iw, &c.iw_cap, (2 * L + K1_WZ_PAD) * sizeof(double));   // K1's layout: iw | z weights
     if (rc) return rc;
-    KSN_CUDA(cudaMemcpyAsync(c.d_iw, invwin, L * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    static double *d_gz = nullptr;
+    static size_t gz_cap = 0;
+    rc = ensure_device_buffer((void **) &d_gz, &gz_cap, L * sizeof(double));
+    if (rc) return rc;
+    double *gz = (double *) malloc(L * sizeof(double));
+    if (!gz) return set_error(KSN_ENOMEM, "K3: out of host memory");
+    for (size_t z = 0; z < L; z++) {
+        const double w2 = invwin[z] * invwin[z];
+        gz[z] = exp(-(double) (z * z) * asmth2) * (w2 * w2);
+    }
+    cudaError_t e = cudaMemcpyAsync(c.d_iw, invwin, L * sizeof(double), cudaMemcpyHostToDevice, c.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_gz, gz, L * sizeof(double), cudaMemcpyHostToDevice, c.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);       // gz is about to be freed
+    free(gz);
+    KSN_CUDA(e);
     g_k3greens.on = 1;
     g_k3greens.asmth2 = asmth2;
     g_k3greens.iw = c.d_iw;
+    g_k3greens.gz = d_gz;
     return KSN_OK;
 }
 

@@ -21,6 +21,7 @@
 
 #include <float.h>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -467,6 +468,7 @@ k2_prep_splines_kernel(const double *__restrict__ fsscales, const double *__rest
 // ---------------------------------------------------------------- the per-k integral
 struct K2Dev {
     int nk, Na, namax, Nfs;
+    int k_first;            // this launch integrates bins [k_first, k_first + gridDim.x)
     double loga0, loga, light, delta_nu_prefac, deriv_prefac, nufrac_low0;
     double mnubykT[3], qc[3], relerr[3];
     int integrate[3];
@@ -514,7 +516,7 @@ k2_delta_nu_kernel(const __grid_constant__ K2Dev p)
     __shared__ QagShared S;
     double *sx = (double *) smem_raw, *sy = sx + p.Na, *sc = sy + p.Na, *sb = sc + p.Na, *sd = sb + p.Na;
     __shared__ double enq_s[19];
-    const int ik = blockIdx.x, sp = blockIdx.y;
+    const int ik = p.k_first + blockIdx.x, sp = blockIdx.y;
     if (threadIdx.x < 19) {
         const int n = threadIdx.x + 1;
         enq_s[threadIdx.x] = ((n & 1) ? 1.0 : -1.0) * exp(-(double) n * p.qc[sp]);
@@ -748,8 +750,18 @@ extern "C" int ksn_delta_nu_integrate(const ksn_delta_nu_args *A, double *out, u
         k2_prep_splines_kernel<<<2, 256, 0, c.stream>>>(d_fsscales, d_fslengths, Nfs, d_fsc, d_fsb, d_fsd, d_sa, d_sg, d_in, Na, d_dta, d_dtg);
         c.launches++;
     }
+    // bins of this launch: all of them, or (experiment: KSN_K2_SHARD="r,R") the r-th of R contiguous shares
+    int k_first = 0, k_count = nk;
+    {
+        int r = 0, R = 0;
+        const char *env = getenv("KSN_K2_SHARD");
+        if (env && sscanf(env, "%d,%d", &r, &R) == 2 && R > 0 && r >= 0 && r < R) {
+            k_first = (int) ((long long) nk * r / R);
+            k_count = (int) ((long long) nk * (r + 1) / R) - k_first;
+        }
+    }
     K2Dev p;
-    p.nk = nk; p.Na = Na; p.namax = A->namax; p.Nfs = Nfs;
+    p.nk = nk; p.Na = Na; p.namax = A->namax; p.Nfs = Nfs; p.k_first = k_first;
     p.loga0 = loga0; p.loga = loga; p.light = A->light; p.delta_nu_prefac = A->delta_nu_prefac;
     p.deriv_prefac = A->deriv_prefac; p.nufrac_low0 = A->nufrac_low0;
     for (int s = 0; s < 3; s++) {
@@ -760,7 +772,7 @@ extern "C" int ksn_delta_nu_integrate(const ksn_delta_nu_args *A, double *out, u
     p.delta_nu_init = p.wavenum + nk;
     p.fsscales = d_fsscales; p.fslengths = d_fslengths; p.fs_c = d_fsc; p.fs_b = d_fsb; p.fs_d = d_fsd; p.dt_alpha = d_dta; p.dt_gamma = d_dtg;
     p.out = d_out; p.status = d_status; p.evals = d_evals; p.bg = bg;
-    k2_delta_nu_kernel<<<dim3(nk, ns), K2_THREADS, 5 * (size_t) Na * sizeof(double), c.stream>>>(p);
+    if (k_count > 0) k2_delta_nu_kernel<<<dim3(k_count, ns), K2_THREADS, 5 * (size_t) Na * sizeof(double), c.stream>>>(p);
     c.launches++;
     KSN_CUDA(cudaGetLastError());
     double *h_out = h + n_in;

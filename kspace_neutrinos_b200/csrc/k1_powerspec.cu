@@ -914,40 +914,46 @@ static int k1_upload_tables(int dims, int nrbins, const unsigned int *thresholds
     return KSN_OK;
 }
 
-// Plane-chunked staging of a host-resident slab into c.d_stage, K1 on each chunk as it lands.
+// Plane-chunked staging of a host-resident slab into c.d_stage, K1 on each chunk as it lands.  Resident plan: chunk i
+// lives at its own offset and stays for K3.  Streaming plan (the slab does not fit): chunk i lands in ring slot i % 3,
+// which is free again once K1 has read it.
 static int k1_over_host_grid(const void *hgrid, int real_bytes, int dims, int nrbins, long long startslab, long long nslab,
-                             bool full, int *ctas, int *stride)
+                             bool full, int *ctas, int *stride, const void **origin)
 {
     Ctx &c = ctx();
-    const size_t plane_bytes = (size_t) dims * (dims / 2 + 1) * 2 * real_bytes;
-    const size_t total = plane_bytes * (size_t) nslab;
-    int rc = ensure_device_buffer(&c.d_stage, &c.stage_cap, total);
-    if (rc) return set_error(KSN_ENOMEM, "staging a %zu-byte host grid needs as much free HBM (streaming path not built yet)", total);
-    ensure_host_pinned(hgrid, total);
-    long long chunk = (long long) ((256ull << 20) / plane_bytes);
-    if (chunk < 1) chunk = 1;
-    const int nchunks = (int) ((nslab + chunk - 1) / chunk);
-    cudaEvent_t *evs = (cudaEvent_t *) malloc(sizeof(cudaEvent_t) * nchunks);
-    for (int i = 0; i < nchunks; i++) cudaEventCreateWithFlags(&evs[i], cudaEventDisableTiming);
+    StagePlan pl;
+    int rc = stage_plan(real_bytes, dims, nslab, &pl);
+    if (rc) return rc;
+    c.stage_streaming = pl.streaming;
+    ensure_host_pinned(hgrid, pl.total);
+    const int nev = pl.streaming ? STAGE_RING : pl.nchunks;
+    cudaEvent_t *landed = (cudaEvent_t *) malloc(sizeof(cudaEvent_t) * nev), *read = (cudaEvent_t *) malloc(sizeof(cudaEvent_t) * nev);
+    for (int i = 0; i < nev; i++) {
+        cudaEventCreateWithFlags(&landed[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&read[i], cudaEventDisableTiming);
+    }
     // make sure the staging buffer is not still being read by a previous step
     KSN_CUDA(cudaStreamSynchronize(c.stream));
+    *origin = pl.streaming ? c.d_origin : c.d_stage;
     phase_begin(PH_H2D);
-    for (int i = 0; i < nchunks; i++) {
-        const long long p0 = i * chunk, np = (p0 + chunk <= nslab) ? chunk : nslab - p0;
-        cudaMemcpyAsync((char *) c.d_stage + p0 * plane_bytes, (const char *) hgrid + p0 * plane_bytes,
-                        np * plane_bytes, cudaMemcpyHostToDevice, c.copy_stream);
-        cudaEventRecord(evs[i], c.copy_stream);
+    phase_begin(PH_K1);
+    for (int i = 0; i < pl.nchunks && !rc; i++) {
+        const long long p0 = i * pl.chunk, np = (p0 + pl.chunk <= nslab) ? pl.chunk : nslab - p0;
+        const int s = pl.streaming ? i % STAGE_RING : i;
+        char *slot = (char *) c.d_stage + (pl.streaming ? (size_t) s * pl.chunk : (size_t) p0) * pl.plane_bytes;
+        if (pl.streaming && i >= STAGE_RING) cudaStreamWaitEvent(c.copy_stream, read[s], 0);
+        cudaMemcpyAsync(slot, (const char *) hgrid + p0 * pl.plane_bytes, np * pl.plane_bytes, cudaMemcpyHostToDevice, c.copy_stream);
+        cudaEventRecord(landed[s], c.copy_stream);
+        cudaStreamWaitEvent(c.stream, landed[s], 0);
+        if (pl.streaming && i == 0) cudaMemcpyAsync(c.d_origin, slot, 2 * real_bytes, cudaMemcpyDeviceToDevice, c.stream);
+        rc = k1_launch(slot, real_bytes, dims, nrbins, startslab + p0, np, full, i > 0, ctas, stride);
+        cudaEventRecord(read[s], c.stream);
     }
     phase_end(PH_H2D);
-    phase_begin(PH_K1);
-    for (int i = 0; i < nchunks && !rc; i++) {
-        const long long p0 = i * chunk, np = (p0 + chunk <= nslab) ? chunk : nslab - p0;
-        cudaStreamWaitEvent(c.stream, evs[i], 0);
-        rc = k1_launch((char *) c.d_stage + p0 * plane_bytes, real_bytes, dims, nrbins, startslab + p0, np, full, i > 0, ctas, stride);
-    }
     phase_end(PH_K1);
-    for (int i = 0; i < nchunks; i++) cudaEventDestroy(evs[i]);
-    free(evs);
+    for (int i = 0; i < nev; i++) { cudaEventDestroy(landed[i]); cudaEventDestroy(read[i]); }
+    free(landed);
+    free(read);
     if (rc) return rc;
     KSN_CUDA(cudaGetLastError());
     return KSN_OK;
@@ -974,8 +980,7 @@ int k1_sums(const void *dgrid, const void *hgrid, int real_bytes, int dims, int 
             phase_end(PH_K1);
             origin = dgrid;
         } else {
-            rc = k1_over_host_grid(hgrid, real_bytes, dims, nrbins, startslab, nslab, full, &ctas, &stride);
-            origin = c.d_stage;
+            rc = k1_over_host_grid(hgrid, real_bytes, dims, nrbins, startslab, nslab, full, &ctas, &stride, &origin);
         }
         if (rc) return rc;
     } else {

@@ -392,39 +392,57 @@ int k3_launch(void *dgrid, int real_bytes, int dims, long long plane0_global, lo
     return KSN_OK;
 }
 
-// K3 over a slab that already sits in c.d_stage (uploaded by K1's staged path), chunk by chunk, each
-// chunk copied back to the host buffer as soon as it is scaled.
-int k3_over_staged_grid(void *hgrid, int real_bytes, int dims, long long startslab, long long nslab, int nknots)
+// K3 over a host-resident slab, chunk by chunk, each chunk copied back to the host buffer as soon as it is scaled.
+// resident: the slab already sits in c.d_stage (uploaded by K1's staged path).  Otherwise (streaming plan) every chunk is
+// uploaded again into the ring; uploads run on copy_stream and downloads on copy_stream2, so they overlap on the full-duplex
+// PCIe link and the pass costs about one transfer time, like the resident one.
+int k3_over_staged_grid(void *hgrid, int real_bytes, int dims, long long startslab, long long nslab, int nknots, bool resident)
 {
     Ctx &c = ctx();
-    const size_t plane_bytes = (size_t) dims * (dims / 2 + 1) * 2 * real_bytes;
-    long long chunk = (long long) ((256ull << 20) / plane_bytes);
-    if (chunk < 1) chunk = 1;
-    const int nchunks = (int) ((nslab + chunk - 1) / chunk);
-    cudaEvent_t *evs = (cudaEvent_t *) malloc(sizeof(cudaEvent_t) * nchunks);
-    for (int i = 0; i < nchunks; i++) cudaEventCreateWithFlags(&evs[i], cudaEventDisableTiming);
-    int rc = KSN_OK;
+    StagePlan pl;
+    int rc = stage_plan(real_bytes, dims, nslab, &pl);
+    if (rc) return rc;
+    if (resident && pl.streaming) return set_error(KSN_EINVAL, "K3: staging plan changed between the passes");
+    const bool ring = !resident && pl.streaming;
+    const int nev = ring ? STAGE_RING : pl.nchunks;
+    cudaEvent_t *landed = (cudaEvent_t *) malloc(sizeof(cudaEvent_t) * nev), *scaled = (cudaEvent_t *) malloc(sizeof(cudaEvent_t) * nev),
+                *sent = (cudaEvent_t *) malloc(sizeof(cudaEvent_t) * nev);
+    for (int i = 0; i < nev; i++) {
+        cudaEventCreateWithFlags(&landed[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&scaled[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&sent[i], cudaEventDisableTiming);
+    }
+    cudaStream_t down = resident ? c.copy_stream : c.copy_stream2;   // uploads and downloads overlap when both are in this pass
+    if (!resident) {
+        ensure_host_pinned(hgrid, pl.total);
+        KSN_CUDA(cudaStreamSynchronize(c.stream));      // nothing of a previous call may still read the staging buffer
+    }
     phase_begin(PH_K3);
-    for (int i = 0; i < nchunks && !rc; i++) {
-        const long long p0 = i * chunk, np = (p0 + chunk <= nslab) ? chunk : nslab - p0;
-        rc = k3_launch((char *) c.d_stage + p0 * plane_bytes, real_bytes, dims, startslab + p0, np, nknots);
-        cudaEventRecord(evs[i], c.stream);
+    for (int i = 0; i < pl.nchunks && !rc; i++) {
+        const long long p0 = i * pl.chunk, np = (p0 + pl.chunk <= nslab) ? pl.chunk : nslab - p0;
+        const int s = ring ? i % STAGE_RING : i;
+        char *slot = (char *) c.d_stage + (ring ? (size_t) s * pl.chunk : (size_t) p0) * pl.plane_bytes;
+        if (!resident) {
+            if (ring && i >= STAGE_RING) cudaStreamWaitEvent(c.copy_stream, sent[s], 0);
+            cudaMemcpyAsync(slot, (const char *) hgrid + p0 * pl.plane_bytes, np * pl.plane_bytes, cudaMemcpyHostToDevice, c.copy_stream);
+            cudaEventRecord(landed[s], c.copy_stream);
+            cudaStreamWaitEvent(c.stream, landed[s], 0);
+        }
+        rc = k3_launch(slot, real_bytes, dims, startslab + p0, np, nknots);
+        cudaEventRecord(scaled[s], c.stream);
+        cudaStreamWaitEvent(down, scaled[s], 0);
+        cudaMemcpyAsync((char *) hgrid + p0 * pl.plane_bytes, slot, np * pl.plane_bytes, cudaMemcpyDeviceToHost, down);
+        cudaEventRecord(sent[s], down);
     }
     phase_end(PH_K3);
-    phase_begin(PH_D2H);
-    for (int i = 0; i < nchunks && !rc; i++) {
-        const long long p0 = i * chunk, np = (p0 + chunk <= nslab) ? chunk : nslab - p0;
-        cudaStreamWaitEvent(c.copy_stream, evs[i], 0);
-        cudaMemcpyAsync((char *) hgrid + p0 * plane_bytes, (char *) c.d_stage + p0 * plane_bytes, np * plane_bytes,
-                        cudaMemcpyDeviceToHost, c.copy_stream);
-    }
-    phase_end(PH_D2H);
     cudaError_t e1 = cudaStreamSynchronize(c.copy_stream), e2 = cudaStreamSynchronize(c.stream);
-    for (int i = 0; i < nchunks; i++) cudaEventDestroy(evs[i]);
-    free(evs);
+    cudaError_t e3 = resident ? cudaSuccess : cudaStreamSynchronize(c.copy_stream2);
+    for (int i = 0; i < nev; i++) { cudaEventDestroy(landed[i]); cudaEventDestroy(scaled[i]); cudaEventDestroy(sent[i]); }
+    free(landed); free(scaled); free(sent);
     if (rc) return rc;
     KSN_CUDA(e1);
     KSN_CUDA(e2);
+    KSN_CUDA(e3);
     phase_collect();
     return KSN_OK;
 }
@@ -473,16 +491,8 @@ static int scale_modes_impl(void *grid, int real_bytes, int dims, long long star
         phase_collect();
         return KSN_OK;
     }
-    // host grid: upload, scale, download
-    const size_t total = (size_t) nslab * dims * (dims / 2 + 1) * 2 * real_bytes;
-    rc = ensure_device_buffer(&c.d_stage, &c.stage_cap, total);
-    if (rc) return set_error(KSN_ENOMEM, "staging a %zu-byte host grid needs as much free HBM", total);
-    ensure_host_pinned(grid, total);
-    phase_begin(PH_H2D);
-    KSN_CUDA(cudaMemcpyAsync(c.d_stage, grid, total, cudaMemcpyHostToDevice, c.copy_stream));
-    phase_end(PH_H2D);
-    KSN_CUDA(cudaStreamSynchronize(c.copy_stream));
-    return k3_over_staged_grid(grid, real_bytes, dims, startslab, nslab, nbins);
+    // host grid: upload, scale, download -- chunk by chunk
+    return k3_over_staged_grid(grid, real_bytes, dims, startslab, nslab, nbins, false);
 }
 
 extern "C" int ksn_scale_modes(void *grid, int real_bytes, int dims, long long startslab, long long nslab,
@@ -543,7 +553,7 @@ static int step_staged_impl(void *hgrid, int real_bytes, int dims, int nrbins, l
         phase_collect();
         return KSN_OK;
     }
-    return k3_over_staged_grid(hgrid, real_bytes, dims, startslab, nslab, nbins);
+    return k3_over_staged_grid(hgrid, real_bytes, dims, startslab, nslab, nbins, !c.stage_streaming);
 }
 
 extern "C" int ksn_step_staged(void *hgrid, int real_bytes, int dims, int nrbins, long long startslab, long long nslab,

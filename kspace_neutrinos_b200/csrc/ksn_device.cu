@@ -106,6 +106,35 @@ int ensure_pinned_buffer(void **p, size_t *cap, size_t bytes)
     return KSN_OK;
 }
 
+// ---------------------------------------------------------------- staging plan for host-resident slabs
+// Resident when the whole slab fits in free HBM (with 1 GB to spare): uploaded once, used by K1 and K3, downloaded once.
+// Otherwise STREAMING: a ring of STAGE_RING chunks; K1 consumes the chunks as they land, K3 uploads them a second time
+// and sends each back as soon as it is scaled (the second upload overlaps the downloads: PCIe is full duplex).
+// KSN_STAGE_CHUNK_MB (default 256) sets the chunk size, KSN_STAGE_MAX_MB caps what may stay resident (tests).
+int stage_plan(int real_bytes, int dims, long long nslab, StagePlan *plan)
+{
+    Ctx &c = g_ctx;
+    plan->plane_bytes = (size_t) dims * (dims / 2 + 1) * 2 * real_bytes;
+    plan->total = plan->plane_bytes * (size_t) nslab;
+    const char *e = getenv("KSN_STAGE_CHUNK_MB");
+    const size_t chunk_bytes = (size_t) (e && atoi(e) > 0 ? atoi(e) : 256) << 20;
+    plan->chunk = (long long) (chunk_bytes / plan->plane_bytes);
+    if (plan->chunk < 1) plan->chunk = 1;
+    plan->nchunks = (int) ((nslab + plan->chunk - 1) / plan->chunk);
+    size_t freeb = 0, totb = 0;
+    if (cudaMemGetInfo(&freeb, &totb) != cudaSuccess) { cudaGetLastError(); freeb = 0; }
+    e = getenv("KSN_STAGE_MAX_MB");
+    const size_t cap = e ? (size_t) atoll(e) << 20 : (size_t) -1;
+    const bool fits = plan->total <= cap && (c.stage_cap >= plan->total || plan->total + ((size_t) 1 << 30) <= freeb + c.stage_cap);
+    plan->streaming = !fits && plan->nchunks > STAGE_RING;
+    const size_t need = plan->streaming ? (size_t) STAGE_RING * plan->chunk * plan->plane_bytes : plan->total;
+    int rc = ensure_device_buffer(&c.d_stage, &c.stage_cap, need);
+    if (rc) return set_error(KSN_ENOMEM, "staging a host grid needs %zu bytes of free HBM", need);
+    if (!c.copy_stream2) KSN_CUDA(cudaStreamCreateWithFlags(&c.copy_stream2, cudaStreamNonBlocking));
+    if (!c.d_origin) KSN_CUDA(cudaMalloc(&c.d_origin, 16));
+    return KSN_OK;
+}
+
 // ---------------------------------------------------------------- timing
 void phase_begin(Phase p)
 {
@@ -315,6 +344,8 @@ void ksn_shutdown(void)
     for (int i = 0; i < PH_COUNT; i++) for (int j = 0; j < 2; j++) cudaEventDestroy(c.ev[i][j]);
     cudaStreamDestroy(c.stream);
     cudaStreamDestroy(c.copy_stream);
+    if (c.copy_stream2) cudaStreamDestroy(c.copy_stream2);
+    cudaFree(c.d_origin);
     c = Ctx();
 }
 

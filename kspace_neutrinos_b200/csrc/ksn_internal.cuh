@@ -45,6 +45,9 @@ struct Ctx {
     double *d_k3tab = nullptr; size_t k3tab_cap = 0; double *h_k3tab = nullptr; size_t h_k3tab_cap = 0;
     // staging buffer for host-resident grids
     void *d_stage = nullptr; size_t stage_cap = 0;
+    bool stage_streaming = false;        // the slab did not fit: d_stage is a ring of chunks, K3 re-uploads (stage_plan)
+    cudaStream_t copy_stream2 = nullptr; // D2H of the streaming path (H2D keeps copy_stream: PCIe is full duplex)
+    void *d_origin = nullptr;            // copy of the slab's first element (total_mass2) when the ring recycles chunk 0
     // background table 1/(aH)
     double *d_bg = nullptr; int bg_n = 0; double bg_lo = 0, bg_hi = 0, bg_h = 0;
     // K2 workspace
@@ -75,6 +78,11 @@ int allreduce_to_host(double *d_buf, double *h_buf, size_t n);
 
 // Host pointer -> pinned (registers once and remembers).  Returns 1 if the range is pinned afterwards.
 int ensure_host_pinned(const void *p, size_t bytes);
+
+// How a host-resident slab goes through HBM: whole (it stays resident between K1 and K3) or as a ring of chunks.
+constexpr int STAGE_RING = 3;
+struct StagePlan { size_t plane_bytes, total; long long chunk; int nchunks; bool streaming; };
+int stage_plan(int real_bytes, int dims, long long nslab, StagePlan *plan);   // allocates c.d_stage accordingly
 
 // launchers (one per kernel family)
 int k1_launch(const void *dgrid, int real_bytes, int dims, int nrbins, long long plane0_global, long long nplanes,

@@ -230,3 +230,33 @@ def test_hundred_step_run_tracks_oracle(gpu, hybrid, masses):
     assert dt.ia > 90
     assert worst < 1e-10, worst
     np.testing.assert_allclose(final, cur, rtol=1e-9, atol=0)       # 110 multiplicative steps accumulate rounding
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 1e-5)])
+def test_streaming_plan_for_slabs_that_do_not_fit_hbm(gpu, dtype, tol, monkeypatch):
+    """A host slab larger than what may stay resident (forced here with KSN_STAGE_MAX_MB; in production: larger than free
+    HBM) goes through a three-chunk ring twice -- K1 on the chunks as they land, then upload/K3/download per chunk with the
+    uploads overlapping the downloads.  Same result as the resident plan, slab starting at plane 0 (total_mass2 comes from
+    a chunk the ring recycles) and not."""
+    n = 96                                                     # 96 planes of 75 KB (double): 1 MB chunks hold 13 -> 8 chunks
+    g = refs.random_grid(n, seed=31, dtype=dtype)
+    fn = "add_nu_power_to_rhogrid_f64" if dtype == np.float64 else "add_nu_power_to_rhogrid_f32"
+    outs = []
+    for streaming in (False, True):
+        if streaming:
+            monkeypatch.setenv("KSN_STAGE_MAX_MB", "0")
+            monkeypatch.setenv("KSN_STAGE_CHUNK_MB", "1")       # 1 MB: 8 chunks (double) or 4 (float) -> the ring of 3 is recycled
+        refs.init_module(gpu, n, masses=(0.15, 0.15, 0.15))
+        dt = capi.global_delta_tot_table()
+        cur = g.copy()
+        for a in (0.01, 0.02, 0.03):
+            getattr(gpu, fn)(a, refs.BOX, cur.ctypes.data_as(C.c_void_p), n, 0, n, 0)
+        part = g[20:93].copy()                                     # ragged slab that does not hold plane 0: K3 alone (a COPY: a slice of g is a view)
+        logkk = np.log(np.array([dt.wavenum[i] for i in range(dt.nk)]))
+        ratio = np.linspace(0.5, 0.1, dt.nk)
+        capi.check(gpu.ksn_scale_modes(part.ctypes.data_as(C.c_void_p), g.dtype.itemsize, n, 20, 73, refs.BOX,
+                                       refs.dptr(logkk), refs.dptr(ratio), dt.nk, 0.01))
+        outs.append((cur, part, np.array([dt.delta_nu_last[i] for i in range(dt.nk)])))
+    np.testing.assert_allclose(outs[1][2], outs[0][2], rtol=1e-12)
+    np.testing.assert_allclose(outs[1][0], outs[0][0], rtol=tol)
+    np.testing.assert_array_equal(outs[1][1], outs[0][1])

@@ -117,9 +117,10 @@ def cpu_throughput(n, steps, planes=0):
     while n % ranks:
         ranks -= 1
     if planes <= 0:
-        # ~0.5 us per mode per core for the two grid passes -> aim at ~4 s per step
-        per_plane = n * (n // 2 + 1) * 0.5e-6
-        planes = max(1, min(n // ranks, int(4.0 / per_plane)))
+        # ~0.2 us per mode per core for the two grid passes (measured 0.1-0.25) -> aim at ~6 s of CPU work per step:
+        # long enough that the extrapolation to the full slab is not dominated by start-up noise
+        per_plane = n * (n // 2 + 1) * 0.2e-6
+        planes = max(1, min(n // ranks, int(6.0 / per_plane)))
     if os.path.exists(REF_BENCH):
         kind, r = "reference", run_ref_bench(n, planes, ranks, steps)
     else:

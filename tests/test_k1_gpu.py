@@ -37,7 +37,7 @@ def test_kat_4cube_device_pointer_and_float(gpu):
     assert abs(power[1] - 0.00212722) < 1e-5 * 0.005
 
 
-@pytest.mark.parametrize("n,nrbins", [(8, 4), (16, 8), (32, 16), (64, 32), (96, 48), (128, 64), (128, 200)])
+@pytest.mark.parametrize("n,nrbins", [(8, 4), (16, 8), (32, 16), (64, 32), (96, 48), (128, 64), (128, 200), (192, 96)])
 def test_matches_reference_double(gpu, n, nrbins):
     ref = refs.ref_lib(True)
     if ref is None:
@@ -45,12 +45,15 @@ def test_matches_reference_double(gpu, n, nrbins):
     g = refs.random_grid(n, seed=n)
     r_n, r_p, r_c, r_k = refs.total_powerspectrum(ref, g, nrbins)
     d = refs.DeviceBuffer(gpu, g)
-    m_n, m_p, m_c, m_k = refs.total_powerspectrum(gpu, g, nrbins, fn="total_powerspectrum_f64", pointer=d.ptr)
+    # first sweep of a geometry: k1_bin_kernel (power, keff, counts); second: the tile kernel (power) + cached geometry
+    for sweep in ("first", "cached"):
+        m_n, m_p, m_c, m_k = refs.total_powerspectrum(gpu, g, nrbins, fn="total_powerspectrum_f64", pointer=d.ptr)
+        assert m_n == r_n, sweep
+        assert np.array_equal(m_c[:m_n], r_c[:r_n]), sweep             # mode counts: bit-exact
+        np.testing.assert_allclose(m_p[:m_n], r_p[:r_n], rtol=1e-10, atol=0, err_msg=sweep)   # north-star tolerance, double grid
+        np.testing.assert_allclose(m_k[:m_n], r_k[:r_n], rtol=1e-10, atol=0, err_msg=sweep)
+    assert b"k1_tile_kernel" in gpu.ksn_last_k1_kernel()
     d.free()
-    assert m_n == r_n
-    assert np.array_equal(m_c[:m_n], r_c[:r_n])                    # mode counts: bit-exact
-    np.testing.assert_allclose(m_p[:m_n], r_p[:r_n], rtol=1e-10, atol=0)   # north-star tolerance, double grid
-    np.testing.assert_allclose(m_k[:m_n], r_k[:r_n], rtol=1e-10, atol=0)
 
 
 def test_matches_reference_float(gpu):

@@ -11,11 +11,30 @@
 
 static struct { int dims, nrbins; unsigned int *thr; double *iw; } tabs;
 
-/* the reference's bin of a mode with squared integer wave number k2 (powerspectrum.c:40,67) */
+/* The reference's bin of a mode with squared integer wave number k2: floor(binsperunit*log(sqrt(k2))) with
+ * binsperunit = (nrbins-1)/log(sqrt(3)*dims/2.0) (powerspectrum.c:40,67) -- evaluated the way the reference's own build
+ * evaluates it.  Its Makefile compiles with -ffast-math (Makefile:2), under which gcc folds log(sqrt(x)) into 0.5*log(x)
+ * and sqrt(3)*dims/2.0 into dims*(sqrt(3)/2) (checked in the disassembly of oracle/_ref: log() is called on k2 and the
+ * product is taken with a pre-halved binsperunit).  The form matters exactly where a mode sits on a bin edge: the corner
+ * mode (N/2,N/2,N/2) has binsperunit*log(kk) == nrbins-1 up to one ulp, and at PMGRID=192 the literal form puts it in the
+ * last bin while the reference's binary (and this table) put it one below.  -DKSN_LITERAL_BIN_FORMULA restores the
+ * literal evaluation. */
+static double ref_binsperunit(int dims, int nrbins)
+{
+#ifdef KSN_LITERAL_BIN_FORMULA
+    return (nrbins - 1) / log(sqrt(3) * dims / 2.0);
+#else
+    return (nrbins - 1) / log(dims * 0.8660254037844386);      /* sqrt(3)/2, correctly rounded */
+#endif
+}
+
 static double ref_bin(double binsperunit, unsigned int k2)
 {
-    const double kk = sqrt((double) k2);
-    return floor(binsperunit * log(kk));
+#ifdef KSN_LITERAL_BIN_FORMULA
+    return floor(binsperunit * log(sqrt((double) k2)));
+#else
+    return floor((0.5 * binsperunit) * log((double) k2));
+#endif
 }
 
 int ksn_bin_tables(int dims, int nrbins, const unsigned int **thresholds, const double **invwin)
@@ -26,7 +45,7 @@ int ksn_bin_tables(int dims, int nrbins, const unsigned int **thresholds, const 
         tabs.thr = malloc(sizeof(unsigned int) * nrbins);
         tabs.iw = malloc(sizeof(double) * (dims / 2 + 1));
         if (!tabs.thr || !tabs.iw) return -1;
-        const double binsperunit = (nrbins - 1) / log(sqrt(3) * dims / 2.0);
+        const double binsperunit = ref_binsperunit(dims, nrbins);
         const unsigned int k2max = 3u * (unsigned int) (dims / 2) * (unsigned int) (dims / 2);
         tabs.thr[0] = 0;
         for (int b = 1; b < nrbins; b++) {

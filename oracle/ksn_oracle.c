@@ -177,8 +177,11 @@ static int kval(long long i, int n) { return i <= n / 2 ? (int) i : (int) (i - n
 void orc_powerspectrum_sums(int dims, const void *grid, int is_double, int nrbins, long long startslab, long long nslab,
                             double *power_sum, double *keff_sum, long long *count, double *total_mass2)
 {
-    /* powerspectrum.c:36-89 */
-    const double binsperunit = (nrbins - 1) / log(sqrt(3) * dims / 2.0);
+    /* powerspectrum.c:36-89.  The bin expression floor(binsperunit*log(kk)), binsperunit = (nrbins-1)/log(sqrt(3)*dims/2.0)
+     * (:40,67) is written here as the reference's own -ffast-math build (Makefile:2) evaluates it -- log(sqrt(x)) folded
+     * into 0.5*log(x), sqrt(3)*dims/2.0 into dims*(sqrt(3)/2); seen in the disassembly of oracle/_ref -- because the corner
+     * mode (N/2,N/2,N/2) sits on the last bin edge to within one ulp and the two forms split at PMGRID=192. */
+    const double halfbinsperunit = 0.5 * ((nrbins - 1) / log(dims * 0.8660254037844386));
     const int nzc = dims / 2 + 1;
     const double *gd = grid;
     const float *gf = grid;
@@ -197,7 +200,7 @@ void orc_powerspectrum_sums(int dims, const void *grid, int is_double, int nrbin
                 const double kk = sqrt((double) ki * ki + (double) kj * kj + (double) k * k);
                 if (!(kk > 0)) continue;
                 const size_t idx = (size_t) ((i - startslab) * dims + j) * nzc + k;
-                const int b = (int) floor(binsperunit * log(kk));
+                const int b = (int) floor(halfbinsperunit * log((double) ki * ki + (double) kj * kj + (double) k * k));
                 const int mult = (k == 0 || k == dims / 2) ? 1 : 2;
                 double mod2, win;
                 if (is_double) {

@@ -131,7 +131,8 @@ needs_ref = pytest.mark.skipif(refs.ref_lib(True) is None, reason="oracle/_ref n
 
 
 @needs_ref
-@pytest.mark.parametrize("n,nrbins,dtype", [(8, 4, np.float64), (16, 8, np.float64), (32, 16, np.float64), (48, 100, np.float64), (32, 16, np.float32)])
+@pytest.mark.parametrize("n,nrbins,dtype", [(8, 4, np.float64), (16, 8, np.float64), (32, 16, np.float64), (48, 100, np.float64), (32, 16, np.float32),
+                                            (192, 96, np.float64)])   # 192: the corner mode sits on the last bin edge (1-ulp case)
 def test_k1_oracle_equals_reference(n, nrbins, dtype):
     ref = refs.ref_lib(dtype == np.float64)
     g = refs.random_grid(n, seed=n, dtype=dtype)

@@ -198,13 +198,12 @@ def test_total_power_path_and_output_files(gpu, tmp_path):
     np.testing.assert_allclose([float(r[0]) for r in rows], k[:nret] * 2 * np.pi / refs.BOX, rtol=6e-6)    # %g keeps 6 significant digits
 
 
-@pytest.mark.parametrize("hybrid,masses", [(False, (0.1, 0.1, 0.1)), (True, (0.2, 0.1, 0.3))])
-def test_hundred_step_run_tracks_oracle(gpu, hybrid, masses):
+@pytest.mark.parametrize("n,hybrid,masses", [(32, False, (0.1, 0.1, 0.1)), (32, True, (0.2, 0.1, 0.3)), (64, True, (0.06, 0.1, 0.15))])
+def test_hundred_step_run_tracks_oracle(gpu, n, hybrid, masses):
     """A whole simulated run, a = 0.01 ... 1.0 in 110 PM steps (kept and dropped rows, the history growing to ~100 rows, the
     hybrid switch-on at a = 0.333): after EVERY step delta_nu and the row bookkeeping must agree with the CPU oracle to the
     north-star tolerance.  ~10^5 adaptive-quadrature decisions are replayed; one flipped decision would show up as ~1e-7."""
     o = refs.orc()
-    n = 32
     g = refs.random_grid(n, seed=77)
     refs.init_module(gpu, n, masses=masses, hybrid=hybrid)
     dt = capi.global_delta_tot_table()

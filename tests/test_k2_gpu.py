@@ -162,3 +162,42 @@ def test_update_sequence_matches_oracle_port(gpu, state):
         assert o.orc_get_delta_nu_update(C.byref(od), a, n, refs.dptr(state["kk"]), refs.dptr(state["delta_cdm"]), refs.dptr(w), tl, tt, nt) == 0
         assert d.ia == od.ia
         np.testing.assert_allclose(g, w, rtol=1e-10, atol=0)
+
+
+@pytest.mark.parametrize("masses", [(0.1, 0.1, 0.1), (0.2, 0.1, 0.3)])
+def test_benchmark_shape_matches_oracle(gpu, masses):
+    """K2 at the shape bench.py times (BASELINE configs 3-4): ~780 k bins up to the grid's Nyquist corner, a 98-row
+    delta_tot history, hybrid neutrinos on and a > NuPartTime -- the regime where the highest-k bins need > 100
+    applications of the 61-point rule.  delta_nu against the oracle restatement, three consecutive steps."""
+    o = refs.orc()
+    nk, rows = 783, 98
+    om = refs.make_omnu(gpu, masses)
+    gpu.init_hybrid_nu(C.byref(om.hybnu), (C.c_double * 3)(*masses), 500.0, 2.99792458e10 / 1e5, 0.333, om.kBtnu)
+    refs.set_background(gpu, om)
+    tr = refs.load_transfer(gpu)
+    kk = np.geomspace(2 * np.pi / refs.BOX * 1.01, 2 * np.pi / refs.BOX * 1700, nk)
+    dcdm = 1e5 * (kk / kk[0]) ** -0.8
+    d = refs.new_delta_tot(gpu, om, nk)
+    gpu.delta_tot_init(C.byref(d), nk, refs.dptr(kk), refs.dptr(dcdm), C.byref(tr), 0.01)
+    oc = refs.orc_cosmo(masses, hybrid=True)
+    od = refs.OrcDtot()
+    o.orc_dtot_alloc(C.byref(od), nk, 0.01, 1.0, refs.OMEGA0, C.byref(oc), refs.UNIT_TIME, refs.UNIT_LENGTH)
+    tl, tt = capi.c_double_p(), capi.c_double_p()
+    nt = o.orc_transfer_read(os.path.join(refs.GOLDEN, "ics_transfer_99.dat").encode(), refs.BOX, refs.UNIT_LENGTH, refs.UNIT_LENGTH * 1e3, C.byref(tl), C.byref(tt))
+    o.orc_dtot_init(C.byref(od), nk, refs.dptr(kk), refs.dptr(dcdm), tl, tt, nt, 0.01)
+    for i in range(1, rows):                       # the same synthetic history in both tables: delta_tot grows like a
+        d.scalefact[i] = od.scalefact[i] = math.log(0.01 * (i + 1))
+        for k in range(nk):
+            d.delta_tot[k][i] = d.delta_tot[k][0] * (i + 1)
+            od.delta_tot[k * od.namax + i] = od.delta_tot[k * od.namax] * (i + 1)
+    d.ia = od.ia = rows
+    worst, deepest = 0.0, 0
+    for a in (0.981, 0.982, 0.9915):               # two dropped rows, then a kept one
+        g, w = np.zeros(nk), np.zeros(nk)
+        gpu.get_delta_nu_update(C.byref(d), a, nk, refs.dptr(kk), refs.dptr(dcdm), refs.dptr(g), C.byref(tr))
+        deepest = max(deepest, gpu.ksn_last_k2_max_passes())
+        assert o.orc_get_delta_nu_update(C.byref(od), a, nk, refs.dptr(kk), refs.dptr(dcdm), refs.dptr(w), tl, tt, nt) == 0
+        assert d.ia == od.ia
+        worst = max(worst, float(np.max(np.abs(g / w - 1))))
+    assert deepest > 60                             # the deep-bisection regime was really entered
+    assert worst < 1e-10, worst

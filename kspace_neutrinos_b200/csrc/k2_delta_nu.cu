@@ -18,6 +18,7 @@
 // default 16384 points, far inside the 1e-10 parity budget).
 #include "ksn_internal.cuh"
 #include "ksn_gk61_tables.h"
+#include "ksn_qag_spec.h"
 
 #include <float.h>
 #include <math.h>
@@ -33,6 +34,9 @@ __constant__ double c_wg[15] = KSN_WG30_INIT;
 
 constexpr int K2_THREADS = 128;
 constexpr int QAG_LIMIT = 200;      // GSL_VAL, kspace_neutrino_const.h:19
+#ifndef KSN_K2_SPEC_DEFAULT
+#define KSN_K2_SPEC_DEFAULT 1       // see k2_spec_width()
+#endif
 
 enum { Q_OK = 0, Q_EROUND = 18, Q_ESING = 21, Q_EMAXITER = 11, Q_EFAILED = 5 };
 
@@ -558,6 +562,223 @@ k2_delta_nu_kernel(const __grid_constant__ K2Dev p)
     }
 }
 
+// ---------------------------------------------------------------- the per-k integral, bisections integrated ahead of time
+// K2's time is the critical path of its deepest bin: up to 57 SEQUENTIAL bisections of ~5 us each with hybrid neutrinos.
+// A bisection's values depend only on the interval, so a CTA of 128 M threads integrates the halves of the M worst
+// intervals at once and warp 0 then replays QAG's loop over the cached results (ksn_qag_spec.h): same decisions, same
+// sums in the same order, hence bit-identical output -- with up to M loop trips per pass through the integrand.
+template <int M>
+struct SpecShared {
+    QagSpecList L;
+    double red[4 * M][4];      // per warp: Kronrod, Gauss, |f|, |f - mean| partial sums
+    double q0[4];              // the rule on the whole interval: result, abserr, resabs, resasc
+    double result, abserr;
+    int sel[M];                // slots whose halves the next pass integrates
+    int nsel, done, status;
+    unsigned passes, rules;    // rule applications of the sequential algorithm / actually computed
+};
+
+// 2M groups of 64 threads: group g integrates half (g & 1) of slot sel[g >> 1]; `whole`: group 0 integrates slot 0 itself.
+// Same arithmetic, same reduction tree as qk61_pair.  Must be called by all 128 M threads; ends with a barrier.
+template <int M, class F>
+__device__ void qk61_groups(const F &f, SpecShared<M> &S, bool whole)
+{
+    const int tid = threadIdx.x, g = tid >> 6, n = tid & 63, warp = tid >> 5;
+    const int which = g >> 1, child = g & 1;
+    const bool gactive = whole ? g == 0 : which < S.nsel;
+    int slot = 0;
+    double a = 0.0, b = 0.0;
+    if (gactive) {
+        slot = whole ? 0 : S.sel[which];
+        const double a_i = S.L.a[slot], b_i = S.L.b[slot];
+        if (whole) {
+            a = a_i; b = b_i;
+        } else {
+            const double mid = 0.5 * (a_i + b_i);
+            a = child ? mid : a_i;
+            b = child ? b_i : mid;
+        }
+    }
+    const double center = 0.5 * (a + b), half_length = 0.5 * (b - a);
+    const bool active = gactive && n < 61;
+    const int j = n <= 30 ? n : 60 - n;
+    double fv = 0.0, wk = 0.0, wgs = 0.0;
+    if (active) {
+        const double absc = half_length * c_xgk[j];
+        fv = f(n <= 30 ? center - absc : center + absc);
+        wk = c_wgk[j];
+        wgs = (j & 1) ? c_wg[j >> 1] : 0.0;
+    }
+    const double sk = warp_sum(wk * fv), sg = warp_sum(wgs * fv), sa = warp_sum(wk * fabs(fv));
+    if ((tid & 31) == 0) { S.red[warp][0] = sk; S.red[warp][1] = sg; S.red[warp][2] = sa; }
+    __syncthreads();
+    const double kron = S.red[2 * g][0] + S.red[2 * g + 1][0];
+    const double gaus = S.red[2 * g][1] + S.red[2 * g + 1][1];
+    const double rabs = S.red[2 * g][2] + S.red[2 * g + 1][2];
+    const double mean = kron * 0.5;
+    const double sc = warp_sum(active ? wk * fabs(fv - mean) : 0.0);
+    if ((tid & 31) == 0) S.red[warp][3] = sc;
+    __syncthreads();
+    if (gactive && n == 0) {
+        const double rasc = S.red[2 * g][3] + S.red[2 * g + 1][3];
+        QkOut o;
+        o.result = kron * half_length;
+        o.resabs = rabs * fabs(half_length);
+        o.resasc = rasc * fabs(half_length);
+        o.abserr = rescale_error_d((kron - gaus) * half_length, o.resabs, o.resasc);
+        if (whole) {
+            S.q0[0] = o.result; S.q0[1] = o.abserr; S.q0[2] = o.resabs; S.q0[3] = o.resasc;
+        } else {
+            S.L.cr[2 * slot + child] = o.result;
+            S.L.ce[2 * slot + child] = o.abserr;
+            S.L.cf[2 * slot + child] = o.resasc != o.abserr;
+        }
+    }
+    __syncthreads();
+}
+
+// Slot with the largest error estimate, the lowest index among equals (what a sequential scan with '>' finds).
+// skip != nullptr: only slots with skip[k] == 0 and e[k] > floor; -1 if there is none.  One warp, all lanes.
+__device__ __forceinline__ int warp_argmax_err(const double *e, const unsigned char *skip, double floor_, int size, int lane)
+{
+    int best = -1;
+    double bv = 0.0;
+    for (int k = lane; k < size; k += 32) {
+        if (skip && (skip[k] || !(e[k] > floor_))) continue;
+        const double v = e[k];
+        if (best < 0 || v > bv) { bv = v; best = k; }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, d);
+        const int oi = __shfl_xor_sync(0xffffffffu, best, d);
+        if (oi >= 0 && (best < 0 || ov > bv || (ov == bv && oi < best))) { bv = ov; best = oi; }
+    }
+    return best;
+}
+
+// gsl_integration_qag (key 6) by a CTA of 128 M threads; all threads return the same values.
+template <int M, class F>
+__device__ int qag61_spec(const F &f, double a, double b, double epsabs, double epsrel, int limit,
+                          SpecShared<M> &S, double *result, double *abserr, unsigned *passes, unsigned *rules)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { S.L.a[0] = a; S.L.b[0] = b; S.nsel = 0; S.done = 0; }
+    __syncthreads();
+    qk61_groups<M>(f, S, true);
+    QagSpecState s;                       // lives in lane 0 of warp 0
+    unsigned nrules = 1;
+    int size = 1;                         // uniform in warp 0
+    if (warp == 0) {
+        if (lane == 0) {
+            int st = QAGS_OK;
+            if (qags_begin(s, S.L, a, b, epsabs, epsrel, limit, S.q0[0], S.q0[1], S.q0[2], S.q0[3], &st)) {
+                S.result = S.q0[0]; S.abserr = S.q0[1]; S.status = st; S.passes = 1; S.rules = 1; S.done = 1;
+            } else {
+                S.L.cached[0] = 1; S.sel[0] = 0; S.nsel = 1;
+            }
+        }
+    }
+    for (;;) {
+        __syncthreads();                  // selection (or the verdict) of warp 0 is visible
+        if (S.done) break;
+        qk61_groups<M>(f, S, false);
+        if (warp != 0) continue;
+        nrules += 2 * S.nsel;
+        // replay QAG's loop over the cached halves
+        for (;;) {
+            const int i = warp_argmax_err(S.L.e, nullptr, 0.0, size, lane);
+            int act = 1;                  // 0: one trip made, go on; 1: slot i must be integrated first; 2: finished
+            double floor_ = 0.0;
+            if (lane == 0) {
+                if (S.L.cached[i]) act = qags_apply(s, S.L, i) ? 0 : 2;
+                else floor_ = qags_spec_threshold(s);
+            }
+            act = __shfl_sync(0xffffffffu, act, 0);
+            __syncwarp();                 // list updates of lane 0 are visible to the scans below
+            if (act != 1) size++;
+            if (act == 0) continue;
+            if (act == 2) {
+                if (lane == 0) {
+                    double res, err;
+                    S.status = qags_finish(s, S.L, &res, &err);
+                    S.result = res; S.abserr = err; S.passes = s.passes; S.rules = nrules; S.done = 1;
+                }
+                break;
+            }
+            // next pass: slot i, and the worst of the other slots the loop is likely to reach
+            floor_ = __shfl_sync(0xffffffffu, floor_, 0);
+            if (lane == 0) { S.L.cached[i] = 1; S.sel[0] = i; }
+            int ns = 1;
+            for (; ns < M; ns++) {
+                __syncwarp();
+                const int jn = warp_argmax_err(S.L.e, S.L.cached, floor_, size, lane);
+                if (jn < 0) break;
+                if (lane == 0) { S.L.cached[jn] = 1; S.sel[ns] = jn; }
+            }
+            if (lane == 0) S.nsel = ns;
+            break;
+        }
+    }
+    *result = S.result;
+    *abserr = S.abserr;
+    if (passes) *passes = S.passes;
+    if (rules) *rules = S.rules;
+    const int st = S.status;
+    __syncthreads();
+    return st;
+}
+
+template <int M, int MINB>
+__global__ void __launch_bounds__(K2_THREADS * M, MINB)
+k2_delta_nu_spec_kernel(const __grid_constant__ K2Dev p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ SpecShared<M> S;
+    double *sx = (double *) smem_raw, *sy = sx + p.Na, *sc = sy + p.Na, *sb = sc + p.Na, *sd = sb + p.Na;
+    __shared__ double enq_s[19];
+    const int ik = p.k_first + (int) (gridDim.x - 1 - blockIdx.x);      // deepest (highest-k) bins are scheduled first
+    const int sp = blockIdx.y;
+    if (threadIdx.x < 19) {
+        const int n = threadIdx.x + 1;
+        enq_s[threadIdx.x] = ((n & 1) ? 1.0 : -1.0) * exp(-(double) n * p.qc[sp]);
+    }
+    for (int i = threadIdx.x; i < p.Na; i += blockDim.x) {
+        sx[i] = p.scalefact[i];
+        sy[i] = p.delta_tot[(size_t) ik * p.namax + i];
+    }
+    __syncthreads();
+    const double k = p.wavenum[ik], mnubykT = p.mnubykT[sp];
+    const double fsl_A0a = p.fslengths[0];
+    const double specJ0 = specialJ_fit_d(k * fsl_A0a / (mnubykT > 0 ? mnubykT : 1));
+    double dnu = specJ0 * p.delta_nu_init[ik] * (1. + p.deriv_prefac * fsl_A0a);
+    int st = Q_OK;
+    unsigned passes = 0, rules = 0;
+    if (p.integrate[sp]) {
+        if (p.Na > 2) {
+            for (int i = threadIdx.x; i < p.Na - 2; i += blockDim.x) sc[i + 1] = spline_rhs(sx, sy, i);
+            __syncthreads();
+            if (threadIdx.x == 0) spline_solve_seq(p.Na, p.dt_alpha, p.dt_gamma, sc);
+            __syncthreads();
+            for (int i = threadIdx.x; i < p.Na - 1; i += blockDim.x) cspline_segment(sx, sy, sc, i, sb[i], sd[i]);
+            __syncthreads();
+        }
+        DeltaNuIntegrand f;
+        f.P = &p; f.sx = sx; f.sy = sy; f.sc = sc; f.sb = sb; f.sd = sd;
+        f.k = k; f.mnubykT = mnubykT; f.qc = p.qc[sp]; f.enq = enq_s;
+        f.fs_x0 = p.loga0;
+        f.fs_inv_dx = (p.Nfs - 1.) / (p.loga - p.loga0);
+        double res, err;
+        st = qag61_spec<M>(f, p.loga0, p.loga, 0.0, p.relerr[sp], QAG_LIMIT, S, &res, &err, &passes, &rules);
+        dnu += p.delta_nu_prefac * res;
+    }
+    if (threadIdx.x == 0) {
+        p.out[(size_t) sp * p.nk + ik] = dnu;
+        p.status[(size_t) sp * p.nk + ik] = st | ((int) passes << 8);     // the SEQUENTIAL algorithm's count, as k2_delta_nu_kernel reports it
+        if (p.evals && rules) atomicAdd(p.evals, 61ull * rules);          // integrand evaluations actually made
+    }
+}
+
 static BgPatch g_bg_patch[BG_MAX_PATCH];
 static int g_bg_npatch = 0, g_bg_flagged = 0;
 
@@ -580,6 +801,16 @@ struct Bump {
 }  // namespace ksn
 
 using namespace ksn;
+
+// How many intervals a K2 CTA bisects per pass through the integrand (k2_delta_nu_spec_kernel<M>); 1 = the plain
+// sequential kernel.  KSN_K2_SPEC overrides the default.
+static int k2_spec_width(void)
+{
+    const char *env = getenv("KSN_K2_SPEC");
+    const int m = env ? atoi(env) : KSN_K2_SPEC_DEFAULT;
+    return m >= 2 && m <= 4 ? m : 1;
+}
+extern "C" int ksn_k2_spec_width(void) { return k2_spec_width(); }
 
 static unsigned long long g_last_evals = 0;
 static unsigned g_max_passes = 0;
@@ -772,7 +1003,19 @@ extern "C" int ksn_delta_nu_integrate(const ksn_delta_nu_args *A, double *out, u
     p.delta_nu_init = p.wavenum + nk;
     p.fsscales = d_fsscales; p.fslengths = d_fslengths; p.fs_c = d_fsc; p.fs_b = d_fsb; p.fs_d = d_fsd; p.dt_alpha = d_dta; p.dt_gamma = d_dtg;
     p.out = d_out; p.status = d_status; p.evals = d_evals; p.bg = bg;
-    if (k_count > 0) k2_delta_nu_kernel<<<dim3(k_count, ns), K2_THREADS, 5 * (size_t) Na * sizeof(double), c.stream>>>(p);
+    if (k_count > 0) {
+        const dim3 grid(k_count, ns);
+        const size_t smem = 5 * (size_t) Na * sizeof(double);
+        switch (k2_spec_width()) {
+        case 2: k2_delta_nu_spec_kernel<2, 3><<<grid, 2 * K2_THREADS, smem, c.stream>>>(p); break;
+        case 3: k2_delta_nu_spec_kernel<3, 2><<<grid, 3 * K2_THREADS, smem, c.stream>>>(p); break;
+        case 4:
+            if (getenv("KSN_K2_SPEC4_ONE_PER_SM")) k2_delta_nu_spec_kernel<4, 1><<<grid, 4 * K2_THREADS, smem, c.stream>>>(p);
+            else k2_delta_nu_spec_kernel<4, 2><<<grid, 4 * K2_THREADS, smem, c.stream>>>(p);
+            break;
+        default: k2_delta_nu_kernel<<<grid, K2_THREADS, smem, c.stream>>>(p); break;
+        }
+    }
     c.launches++;
     KSN_CUDA(cudaGetLastError());
     double *h_out = h + n_in;

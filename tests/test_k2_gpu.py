@@ -201,3 +201,55 @@ def test_benchmark_shape_matches_oracle(gpu, masses):
         worst = max(worst, float(np.max(np.abs(g / w - 1))))
     assert deepest > 60                             # the deep-bisection regime was really entered
     assert worst < 1e-10, worst
+
+
+def _benchmark_state(gpu, om, nk=783, rows=98):
+    """The synthetic 98-row history of test_benchmark_shape_matches_oracle, product side only."""
+    tr = refs.load_transfer(gpu)
+    kk = np.geomspace(2 * np.pi / refs.BOX * 1.01, 2 * np.pi / refs.BOX * 1700, nk)
+    dcdm = 1e5 * (kk / kk[0]) ** -0.8
+    d = refs.new_delta_tot(gpu, om, nk)
+    gpu.delta_tot_init(C.byref(d), nk, refs.dptr(kk), refs.dptr(dcdm), C.byref(tr), 0.01)
+    for i in range(1, rows):
+        d.scalefact[i] = math.log(0.01 * (i + 1))
+        for k in range(nk):
+            d.delta_tot[k][i] = d.delta_tot[k][0] * (i + 1)
+    d.ia = rows
+    return d, kk, dcdm, tr
+
+
+@pytest.mark.parametrize("hybrid", [True, False])
+@pytest.mark.parametrize("masses", [(0.1, 0.1, 0.1), (0.2, 0.1, 0.3)])
+def test_speculative_bisection_is_bit_identical(gpu, masses, hybrid):
+    """k2_delta_nu_spec_kernel<M> integrates the halves of the M worst intervals at once and replays QAG's loop over the
+    cached results (csrc/ksn_qag_spec.h).  The replay makes the sequential loop's decisions in the sequential order, so
+    delta_nu, the per-bin status and the count of rule applications must equal the sequential kernel's BIT FOR BIT, for
+    every width, at the benchmark's shape (deepest bins > 100 rule applications with hybrid neutrinos)."""
+    om = refs.make_omnu(gpu, masses)
+    if hybrid:
+        gpu.init_hybrid_nu(C.byref(om.hybnu), (C.c_double * 3)(*masses), 500.0, 2.99792458e10 / 1e5, 0.333, om.kBtnu)
+    refs.set_background(gpu, om)
+    runs = {}
+    old = os.environ.get("KSN_K2_SPEC")
+    try:
+        for width in (1, 2, 3, 4):
+            os.environ["KSN_K2_SPEC"] = str(width)
+            assert gpu.ksn_k2_spec_width() == width
+            d, kk, dcdm, tr = _benchmark_state(gpu, om)
+            outs = []
+            for a in (0.981, 0.982, 0.9915):
+                g = np.zeros(len(kk))
+                gpu.get_delta_nu_update(C.byref(d), a, len(kk), refs.dptr(kk), refs.dptr(dcdm), refs.dptr(g), C.byref(tr))
+                outs.append((g.copy(), gpu.ksn_last_k2_max_passes(), d.ia))
+            runs[width] = outs
+    finally:
+        if old is None:
+            os.environ.pop("KSN_K2_SPEC", None)
+        else:
+            os.environ["KSN_K2_SPEC"] = old
+    if hybrid:
+        assert max(p for _, p, _ in runs[1]) > 60
+    for width in (2, 3, 4):
+        for (g1, p1, ia1), (gm, pm, iam) in zip(runs[1], runs[width]):
+            assert ia1 == iam and p1 == pm, (width, p1, pm)
+            assert np.array_equal(g1, gm), (width, float(np.max(np.abs(gm / g1 - 1))))

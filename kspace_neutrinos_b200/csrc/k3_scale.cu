@@ -182,7 +182,7 @@ __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned) 
 template <typename real, bool ONE_ROW>
 __global__ void __launch_bounds__(K3_TMA_THREADS, 8)
 k3_scale_tma_kernel(C2<real> *__restrict__ grid, int nrows, int rows_per_cta, int N, long long plane0,
-                    const double *__restrict__ tab, const K3Params prm, const K3Greens gr)
+                    const double *__restrict__ tab, const K3Params prm, const K3Greens gr, int segs, int seg_len)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
@@ -190,11 +190,20 @@ k3_scale_tma_kernel(C2<real> *__restrict__ grid, int nrows, int rows_per_cta, in
     const K3Seg *seg = (const K3Seg *) tab;
     const unsigned short *cellv = (const unsigned short *) (seg + prm.n + 1);
     const int L = N / 2 + 1;
-    const int row0 = blockIdx.x * rows_per_cta;
-    const int nr = min(rows_per_cta, nrows - row0);
-    const int nel = nr * L;
+    // ONE_ROW: the CTA owns segment (blockIdx % segs) of row (blockIdx / segs) -- the whole row when segs == 1, a piece of
+    // seg_len modes when a row does not fit one CTA (PMGRID = 4096: two pieces of 1025 and 1024 modes).  Otherwise a
+    // block of rows_per_cta whole rows.
+    int row0, nel, z0 = 0;
+    if (ONE_ROW) {
+        row0 = (int) (blockIdx.x / (unsigned) segs);
+        z0 = (int) (blockIdx.x - (unsigned) row0 * (unsigned) segs) * seg_len;
+        nel = min(seg_len, L - z0);
+    } else {
+        row0 = blockIdx.x * rows_per_cta;
+        nel = min(rows_per_cta, nrows - row0) * L;
+    }
     const unsigned bytes = (unsigned) nel * (unsigned) sizeof(C2<real>);
-    C2<real> *base = grid + (size_t) row0 * L;
+    C2<real> *base = grid + (size_t) row0 * L + z0;
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -223,10 +232,10 @@ k3_scale_tma_kernel(C2<real> *__restrict__ grid, int nrows, int rows_per_cta, in
         const int e = threadIdx.x + K3_TMA_THREADS * k;
         smth[k] = 1.0;
         if (e < nel) {
-            int k2i, z = e;
+            int k2i, z = z0 + e;
             double wxy4 = w0;
             if (ONE_ROW) {
-                k2i = c0 + e * e;
+                k2i = c0 + z * z;
             } else {
                 const int rl = e / L;
                 z = e - rl * L;
@@ -361,17 +370,21 @@ int k3_launch(void *dgrid, int real_bytes, int dims, long long plane0_global, lo
     if (nrows == 0) return KSN_OK;
     constexpr int U = 4;
     const int L = dims / 2 + 1;
-    if (real_bytes == 8 && !getenv("KSN_K3_NOTMA") && L <= K3_TMA_THREADS * K3_EPT) {   // bulk copies need 16-byte granules: double grids
-        // ~16 KB of grid per CTA (at least one row): one row at PMGRID=2048, 7 CTAs per SM inside a 132 KB carve-out
+    const int cap = K3_TMA_THREADS * K3_EPT;                    // modes one CTA holds
+    const int segs = (L + cap - 1) / cap;                       // pieces per row when a row is longer than that (PMGRID > 2302)
+    const bool split_ok = segs == 1 || (!getenv("KSN_K3_NOSPLIT") && (long long) nrows * segs <= 0x7fffffffLL);
+    if (real_bytes == 8 && !getenv("KSN_K3_NOTMA") && split_ok) {   // bulk copies need 16-byte granules: double grids
+        // ~16 KB of grid per CTA: one row at PMGRID=2048 (7 CTAs per SM inside a 132 KB carve-out), half a row at 4096
         const size_t row_bytes = (size_t) L * 2 * real_bytes;
-        int rpc = (int) ((size_t) K3_TMA_THREADS * K3_EPT / L);
+        int rpc = segs > 1 ? 1 : cap / L;
         while (rpc > 1 && rpc * row_bytes > 18432) rpc--;
-        const size_t smem = rpc * row_bytes + 128;
-        const int nct = (nrows + rpc - 1) / rpc;
+        const int seg_len = (L + segs - 1) / segs;
+        const size_t smem = (segs > 1 ? (size_t) seg_len * 2 * real_bytes : rpc * row_bytes) + 128;
+        const int nct = segs > 1 ? nrows * segs : (nrows + rpc - 1) / rpc;
         auto go = [&](auto kern) -> int {
             KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
             KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 58));   // ~132 of 228 KB: L1 keeps the tables
-            kern<<<nct, K3_TMA_THREADS, smem, c.stream>>>((C2<double> *) dgrid, nrows, rpc, dims, plane0_global, c.d_k3tab, g_k3prm, gr);
+            kern<<<nct, K3_TMA_THREADS, smem, c.stream>>>((C2<double> *) dgrid, nrows, rpc, dims, plane0_global, c.d_k3tab, g_k3prm, gr, segs, seg_len);
             return KSN_OK;
         };
         const int rcl = rpc == 1 ? go(k3_scale_tma_kernel<double, true>) : go(k3_scale_tma_kernel<double, false>);

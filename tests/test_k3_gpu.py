@@ -122,3 +122,44 @@ def test_fused_step_entry_equals_step_then_greens(gpu):
     # differ from the tile kernel's in the last bits)
     np.testing.assert_allclose(outs[0][2], outs[1][2], rtol=1e-12, atol=0)
     np.testing.assert_allclose(outs[1][0], refs.greens_numpy(outs[0][0], 0, asmth2), rtol=1e-11, atol=0)
+
+
+@pytest.mark.parametrize("start,greens", [(0, False), (0, True), (3000, False)])
+def test_long_rows_split_between_ctas_at_pmgrid_4096(gpu, start, greens):
+    """A row of PMGRID = 4096 (2049 modes, 32.8 KB) does not fit the one-row-per-CTA bulk-copy kernel: it is cut into two
+    pieces of 1025 and 1024 modes, one CTA each.  Thin slab of the full-size grid against the numpy restatement, and bit
+    for bit against the plain-load kernel (KSN_K3_NOSPLIT), which computes the same factors."""
+    import os
+    from kspace_neutrinos_b200 import capi
+    n, nslab, box = 4096, 2, refs.BOX
+    rng = np.random.default_rng(11 + start)
+    g = rng.standard_normal((nslab, n, n // 2 + 1, 2))
+    kmin, kmax = 2 * np.pi / box, np.sqrt(3) * (n / 2) * 2 * np.pi / box
+    nk = 300                                                         # jittered, but no two knots closer than 0.6 of the mean spacing
+    step = (np.log(kmax * 0.8) - np.log(kmin * 1.3)) / (nk - 1)
+    logkk = np.log(kmin * 1.3) + step * (np.arange(nk) + rng.uniform(-0.2, 0.2, nk))
+    ratio, norm = 0.2 + 0.6 * rng.random(nk), 0.0123
+    asmth2 = (2 * np.pi * 1.25 / n) ** 2
+    iw = _invwin(gpu, n)
+
+    def run():
+        d = refs.DeviceBuffer(gpu, g)
+        if greens:
+            capi.check(gpu.ksn_scale_modes_greens(d.ptr, 8, n, start, nslab, box, refs.dptr(logkk), refs.dptr(ratio), len(logkk), norm, iw, asmth2))
+        else:
+            capi.check(gpu.ksn_scale_modes(d.ptr, 8, n, start, nslab, box, refs.dptr(logkk), refs.dptr(ratio), len(logkk), norm))
+        out = d.download(g)
+        d.free()
+        return out
+
+    split = run()
+    os.environ["KSN_K3_NOSPLIT"] = "1"
+    try:
+        plain = run()
+    finally:
+        del os.environ["KSN_K3_NOSPLIT"]
+    assert np.array_equal(split, plain)
+    want = refs.k3_numpy(g, start, box, logkk, ratio, norm)
+    if greens:
+        want = refs.greens_numpy(want, start, asmth2)
+    np.testing.assert_allclose(split, want, rtol=1e-10, atol=0)

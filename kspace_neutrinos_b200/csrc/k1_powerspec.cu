@@ -27,6 +27,7 @@
 
 #include <math.h>
 #include <type_traits>
+#include <algorithm>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -401,6 +402,9 @@ k1_pair_kernel(const Cplx<real> *__restrict__ grid, int nrows, int N, int nrbins
 //    queued runs of different lanes hit disjoint bins (plain read-modify-write, fixed order), except the FIRST run of a
 //    lane, which may share its bin with the runs of the lanes before it: those 32 partial sums are combined by one
 //    segmented warp scan per tile.
+#ifndef KSN_K1_WIN_DEFAULT
+#define KSN_K1_WIN_DEFAULT 0              // see k1_tile_config()
+#endif
 constexpr int K1T_MAXW = 16;
 constexpr int K1T_QRUNS = 8;              // queue slots per lane: up to seven closed runs and the open one
 
@@ -429,11 +433,16 @@ __device__ __forceinline__ double queue_get(unsigned addr)
 }
 
 // CT > 0: modes per lane known at compile time (walk fully unrolled, weights in registers); CT == 0: run-time C.
-template <int CT>
+// WIN (bin window): at PMGRID = 4096 a warp's private copy of all 2048 bins (16 KB) leaves shared memory for six warps
+// only.  Bins are logarithmic, so all but a sliver of the rows (those within ~60 grid units of the k_x = k_y = 0 axis at
+// 4096) touch only the upper part of the bin range: with WIN a warp keeps the bins >= hot_lo in shared memory and the
+// rarely used ones below in a global-memory array of its own (`cold`, read and written through L1 by this warp only, in
+// the same fixed order), which makes room for eight warps again.
+template <int CT, bool WIN>
 __global__ void __launch_bounds__((CT == 5 || CT == 9 ? K1T_MAXW : 8) * 32, 1)
 k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbins, long long plane0, float binscale,
                const unsigned *__restrict__ thr, const double *__restrict__ iw, double *__restrict__ partial, int accumulate,
-               int Crt, int T, int S, int stage_bytes, unsigned k2_single, int log2N)
+               int Crt, int T, int S, int stage_bytes, unsigned k2_single, int log2N, int hot_lo, double *__restrict__ cold)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int C = CT > 0 ? CT : Crt;
@@ -443,12 +452,15 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
     const double *__restrict__ iwz_g = iw + L;                 // m_z * iwz^4 (Hermitian multiplicity folded in), zeros past the row end
     unsigned char *sp = smem_raw;
     unsigned char *stages = sp;                   sp += (size_t) W * S * stage_bytes;
-    double *bins_s = (double *) sp;               sp += (size_t) W * nrbins * sizeof(double);
+    const int nhot = WIN ? nrbins - hot_lo : nrbins;           // bins a warp keeps in shared memory
+    double *bins_s = (double *) sp;               sp += (size_t) W * nhot * sizeof(double);
     double *queue_s = (double *) sp;              sp += (size_t) W * K1T_QRUNS * 32 * sizeof(double);
     unsigned long long *bars = (unsigned long long *) sp;  sp += (size_t) W * S * sizeof(unsigned long long);
     unsigned *thr_s = (unsigned *) sp;                      // nrbins + 3, padded with "never"
     for (int i = threadIdx.x; i < nrbins + 3; i += blockDim.x) thr_s[i] = i < nrbins ? thr[i] : 0xffffffffu;
-    for (int i = threadIdx.x; i < W * nrbins; i += blockDim.x) bins_s[i] = 0.0;
+    for (int i = threadIdx.x; i < W * nhot; i += blockDim.x) bins_s[i] = 0.0;
+    double *mycold = WIN ? cold + ((size_t) blockIdx.x * W + warp) * hot_lo : nullptr;
+    if (WIN) for (int i = lane; i < hot_lo; i += 32) mycold[i] = 0.0;
     // the stages start as zeros: modes past a row's end are walked like any other (weight 0), so they must be finite
     for (int i = threadIdx.x; i < W * S * stage_bytes / 16; i += blockDim.x) ((double2 *) stages)[i] = make_double2(0.0, 0.0);
     if (lane == 0) {
@@ -462,7 +474,11 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
     const int dr = (int) (stride / T), dt = (int) (stride - (long long) dr * T);     // a step of `stride` tiles in (row, tile-of-row)
     unsigned char *mystage = stages + (size_t) warp * S * stage_bytes;
     const unsigned bar0 = smem_addr(bars + warp * S);
-    double *mybins = bins_s + (size_t) warp * nrbins;
+    double *mybins = bins_s + (size_t) warp * nhot;
+    auto binp = [&](int idx) -> double * {          // where this warp keeps bin idx
+        if (WIN) return idx >= hot_lo ? mybins + (idx - hot_lo) : mycold + idx;
+        return mybins + idx;
+    };
     const unsigned q0 = smem_addr(queue_s + (size_t) warp * K1T_QRUNS * 32 + lane);   // run i of this lane: q0 + 256 i
     const unsigned le_mask = 0xffffffffu >> (31 - lane);
 
@@ -492,7 +508,7 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
     auto merge_first_runs = [&]() {
         double v1[1] = { p_facc };
         const unsigned tails = segmented_sum<1>(p_fbin, v1, lane, le_mask);
-        if (((tails >> lane) & 1u) && p_fbin != 0x7fffffff) mybins[p_fbin] = fma(v1[0], p_wxy, mybins[p_fbin]);
+        if (((tails >> lane) & 1u) && p_fbin != 0x7fffffff) { double *bp = binp(p_fbin); *bp = fma(v1[0], p_wxy, *bp); }
         __syncwarp();
     };
     double wreg[CT > 0 ? CT : 1];
@@ -590,10 +606,10 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
             double g[R - 1], m[R - 1];
 #pragma unroll
             for (int i = 1; i < R; i++)
-                if (i <= closed) { g[i - 1] = queue_get(q0 + 256u * i); m[i - 1] = mybins[fbin + i]; }
+                if (i <= closed) { g[i - 1] = queue_get(q0 + 256u * i); m[i - 1] = *binp(fbin + i); }
 #pragma unroll
             for (int i = 1; i < R; i++)
-                if (i <= closed) mybins[fbin + i] = fma(g[i - 1], wxy, m[i - 1]);
+                if (i <= closed) *binp(fbin + i) = fma(g[i - 1], wxy, m[i - 1]);
             facc = queue_get(q0);
         };
         if (single && spread <= 3) {
@@ -606,7 +622,7 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
             auto step = [&](const Cplx<double> v, double w) {
                 const double pp = fma(v.im, v.im, v.re * v.re);
                 if (k2 >= nxt) {
-                    if (b == fbin) facc = acc; else mybins[b] = fma(acc, wxy, mybins[b]);
+                    if (b == fbin) facc = acc; else { double *bp = binp(b); *bp = fma(acc, wxy, *bp); }
                     acc = 0.0;
                     do { b++; nxt = thr_s[b + 1]; } while (k2 >= nxt);
                 }
@@ -617,7 +633,7 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
             step(chunk[0], __ldg(wz) * worigin);
 #pragma unroll 1
             for (int e = 1; e < C; e++) step(chunk[e], __ldg(wz + e));
-            if (b == fbin) facc = acc; else mybins[b] = fma(acc, wxy, mybins[b]);
+            if (b == fbin) facc = acc; else { double *bp = binp(b); *bp = fma(acc, wxy, *bp); }
             __syncwarp();
             if (lane == 0 && ri < nrows) issue(ri, ti, s);
         }
@@ -634,23 +650,26 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
     double *out = partial + (size_t) blockIdx.x * nrbins;
     for (int i = threadIdx.x; i < nrbins; i += blockDim.x) {
         double sum = 0.0;
-        for (int w = 0; w < W; w++) sum += bins_s[(size_t) w * nrbins + i];
+        for (int w = 0; w < W; w++)
+            sum += !WIN ? bins_s[(size_t) w * nrbins + i]
+                        : (i >= hot_lo ? bins_s[(size_t) w * nhot + (i - hot_lo)] : cold[((size_t) blockIdx.x * W + w) * hot_lo + i]);
         out[i] = accumulate ? out[i] + sum : sum;
     }
 }
 
 static unsigned g_k1_k2_single = 0xffffffffu;
-static char g_k1_last[96] = "none";
+static char g_k1_last[192] = "none";
 
-struct K1TileCfg { int W, C, S, T, stage_bytes; size_t smem, inflight; };
+struct K1TileCfg { int W, C, S, T, stage_bytes, hot_lo; size_t smem, inflight; };
 
-static size_t k1_tile_smem(int L, int nrbins, int W, int C, int S, int *T_out, int *stage_out)
+// nhot: bins a warp keeps in shared memory (all nrbins of them without the bin window)
+static size_t k1_tile_smem(int L, int nrbins, int nhot, int W, int C, int S, int *T_out, int *stage_out)
 {
     const int TE = 32 * C, T = (L + TE - 1) / TE;
     const int stage = (int) ((((size_t) TE + 8) * 16 + 127) & ~(size_t) 127);
     if (T_out) *T_out = T;
     if (stage_out) *stage_out = stage;
-    return (size_t) W * S * stage + (size_t) W * nrbins * 8 + (size_t) W * K1T_QRUNS * 32 * 8 + (size_t) W * S * 8 +
+    return (size_t) W * S * stage + (size_t) W * nhot * 8 + (size_t) W * K1T_QRUNS * 32 * 8 + (size_t) W * S * 8 +
            (size_t) (nrbins + 3 + K1T_QRUNS) * 4 + 128;
 }
 
@@ -663,26 +682,43 @@ static int k1_tile_max_warps(int C) { return (C == 5 || C == 9) ? K1T_MAXW : 8; 
 static bool k1_tile_config(int L, int nrbins, size_t budget, int ctas, K1TileCfg *best)
 {
     best->W = 0;
+    best->hot_lo = 0;
     double best_score = -1;
     int fw = 0, fc = 0, fs = 0;
     const char *env = getenv("KSN_K1_TILE");
     if (env && sscanf(env, "%d,%d,%d", &fw, &fc, &fs) != 3) fw = 0;
+    // bin window: "0" off, "1" where all the bins do not fit for eight warps, "2" (tests) always, with a quarter of the bins
+    const char *wenv = getenv("KSN_K1_WIN");
+    const int window = wenv ? atoi(wenv) : KSN_K1_WIN_DEFAULT;
     for (int C = 1; C <= 65; C += 4)
         for (int W = 4; W <= k1_tile_max_warps(C); W++)
             for (int S = 1; S <= 4; S++) {
                 if (fw ? (W != fw || C != fc || S != fs) : S < 2) continue;
                 int T, stage;
-                const size_t smem = k1_tile_smem(L, nrbins, W, C, S, &T, &stage);
-                if (smem > budget) continue;
+                size_t smem = k1_tile_smem(L, nrbins, nrbins, W, C, S, &T, &stage);
+                const bool compile_time = C == 5 || C == 9 || C == 13 || C == 17;
+                int hot_lo = 0;
+                if (smem > budget || window == 2) {
+                    // bin window (k1_tile_kernel<CT, true>): only where all the bins fit for fewer than eight warps, only
+                    // up to eight warps, and with at least a quarter of the bins (the upper e-fold and more) in shared memory
+                    if (!window || !compile_time || C < 9 || W > 8) continue;
+                    const size_t rest = k1_tile_smem(L, nrbins, 0, W, C, S, nullptr, nullptr);
+                    if (rest >= budget) continue;
+                    int nhot = (int) ((budget - rest) / ((size_t) W * 8)) & ~31;
+                    if (window == 2) nhot = std::min(nhot, std::max(64, (nrbins / 4) & ~31));
+                    if (nhot < nrbins / 4 || nhot < 64 || nhot >= nrbins) continue;
+                    hot_lo = nrbins - nhot;
+                    smem = k1_tile_smem(L, nrbins, nhot, W, C, S, nullptr, nullptr);
+                }
                 const int TE = 32 * C;
                 if (T > 1 && C < 5) continue;                             // tiny tiles only for tiny rows
                 const double eff = (double) L / ((double) T * TE);        // lane slots that carry a mode
-                const bool compile_time = C == 5 || C == 9 || C == 13 || C == 17;
-                double score = W * (C / (C + 10.0)) * eff * (compile_time ? 1.0 : 0.88) * (1.0 + 0.01 * S);
+                double score = W * (C / (C + 10.0)) * eff * (compile_time ? 1.0 : 0.88) * (1.0 + 0.01 * S) * (hot_lo ? 0.99 : 1.0);
                 if (((long long) ctas * W) % T) score *= 0.97;            // the warp's tile-of-row changes every tile: weights reloaded
                 if (score > best_score) {
                     best_score = score;
                     best->W = W; best->C = C; best->S = S; best->T = T; best->stage_bytes = stage; best->smem = smem;
+                    best->hot_lo = hot_lo;
                     best->inflight = (size_t) W * S * TE * 16;
                 }
             }
@@ -815,25 +851,38 @@ static int k1_launch_t(const void *dgrid, int dims, int nrbins, long long plane0
         k1_tile_config(dims / 2 + 1, nrbins, c.smem_optin, c.num_sms, &tc)) {
         int log2N = -1;
         if ((dims & (dims - 1)) == 0) { log2N = 0; while ((1 << log2N) < dims) log2N++; }
+        static double *d_cold = nullptr;          // per-warp bins below the window (bin window only)
+        static size_t cold_cap = 0;
+        if (tc.hot_lo) {
+            rc = ensure_device_buffer((void **) &d_cold, &cold_cap, (size_t) ctas * tc.W * tc.hot_lo * sizeof(double));
+            if (rc) return rc;
+        }
         auto go = [&](auto kern) -> int {
             KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc.smem));
             kern<<<ctas, tc.W * 32, tc.smem, c.stream>>>((const Cplx<double> *) dgrid, nrows, dims, nrbins, plane0, binscale,
                                                          c.d_thr, c.d_iw, c.d_partial, accumulate ? 1 : 0, tc.C, tc.T, tc.S, tc.stage_bytes,
-                                                         g_k1_k2_single, log2N);
+                                                         g_k1_k2_single, log2N, tc.hot_lo, d_cold);
             return KSN_OK;
         };
         int rct;
-        switch (tc.C) {
-        case 5: rct = go(k1_tile_kernel<5>); break;
-        case 9: rct = go(k1_tile_kernel<9>); break;
-        case 13: rct = go(k1_tile_kernel<13>); break;
-        case 17: rct = go(k1_tile_kernel<17>); break;
-        default: rct = go(k1_tile_kernel<0>); break;
+        switch (tc.hot_lo ? -tc.C : tc.C) {
+        case 5: rct = go(k1_tile_kernel<5, false>); break;
+        case 9: rct = go(k1_tile_kernel<9, false>); break;
+        case 13: rct = go(k1_tile_kernel<13, false>); break;
+        case 17: rct = go(k1_tile_kernel<17, false>); break;
+        case -9: rct = go(k1_tile_kernel<9, true>); break;
+        case -13: rct = go(k1_tile_kernel<13, true>); break;
+        case -17: rct = go(k1_tile_kernel<17, true>); break;
+        default: rct = go(k1_tile_kernel<0, false>); break;
         }
         if (rct) return rct;
         c.launches++;
         KSN_CUDA(cudaGetLastError());
-        snprintf(g_k1_last, sizeof g_k1_last, "k1_tile_kernel (%d warps x %d modes per lane, %d stages, %d tiles per row)", tc.W, tc.C, tc.S, tc.T);
+        if (tc.hot_lo)
+            snprintf(g_k1_last, sizeof g_k1_last, "k1_tile_kernel (%d warps x %d modes per lane, %d stages, %d tiles per row, bins >= %d of %d in shared memory)",
+                     tc.W, tc.C, tc.S, tc.T, tc.hot_lo, nrbins);
+        else
+            snprintf(g_k1_last, sizeof g_k1_last, "k1_tile_kernel (%d warps x %d modes per lane, %d stages, %d tiles per row)", tc.W, tc.C, tc.S, tc.T);
         *ctas_out = ctas;
         *stride_out = NV * nrbins;
         return KSN_OK;

@@ -241,3 +241,65 @@ def test_full_size_slabs_kernels_agree(gpu):
         live = first[0] != 0
         np.testing.assert_allclose(tile[0][live], first[0][live], rtol=2e-13)
         np.testing.assert_allclose(pair[0][live], first[0][live], rtol=2e-13)
+
+
+@pytest.mark.parametrize("n,start,nslab", [(256, 0, 256), (256, 100, 31), (512, 0, 64), (512, 250, 24)])
+def test_bin_window_kernel_agrees_small(gpu, n, start, nslab, monkeypatch):
+    """k1_tile_kernel<CT, true> keeps only the upper bins of a warp's private copy in shared memory and the rarely used
+    lower ones in a global-memory array of the warp's own.  KSN_K1_WIN=2 forces the window on small grids with only a
+    QUARTER of the bins in shared memory, so the global-memory path is exercised hard; sums must equal the plain tile
+    kernel's and the three-sum kernel's to rounding, run to run bit for bit."""
+    nrbins = n // 2
+    g = refs.random_grid(n, seed=2 * n + start)[start:start + nslab].copy()
+    d = refs.DeviceBuffer(gpu, g)
+    monkeypatch.setenv("KSN_NO_GEOM_CACHE", "1")
+    full = _sums(gpu, g, nrbins, start, nslab, pointer=d.ptr)
+    monkeypatch.delenv("KSN_NO_GEOM_CACHE")
+    _sums(gpu, g, nrbins, start, nslab, pointer=d.ptr)              # fills the geometry cache
+    monkeypatch.setenv("KSN_K1_WIN", "0")
+    plain = _sums(gpu, g, nrbins, start, nslab, pointer=d.ptr)
+    assert b"k1_tile_kernel" in gpu.ksn_last_k1_kernel() and b"in shared memory" not in gpu.ksn_last_k1_kernel()
+    monkeypatch.setenv("KSN_K1_WIN", "2")
+    win = _sums(gpu, g, nrbins, start, nslab, pointer=d.ptr)
+    name = gpu.ksn_last_k1_kernel()
+    assert b"k1_tile_kernel" in name and f"of {nrbins} in shared memory".encode() in name, name
+    win2 = _sums(gpu, g, nrbins, start, nslab, pointer=d.ptr)
+    d.free()
+    assert np.array_equal(win[0], win2[0])
+    assert np.array_equal(full[2], win[2]) and win[3] == full[3]
+    live = full[0] != 0
+    assert np.array_equal(live, win[0] != 0)
+    np.testing.assert_allclose(win[0][live], plain[0][live], rtol=2e-13)
+    np.testing.assert_allclose(win[0][live], full[0][live], rtol=2e-13)
+
+
+def test_bin_window_kernel_agrees_at_pmgrid_4096(gpu, monkeypatch):
+    """At PMGRID = 4096 (2048 bins, 16 KB per warp) the window is what makes room for eight warps.  Slabs of the full-size
+    grid -- one holding the k_x = k_y = 0 axis, whose rows reach the lowest bins -- against the six-warp kernel without
+    the window and against the scan-based kernel."""
+    from kspace_neutrinos_b200 import capi
+    n, nrbins = 4096, 2048
+    for start, nslab in ((0, 6), (2040, 12)):
+        nbytes = nslab * n * (n // 2 + 1) * 16
+        ptr = C.c_void_p()
+        capi.check(gpu.ksn_device_malloc(C.byref(ptr), nbytes))
+        capi.check(gpu.ksn_fill_synthetic_grid(ptr, 8, n, start, nslab, 13, -1.0))
+        shape = np.empty((nslab, n, 1, 1))
+        first = _sums(gpu, shape, nrbins, start, nslab, pointer=ptr)
+        monkeypatch.setenv("KSN_K1_WIN", "0")
+        plain = _sums(gpu, shape, nrbins, start, nslab, pointer=ptr)
+        assert b"(6 warps x 17 modes per lane" in gpu.ksn_last_k1_kernel(), gpu.ksn_last_k1_kernel()
+        monkeypatch.setenv("KSN_K1_WIN", "1")
+        win = _sums(gpu, shape, nrbins, start, nslab, pointer=ptr)
+        name = gpu.ksn_last_k1_kernel()
+        assert b"(8 warps x 17 modes per lane" in name and b"bins >= 1024 of 2048 in shared memory" in name, name
+        monkeypatch.delenv("KSN_K1_WIN")
+        monkeypatch.setenv("KSN_K1_PAIR", "1")
+        pair = _sums(gpu, shape, nrbins, start, nslab, pointer=ptr)
+        monkeypatch.delenv("KSN_K1_PAIR")
+        gpu.ksn_device_free(ptr)
+        live = first[0] != 0
+        assert np.array_equal(live, win[0] != 0)
+        np.testing.assert_allclose(win[0][live], plain[0][live], rtol=2e-13)
+        np.testing.assert_allclose(win[0][live], pair[0][live], rtol=2e-13)
+        np.testing.assert_allclose(win[0][live], first[0][live], rtol=2e-13)

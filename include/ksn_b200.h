@@ -154,9 +154,13 @@ const char *ksn_last_k1_kernel(void);
 unsigned long long ksn_last_k2_evals(void);
 /* largest number of 61-point rule applications any single k bin needed in that call (the kernel's critical path) */
 unsigned ksn_last_k2_max_passes(void);
+/* passes through the integrand the slowest k bin of that call made (= bisections + 1 for QAG's sequential loop; fewer
+ * when bisections are integrated ahead of time, see ksn_k2_spec_width) */
+unsigned ksn_last_k2_max_trips(void);
 /* how many intervals a K2 CTA bisects per pass through the integrand: 1 = QAG's sequential loop, 2..4 = the halves of
  * the 2..4 worst intervals are integrated at once and the loop is replayed over the cached results (bit-identical
- * output, shorter critical path).  Environment KSN_K2_SPEC overrides the built-in default. */
+ * output, shorter critical path); 0 = chosen per call by regime (hybrid neutrinos with one species: 3, otherwise 1).
+ * Environment KSN_K2_SPEC overrides the built-in default (0). */
 int ksn_k2_spec_width(void);
 
 /* Tabulate 1/(a H(a)) for the device integrand.  hub(a, user) is called on the host at

@@ -114,6 +114,7 @@ PROTOTYPES = {
     "ksn_last_k2_evals": (C.c_ulonglong, []),
     "ksn_last_k2_max_passes": (C.c_uint, []),
     "ksn_k2_spec_width": (C.c_int, []),
+    "ksn_last_k2_max_trips": (C.c_uint, []),
     "ksn_set_background": (C.c_int, [HUBBLE_FN, C.c_void_p, C.c_double, C.c_double, C.c_int]),
     "ksn_background_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ksn_fslength_device": (C.c_int, [c_double_p, C.c_int, C.c_double, C.c_double, c_double_p]),

@@ -403,7 +403,7 @@ k1_pair_kernel(const Cplx<real> *__restrict__ grid, int nrows, int N, int nrbins
 //    lane, which may share its bin with the runs of the lanes before it: those 32 partial sums are combined by one
 //    segmented warp scan per tile.
 #ifndef KSN_K1_WIN_DEFAULT
-#define KSN_K1_WIN_DEFAULT 0              // see k1_tile_config()
+#define KSN_K1_WIN_DEFAULT 1              // see k1_tile_config()
 #endif
 constexpr int K1T_MAXW = 16;
 constexpr int K1T_QRUNS = 8;              // queue slots per lane: up to seven closed runs and the open one

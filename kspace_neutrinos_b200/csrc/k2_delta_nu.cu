@@ -20,6 +20,7 @@
 #include "ksn_gk61_tables.h"
 #include "ksn_qag_spec.h"
 
+#include <algorithm>
 #include <float.h>
 #include <math.h>
 #include <stdio.h>
@@ -35,7 +36,7 @@ __constant__ double c_wg[15] = KSN_WG30_INIT;
 constexpr int K2_THREADS = 128;
 constexpr int QAG_LIMIT = 200;      // GSL_VAL, kspace_neutrino_const.h:19
 #ifndef KSN_K2_SPEC_DEFAULT
-#define KSN_K2_SPEC_DEFAULT 1       // see k2_spec_width()
+#define KSN_K2_SPEC_DEFAULT 0       // see k2_spec_width()
 #endif
 
 enum { Q_OK = 0, Q_EROUND = 18, Q_ESING = 21, Q_EMAXITER = 11, Q_EFAILED = 5 };
@@ -102,11 +103,40 @@ __device__ __forceinline__ double bessel_j0_d(double x)
     return sin(x) / x;
 }
 
-// Truncated Fermi-Dirac transform (delta_tot_table.c:431-454).  enq[n-1] = (-1)^(n+1) exp(-n qc) is
-// tabulated once per launch (it depends on the species only); 1/(n^2+x^2)^2 costs one reciprocal.
-__device__ double Jfrac_high_d(double x, double qc, double nufrac_low, const double *__restrict__ enq)
+// 1/d for a d inside the float range (here d = n^2 + x^2 >= 1 and |qc x| >= 0.5): float seed and two Newton steps, good to
+// about an ulp, in 4 FP64 instructions instead of the ~8 plus a slow-path test of a correctly rounded 1.0/d.  d beyond
+// the float range gives 0 (the term it scales is then below 1e-76 of the leading one), never a NaN.
+__device__ __forceinline__ double fast_rcp_d(double d)
 {
-    double integ = 0;
+    float s;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"((float) d));
+    double r = (double) s;
+    r = fma(r, fma(-d, r, 1.0), r);
+    r = fma(r, fma(-d, r, 1.0), r);
+    return r;
+}
+
+// Truncated Fermi-Dirac transform (delta_tot_table.c:431-454):
+//   J = sum_{n=1}^{19} -(-1)^n e^{-n qc} II(x,qc,n) / (n^2+x^2)^2 / (1.5 zeta(3) (1 - nufrac_low)),
+//   II = (n^2 + n^3 qc + n qc x^2 - x^2) qc j0(qc x) + (2n + n^2 qc + qc x^2) cos(qc x).
+// With D = n^2 + x^2 the two brackets are (n qc - 1) D + 2 n^2 and 2n + qc D, so a term is
+//   e_n [ ((n qc - 1) qc j0 + qc cos) / D + 2n (n qc j0 + cos) / D^2 ]
+// -- the same number (to rounding; the K2 kernel is bound by FP64 issue, and this form needs 7 FP64 instructions per term
+// besides the reciprocal instead of 12).  jt: per-species table (jfrac_table_init): jt[2(n-1)] = (-1)^(n+1) e^{-n qc},
+// jt[2(n-1)+1] = n qc - 1, jt[38] = 1 / (1.5 zeta(3) (1 - nufrac_low)).
+constexpr int JT_DOUBLES = 40;
+__device__ __forceinline__ void jfrac_table_init(double *jt, double qc, double nufrac_low)
+{
+    if (threadIdx.x < 19) {
+        const int n = threadIdx.x + 1;
+        jt[2 * (n - 1)] = ((n & 1) ? 1.0 : -1.0) * exp(-(double) n * qc);
+        jt[2 * (n - 1) + 1] = (double) n * qc - 1.0;
+    }
+    if (threadIdx.x == 19) jt[38] = 1.0 / (1.5 * 1.202056903159594 * (1 - nufrac_low));
+}
+
+__device__ double Jfrac_high_d(double x, double qc, const double *__restrict__ jt)
+{
     const double arg = qc * x, x2 = x * x;
     double sn, cs;
     sincos(arg, &sn, &cs);
@@ -115,22 +145,24 @@ __device__ double Jfrac_high_d(double x, double qc, double nufrac_low, const dou
         const double y = arg * arg;
         j0 = 1.0 + y * (-1.0 / 6.0 + y * (1.0 / 120.0 + y * (-1.0 / 5040.0 + y * (1.0 / 362880.0 + y * (-1.0 / 39916800.0 + y * (1.0 / 6227020800.0))))));
     } else {
-        j0 = sn / arg;
+        j0 = sn * fast_rcp_d(arg);
     }
-    const double qj = qc * j0;
+    const double qj = qc * j0, qcs = qc * cs;
+    double integ = 0;
 #pragma unroll
     for (int n = 1; n < 20; n++) {
-        const double dn = (double) n, n2 = dn * dn;
-        const double II = (n2 + n2 * dn * qc + (dn * qc - 1.0) * x2) * qj + (2 * dn + n2 * qc + qc * x2) * cs;
-        const double r = 1.0 / (n2 + x2);
-        integ += enq[n - 1] * (r * r) * II;
+        const double dn = (double) n;
+        const double r = fast_rcp_d(dn * dn + x2);
+        const double P = fma(jt[2 * n - 1], qj, qcs);
+        const double Q = (2 * dn) * fma(dn, qj, cs);
+        integ = fma(jt[2 * n - 2] * r, fma(Q, r, P), integ);
     }
-    return integ / (1.5 * 1.202056903159594 * (1 - nufrac_low));
+    return integ * jt[38];
 }
 
-__device__ __forceinline__ double specialJ_d(double x, double qc, double nufrac_low, const double *__restrict__ enq)
+__device__ __forceinline__ double specialJ_d(double x, double qc, const double *__restrict__ jt)
 {
-    return qc > 0 ? Jfrac_high_d(x, qc, nufrac_low, enq) : specialJ_fit_d(x);
+    return qc > 0 ? Jfrac_high_d(x, qc, jt) : specialJ_fit_d(x);
 }
 
 // ---------------------------------------------------------------- natural cubic spline (GSL cspline.c)
@@ -489,7 +521,7 @@ struct DeltaNuIntegrand {
     const K2Dev *P;
     const double *sx, *sy, *sc, *sb, *sd;   // shared: knots, delta_tot row, spline c and per-segment b, d
     double k, mnubykT, qc, fs_x0, fs_inv_dx;
-    const double *enq;            // shared: (-1)^(n+1) exp(-n qc), n = 1..19
+    const double *jt;             // shared: the species' table for Jfrac_high_d (jfrac_table_init)
     __device__ double operator()(double logai) const
     {
         const K2Dev &p = *P;
@@ -508,7 +540,7 @@ struct DeltaNuIntegrand {
         } else {
             dtot = sy[0] + (logai - sx[0]) / (sx[1] - sx[0]) * (sy[1] - sy[0]);
         }
-        const double specJ = specialJ_d(k * fsl / mnubykT, qc, p.nufrac_low0, enq);
+        const double specJ = specialJ_d(k * fsl / mnubykT, qc, jt);
         return fsl * bg_eval(p.bg, logai) * specJ * dtot;
     }
 };
@@ -519,12 +551,9 @@ k2_delta_nu_kernel(const __grid_constant__ K2Dev p)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ QagShared S;
     double *sx = (double *) smem_raw, *sy = sx + p.Na, *sc = sy + p.Na, *sb = sc + p.Na, *sd = sb + p.Na;
-    __shared__ double enq_s[19];
+    __shared__ double jt_s[JT_DOUBLES];
     const int ik = p.k_first + blockIdx.x, sp = blockIdx.y;
-    if (threadIdx.x < 19) {
-        const int n = threadIdx.x + 1;
-        enq_s[threadIdx.x] = ((n & 1) ? 1.0 : -1.0) * exp(-(double) n * p.qc[sp]);
-    }
+    jfrac_table_init(jt_s, p.qc[sp], p.nufrac_low0);
     for (int i = threadIdx.x; i < p.Na; i += blockDim.x) {
         sx[i] = p.scalefact[i];
         sy[i] = p.delta_tot[(size_t) ik * p.namax + i];
@@ -548,7 +577,7 @@ k2_delta_nu_kernel(const __grid_constant__ K2Dev p)
         }
         DeltaNuIntegrand f;
         f.P = &p; f.sx = sx; f.sy = sy; f.sc = sc; f.sb = sb; f.sd = sd;
-        f.k = k; f.mnubykT = mnubykT; f.qc = p.qc[sp]; f.enq = enq_s;
+        f.k = k; f.mnubykT = mnubykT; f.qc = p.qc[sp]; f.jt = jt_s;
         f.fs_x0 = p.loga0;
         f.fs_inv_dx = (p.Nfs - 1.) / (p.loga - p.loga0);
         double res, err;
@@ -557,7 +586,8 @@ k2_delta_nu_kernel(const __grid_constant__ K2Dev p)
     }
     if (threadIdx.x == 0) {
         p.out[(size_t) sp * p.nk + ik] = dnu;
-        p.status[(size_t) sp * p.nk + ik] = st | ((int) passes << 8);     // low byte: GSL-style status, rest: 61-point passes
+        // low byte: GSL-style status; bits 8-19: 61-point rule applications; bits 20+: passes through the integrand
+        p.status[(size_t) sp * p.nk + ik] = st | ((int) passes << 8) | ((int) ((passes + 1) / 2) << 20);
         if (p.evals && passes) atomicAdd(p.evals, 61ull * passes);
     }
 }
@@ -576,6 +606,7 @@ struct SpecShared {
     int sel[M];                // slots whose halves the next pass integrates
     int nsel, done, status;
     unsigned passes, rules;    // rule applications of the sequential algorithm / actually computed
+    unsigned trips;            // passes through the integrand (the CTA's critical path)
 };
 
 // 2M groups of 64 threads: group g integrates half (g & 1) of slot sel[g >> 1]; `whole`: group 0 integrates slot 0 itself.
@@ -660,20 +691,20 @@ __device__ __forceinline__ int warp_argmax_err(const double *e, const unsigned c
 // gsl_integration_qag (key 6) by a CTA of 128 M threads; all threads return the same values.
 template <int M, class F>
 __device__ int qag61_spec(const F &f, double a, double b, double epsabs, double epsrel, int limit,
-                          SpecShared<M> &S, double *result, double *abserr, unsigned *passes, unsigned *rules)
+                          SpecShared<M> &S, double *result, double *abserr, unsigned *passes, unsigned *rules, unsigned *trips)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) { S.L.a[0] = a; S.L.b[0] = b; S.nsel = 0; S.done = 0; }
     __syncthreads();
     qk61_groups<M>(f, S, true);
     QagSpecState s;                       // lives in lane 0 of warp 0
-    unsigned nrules = 1;
+    unsigned nrules = 1, ntrips = 1;
     int size = 1;                         // uniform in warp 0
     if (warp == 0) {
         if (lane == 0) {
             int st = QAGS_OK;
             if (qags_begin(s, S.L, a, b, epsabs, epsrel, limit, S.q0[0], S.q0[1], S.q0[2], S.q0[3], &st)) {
-                S.result = S.q0[0]; S.abserr = S.q0[1]; S.status = st; S.passes = 1; S.rules = 1; S.done = 1;
+                S.result = S.q0[0]; S.abserr = S.q0[1]; S.status = st; S.passes = 1; S.rules = 1; S.trips = 1; S.done = 1;
             } else {
                 S.L.cached[0] = 1; S.sel[0] = 0; S.nsel = 1;
             }
@@ -685,6 +716,7 @@ __device__ int qag61_spec(const F &f, double a, double b, double epsabs, double 
         qk61_groups<M>(f, S, false);
         if (warp != 0) continue;
         nrules += 2 * S.nsel;
+        ntrips++;
         // replay QAG's loop over the cached halves
         for (;;) {
             const int i = warp_argmax_err(S.L.e, nullptr, 0.0, size, lane);
@@ -702,7 +734,7 @@ __device__ int qag61_spec(const F &f, double a, double b, double epsabs, double 
                 if (lane == 0) {
                     double res, err;
                     S.status = qags_finish(s, S.L, &res, &err);
-                    S.result = res; S.abserr = err; S.passes = s.passes; S.rules = nrules; S.done = 1;
+                    S.result = res; S.abserr = err; S.passes = s.passes; S.rules = nrules; S.trips = ntrips; S.done = 1;
                 }
                 break;
             }
@@ -724,6 +756,7 @@ __device__ int qag61_spec(const F &f, double a, double b, double epsabs, double 
     *abserr = S.abserr;
     if (passes) *passes = S.passes;
     if (rules) *rules = S.rules;
+    if (trips) *trips = S.trips;
     const int st = S.status;
     __syncthreads();
     return st;
@@ -736,13 +769,10 @@ k2_delta_nu_spec_kernel(const __grid_constant__ K2Dev p)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ SpecShared<M> S;
     double *sx = (double *) smem_raw, *sy = sx + p.Na, *sc = sy + p.Na, *sb = sc + p.Na, *sd = sb + p.Na;
-    __shared__ double enq_s[19];
+    __shared__ double jt_s[JT_DOUBLES];
     const int ik = p.k_first + (int) (gridDim.x - 1 - blockIdx.x);      // deepest (highest-k) bins are scheduled first
     const int sp = blockIdx.y;
-    if (threadIdx.x < 19) {
-        const int n = threadIdx.x + 1;
-        enq_s[threadIdx.x] = ((n & 1) ? 1.0 : -1.0) * exp(-(double) n * p.qc[sp]);
-    }
+    jfrac_table_init(jt_s, p.qc[sp], p.nufrac_low0);
     for (int i = threadIdx.x; i < p.Na; i += blockDim.x) {
         sx[i] = p.scalefact[i];
         sy[i] = p.delta_tot[(size_t) ik * p.namax + i];
@@ -753,7 +783,7 @@ k2_delta_nu_spec_kernel(const __grid_constant__ K2Dev p)
     const double specJ0 = specialJ_fit_d(k * fsl_A0a / (mnubykT > 0 ? mnubykT : 1));
     double dnu = specJ0 * p.delta_nu_init[ik] * (1. + p.deriv_prefac * fsl_A0a);
     int st = Q_OK;
-    unsigned passes = 0, rules = 0;
+    unsigned passes = 0, rules = 0, trips = 0;
     if (p.integrate[sp]) {
         if (p.Na > 2) {
             for (int i = threadIdx.x; i < p.Na - 2; i += blockDim.x) sc[i + 1] = spline_rhs(sx, sy, i);
@@ -765,16 +795,17 @@ k2_delta_nu_spec_kernel(const __grid_constant__ K2Dev p)
         }
         DeltaNuIntegrand f;
         f.P = &p; f.sx = sx; f.sy = sy; f.sc = sc; f.sb = sb; f.sd = sd;
-        f.k = k; f.mnubykT = mnubykT; f.qc = p.qc[sp]; f.enq = enq_s;
+        f.k = k; f.mnubykT = mnubykT; f.qc = p.qc[sp]; f.jt = jt_s;
         f.fs_x0 = p.loga0;
         f.fs_inv_dx = (p.Nfs - 1.) / (p.loga - p.loga0);
         double res, err;
-        st = qag61_spec<M>(f, p.loga0, p.loga, 0.0, p.relerr[sp], QAG_LIMIT, S, &res, &err, &passes, &rules);
+        st = qag61_spec<M>(f, p.loga0, p.loga, 0.0, p.relerr[sp], QAG_LIMIT, S, &res, &err, &passes, &rules, &trips);
         dnu += p.delta_nu_prefac * res;
     }
     if (threadIdx.x == 0) {
         p.out[(size_t) sp * p.nk + ik] = dnu;
-        p.status[(size_t) sp * p.nk + ik] = st | ((int) passes << 8);     // the SEQUENTIAL algorithm's count, as k2_delta_nu_kernel reports it
+        // bits 8-19: the SEQUENTIAL algorithm's rule count, as k2_delta_nu_kernel reports it; bits 20+: passes through the integrand
+        p.status[(size_t) sp * p.nk + ik] = st | ((int) passes << 8) | ((int) trips << 20);
         if (p.evals && rules) atomicAdd(p.evals, 61ull * rules);          // integrand evaluations actually made
     }
 }
@@ -804,17 +835,29 @@ using namespace ksn;
 
 // How many intervals a K2 CTA bisects per pass through the integrand (k2_delta_nu_spec_kernel<M>); 1 = the plain
 // sequential kernel.  KSN_K2_SPEC overrides the default.
+// KSN_K2_SPEC_DEFAULT 0 = by regime (k2_spec_auto).
 static int k2_spec_width(void)
 {
     const char *env = getenv("KSN_K2_SPEC");
     const int m = env ? atoi(env) : KSN_K2_SPEC_DEFAULT;
-    return m >= 2 && m <= 4 ? m : 1;
+    return m >= 0 && m <= 4 ? m : 1;
 }
 extern "C" int ksn_k2_spec_width(void) { return k2_spec_width(); }
 
+// Measured (profiles/r1_k2_widths.txt, nk = 788, Na = 99): integrating ahead pays where the kernel's time is the critical
+// path of a few deep bins -- hybrid neutrinos, one species: 57 sequential bisections on the highest-k bins -- and costs
+// where the launch is throughput-bound (no hybrid cut: <= 8 bisections per bin; three species: 3 nk CTAs).
+static int k2_spec_auto(int nspecies_launched, const double *qc)
+{
+    bool hybrid = false;
+    for (int s = 0; s < nspecies_launched; s++) hybrid |= qc[s] > 0;
+    return hybrid && nspecies_launched == 1 ? 3 : 1;
+}
+
 static unsigned long long g_last_evals = 0;
-static unsigned g_max_passes = 0;
+static unsigned g_max_passes = 0, g_max_trips = 0;
 extern "C" unsigned ksn_last_k2_max_passes(void) { return g_max_passes; }
+extern "C" unsigned ksn_last_k2_max_trips(void) { return g_max_trips; }
 extern "C" unsigned long long ksn_last_k2_evals(void) { return g_last_evals; }
 
 // host mirror of bg_lagrange (same formula), used to validate the table against the host function
@@ -1006,7 +1049,9 @@ extern "C" int ksn_delta_nu_integrate(const ksn_delta_nu_args *A, double *out, u
     if (k_count > 0) {
         const dim3 grid(k_count, ns);
         const size_t smem = 5 * (size_t) Na * sizeof(double);
-        switch (k2_spec_width()) {
+        int width = k2_spec_width();
+        if (width == 0) width = k2_spec_auto(ns, p.qc);
+        switch (width) {
         case 2: k2_delta_nu_spec_kernel<2, 3><<<grid, 2 * K2_THREADS, smem, c.stream>>>(p); break;
         case 3: k2_delta_nu_spec_kernel<3, 2><<<grid, 3 * K2_THREADS, smem, c.stream>>>(p); break;
         case 4:
@@ -1031,9 +1076,13 @@ extern "C" int ksn_delta_nu_integrate(const ksn_delta_nu_args *A, double *out, u
     g_last_evals = *h_evals;
     if (n_evals) *n_evals = *h_evals;
     g_max_passes = 0;
+    g_max_trips = 0;
     for (size_t i = 0; i < (size_t) ns * nk + Nfs; i++) {
         const int st = i < (size_t) ns * nk ? (h_status[i] & 0xff) : h_status[i];
-        if (i < (size_t) ns * nk && (h_status[i] >> 8) > (int) g_max_passes) g_max_passes = (unsigned) (h_status[i] >> 8);
+        if (i < (size_t) ns * nk) {
+            g_max_passes = std::max(g_max_passes, ((unsigned) h_status[i] >> 8) & 0xfffu);
+            g_max_trips = std::max(g_max_trips, (unsigned) h_status[i] >> 20);
+        }
         if (st)
             return set_error(KSN_EQUAD, "quadrature %zu (%s) failed with GSL-style code %d at a=%g",
                              i, i < (size_t) ns * nk ? "delta_nu" : "fslength", st, A->a);

@@ -38,4 +38,4 @@ for it in range(6):
     L.ksn_timing_reset()
     L.get_delta_nu_update(C.byref(d), a, nk, refs.dptr(kk), refs.dptr(dcdm), refs.dptr(out), C.byref(tr))
     L.ksn_timing_get(C.byref(t))
-    print(f"K2 phase: {t.k2_ms:.3f} ms  launches {t.launches}  Na={d.ia + 1}  evals {L.ksn_last_k2_evals()}  -> {(L.ksn_last_k2_evals() - 61 * 16 * (d.ia + 1)) / 61 / nk:.1f} GK61 passes per k, max {L.ksn_last_k2_max_passes()}")
+    print(f"K2 phase: {t.k2_ms:.3f} ms  launches {t.launches}  Na={d.ia + 1}  evals {L.ksn_last_k2_evals()}  -> {(L.ksn_last_k2_evals() - 61 * 16 * (d.ia + 1)) / 61 / nk:.1f} GK61 passes per k, max {L.ksn_last_k2_max_passes()}, slowest bin: {L.ksn_last_k2_max_trips()} passes through the integrand")

@@ -211,7 +211,9 @@ def ours(args):
     capi.check(L.ksn_init(local_rank), "ksn_init")
     if world > 1:
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
-        host.init_nccl_from_torch(rank, world)
+        comm_backend = host.init_comm_from_torch(rank, world)
+    else:
+        comm_backend = "none (one rank)"
 
     def barrier():
         if world > 1:
@@ -357,10 +359,11 @@ def ours(args):
                 "step": {"achieved": 48.0 * local_modes / (step_ms * 1e-3) / 1e9,
                          "frac": 48.0 * local_modes / (step_ms * 1e-3) / 1e9 / peak,
                          "frac_of_nominal_8TBs": 48.0 * local_modes / (step_ms * 1e-3) / 1e9 / 8000.0},
-                "k2_ms_per_step": k2_ms / args.steps, "comm_ms_per_step": comm_ms / args.steps}
+                "k2_ms_per_step": k2_ms / args.steps, "comm_ms_per_step": comm_ms / args.steps,
+                "k2_kernel": f"speculation width {L.ksn_k2_spec_width() or 'by regime (hybrid, one species: 3)'}, slowest bin {L.ksn_last_k2_max_trips()} passes through the integrand"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(n, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "data": "synthetic", "config": workload_config(n, world, {"collective": comm_backend}), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "wall_ms_per_step": wall_ms / args.steps}
     if greens is not None:
         line["greens_fusion"] = greens

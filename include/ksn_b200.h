@@ -48,6 +48,13 @@ int ksn_comm_single(void);
  * file), then every rank calls ksn_comm_nccl_init. */
 int ksn_comm_nccl_unique_id(void *id128);
 int ksn_comm_nccl_init(const void *id128, int nranks, int rank);
+/* Peer memory over NVLink/NVSwitch, one process per GPU of ONE box: the cross-rank sum of the bin sums is done INSIDE
+ * the kernel that produces them (every rank stores its values into mailboxes in all ranks' HBM, waits for the others'
+ * flags and adds the contributions in rank order: no collective launch, bit-identical sums on every rank).  Every rank
+ * calls ksn_comm_p2p_export (allocates its mailbox, returns the 64-byte CUDA-IPC handle), the host gathers the handles
+ * in rank order by any means, then every rank calls ksn_comm_p2p_init with all nranks * 64 bytes (at most 16 ranks). */
+int ksn_comm_p2p_export(void *handle64);
+int ksn_comm_p2p_init(const void *handles, int nranks, int rank);
 /* Host all-reduce callback: buf (n doubles, host memory) must be summed over ranks in
  * place.  This is what an MPI host uses (MPI_Allreduce on its communicator). */
 typedef int (*ksn_allreduce_fn)(double *buf, size_t n, void *user);

@@ -83,6 +83,8 @@ PROTOTYPES = {
     "ksn_comm_single": (C.c_int, []),
     "ksn_comm_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "ksn_comm_nccl_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "ksn_comm_p2p_export": (C.c_int, [C.c_void_p]),
+    "ksn_comm_p2p_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "ksn_comm_host_callback": (C.c_int, [ALLREDUCE_FN, C.c_void_p, C.c_int, C.c_int]),
     "ksn_comm_allreduce_host": (C.c_int, [c_double_p, C.c_size_t]),
     "ksn_comm_rank": (C.c_int, []),

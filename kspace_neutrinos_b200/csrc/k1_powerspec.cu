@@ -24,6 +24,7 @@
 //  * keff and count sums do not depend on the data; the FULL variant computes them (first
 //    call per geometry), the fast variant bins the power only.
 #include "ksn_internal.cuh"
+#include "ksn_p2p.cuh"
 
 #include <math.h>
 #include <type_traits>
@@ -812,6 +813,36 @@ __global__ void k1_final_kernel(const double *__restrict__ partial, int ctas, in
     }
 }
 
+// The same reduction FUSED with the cross-rank sum (peer-memory backend, ksn_p2p.cuh): every value goes straight from the
+// warp that produced it into all ranks' mailboxes over NVLink, so the transfer overlaps the rest of the reduction; the
+// last block to finish raises this rank's flags, waits for the other ranks' and adds the R contributions in rank order.
+// One kernel instead of k1_final_kernel + ncclAllReduce; red = the GLOBAL sums, bit-identical on every rank.
+template <typename real>
+__global__ void __launch_bounds__(256)
+k1_final_p2p_kernel(const double *__restrict__ partial, int ctas, int nv, int nrbins,
+                    const Cplx<real> *origin, double *__restrict__ red, const P2PDev p)
+{
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i < nv * nrbins) {
+        double s = 0.0;
+        for (int c = lane; c < ctas; c += 32) s += partial[(size_t) c * nv * nrbins + i];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        const int which = i / nrbins, b = i - which * nrbins;
+        if (lane == 0) p2p_push(p, which == 0 ? b : which * nrbins + 1 + b, s);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double m2 = 0.0;
+        if (origin) {   // powerspectrum.c:45-47: only the rank holding plane 0
+            const double re = (double) origin->re, im = (double) origin->im;
+            m2 = re * re + im * im;
+        }
+        p2p_push(p, nrbins, m2);
+    }
+    if (!p2p_last_block(p)) return;
+    p2p_finish(p, (size_t) nv * nrbins + 1, red);
+}
+
 static size_t k1_smem_bytes(int dims, int nrbins, int nwarps, int nv)
 {
     return (size_t) (dims / 2 + 1) * 16 + (size_t) nwarps * nv * nrbins * 8 + (size_t) (nrbins + 1) * 8 + 16;
@@ -910,12 +941,24 @@ int k1_launch(const void *dgrid, int real_bytes, int dims, int nrbins, long long
                 : k1_launch_t<float, false>(dgrid, dims, nrbins, plane0_global, nplanes, accumulate, ctas_out, stride_out);
 }
 
-int k1_finish(int real_bytes, int dims, int nrbins, bool full, int ctas, int stride, const void *origin_elem)
+int k1_finish(int real_bytes, int dims, int nrbins, bool full, int ctas, int stride, const void *origin_elem, bool fuse_p2p)
 {
     (void) dims; (void) stride;
     Ctx &c = ctx();
     const int nv = full ? 3 : 1;
     const int threads = 256, blocks = (nv * nrbins * 32 + threads - 1) / threads;
+    if (fuse_p2p) {
+        P2PDev dev;
+        int rc = p2p_next_round(&dev);
+        if (rc) return rc;
+        if (real_bytes == 8)
+            k1_final_p2p_kernel<double><<<blocks, threads, 0, c.stream>>>(c.d_partial, ctas, nv, nrbins, (const Cplx<double> *) origin_elem, c.d_red, dev);
+        else
+            k1_final_p2p_kernel<float><<<blocks, threads, 0, c.stream>>>(c.d_partial, ctas, nv, nrbins, (const Cplx<float> *) origin_elem, c.d_red, dev);
+        c.launches++;
+        KSN_CUDA(cudaGetLastError());
+        return KSN_OK;
+    }
     if (real_bytes == 8)
         k1_final_kernel<double><<<blocks, threads, 0, c.stream>>>(c.d_partial, ctas, nv, nrbins, (const Cplx<double> *) origin_elem, c.d_red);
     else
@@ -1039,12 +1082,15 @@ int k1_sums(const void *dgrid, const void *hgrid, int real_bytes, int dims, int 
         KSN_CUDA(cudaMemsetAsync(c.d_partial, 0, (size_t) 3 * nrbins * sizeof(double), c.stream));
         ctas = 1;
     }
+    const size_t nred = full ? (size_t) 3 * nrbins + 1 : (size_t) nrbins + 1;
+    // peer-memory backend: the cross-rank sum happens inside the final-reduce kernel (KSN_P2P_UNFUSED=1: as a kernel of
+    // its own behind it, for comparison)
+    const bool fuse = c.comm_kind == COMM_P2P && c.nranks > 1 && nred <= KSN_P2P_SLOT && !getenv("KSN_P2P_UNFUSED");
     phase_begin(PH_K1RED);
-    rc = k1_finish(real_bytes, dims, nrbins, full, ctas, stride, (startslab == 0 && nslab > 0) ? origin : nullptr);
+    rc = k1_finish(real_bytes, dims, nrbins, full, ctas, stride, (startslab == 0 && nslab > 0) ? origin : nullptr, fuse);
     phase_end(PH_K1RED);
     if (rc) return rc;
-    const size_t nred = full ? (size_t) 3 * nrbins + 1 : (size_t) nrbins + 1;
-    rc = allreduce_to_host(c.d_red, c.h_red, nred);
+    rc = fuse ? reduced_to_host(c.d_red, c.h_red, nred) : allreduce_to_host(c.d_red, c.h_red, nred);
     if (rc) return rc;
     phase_collect();
     if (full) {

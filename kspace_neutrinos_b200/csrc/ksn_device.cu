@@ -2,6 +2,7 @@
 // C-ABI: include/ksn_b200.h.  No CPU fallback lives here: when CUDA is unusable every
 // compute entry reports KSN_ENODEV.
 #include "ksn_internal.cuh"
+#include "ksn_p2p.cuh"
 
 #include <dlfcn.h>
 #include <math.h>
@@ -217,9 +218,10 @@ static int nccl_fail(int rc, const char *what)
     return set_error(KSN_ECOMM, "%s: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "nccl error");
 }
 
-static void drop_comm()
+static void drop_comm(bool keep_p2p = false)
 {
     Ctx &c = g_ctx;
+    if (!keep_p2p) p2p_drop();
     if (c.nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c.nccl);
     c.nccl = nullptr;
     c.cb = nullptr;
@@ -230,9 +232,33 @@ static void drop_comm()
     c.comm_epoch++;
 }
 
+void drop_comm_backend(bool keep_p2p) { drop_comm(keep_p2p); }
+
+// The producing kernel has already summed d_buf over the ranks through peer memory (k1_final_p2p_kernel): fetch it.
+int reduced_to_host(double *d_buf, double *h_buf, size_t n)
+{
+    Ctx &c = g_ctx;
+    KSN_CUDA(cudaMemcpyAsync(h_buf, d_buf, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    int rc = p2p_status_async();
+    if (rc) return rc;
+    KSN_CUDA(cudaStreamSynchronize(c.stream));
+    return p2p_status_result();
+}
+
 int allreduce_to_host(double *d_buf, double *h_buf, size_t n)
 {
     Ctx &c = g_ctx;
+    if (c.comm_kind == COMM_P2P && c.nranks > 1) {
+        phase_begin(PH_COMM);
+        int rc = p2p_allreduce_device(d_buf, n);
+        phase_end(PH_COMM);
+        if (rc) return rc;
+        KSN_CUDA(cudaMemcpyAsync(h_buf, d_buf, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        rc = p2p_status_async();
+        if (rc) return rc;
+        KSN_CUDA(cudaStreamSynchronize(c.stream));
+        return p2p_status_result();
+    }
     if (c.comm_kind == COMM_NCCL && c.nranks > 1) {
         phase_begin(PH_COMM);
         const int ncclDouble = 8, ncclSum = 0;   // ncclFloat64 / ncclSum enum values (nccl.h)

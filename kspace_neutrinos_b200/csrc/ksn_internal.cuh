@@ -14,7 +14,7 @@ namespace ksn {
 // c.d_iw holds iw[0..L) followed by K1's z-weight table of L entries and this many zeros
 constexpr int K1_WZ_PAD = 32 * 65 + 16;
 
-enum CommKind { COMM_SINGLE = 0, COMM_NCCL = 1, COMM_HOSTCB = 2 };
+enum CommKind { COMM_SINGLE = 0, COMM_NCCL = 1, COMM_HOSTCB = 2, COMM_P2P = 3 };
 
 // Events used for the optional per-phase timing (ksn_timing_*).
 enum Phase { PH_K1 = 0, PH_K1RED, PH_COMM, PH_K2, PH_K3, PH_H2D, PH_D2H, PH_COUNT };
@@ -72,9 +72,13 @@ void phase_collect();   // after a stream sync: fold event times into acc_ms
 
 #define KSN_CUDA(call) do { int _rc = ::ksn::check_cuda((call), #call); if (_rc) return _rc; } while (0)
 
+// Forget the active collective backend (keep_p2p: all but the peer-memory mailboxes, which ksn_comm_p2p_init is setting up).
+void drop_comm_backend(bool keep_p2p);
+
 // Device allreduce-or-host-callback of n doubles living at d_buf (device) with pinned mirror h_buf.
 // On return h_buf holds the global sums (and the stream is synchronized).
 int allreduce_to_host(double *d_buf, double *h_buf, size_t n);
+int reduced_to_host(double *d_buf, double *h_buf, size_t n);   // d_buf is already the global sum (fused peer-memory reduce)
 
 // Host pointer -> pinned (registers once and remembers).  Returns 1 if the range is pinned afterwards.
 int ensure_host_pinned(const void *p, size_t bytes);
@@ -87,7 +91,7 @@ int stage_plan(int real_bytes, int dims, long long nslab, StagePlan *plan);   //
 // launchers (one per kernel family)
 int k1_launch(const void *dgrid, int real_bytes, int dims, int nrbins, long long plane0_global, long long nplanes,
               bool full, bool accumulate, int *ctas_out, int *stride_out);
-int k1_finish(int real_bytes, int dims, int nrbins, bool full, int ctas, int stride, const void *origin_elem);
+int k1_finish(int real_bytes, int dims, int nrbins, bool full, int ctas, int stride, const void *origin_elem, bool fuse_p2p);
 int k3_launch(void *dgrid, int real_bytes, int dims, long long plane0_global, long long nplanes, int nknots);
 int k3_upload_table(int dims, double boxsize, const double *logkk, const double *ratio, int nbins, double norm);
 

@@ -178,6 +178,37 @@ def init_nccl_from_torch(rank: int, world: int) -> None:
     capi.check(L.ksn_comm_nccl_init(raw, world, rank), "ksn_comm_nccl_init")
 
 
+def init_p2p_from_torch(rank: int, world: int) -> None:
+    """One process per GPU of one box: the peer-memory backend (the cross-rank sum of the bin sums fused into the kernel
+    that produces them, over NVLink).  Each rank exports its mailbox as a 64-byte CUDA-IPC handle; the handles are
+    gathered over torch.distributed in rank order."""
+    import torch.distributed as dist
+    L = capi.lib()
+    buf = (C.c_ubyte * 64)()
+    capi.check(L.ksn_comm_p2p_export(buf), "ksn_comm_p2p_export")
+    handles = [None] * world
+    dist.all_gather_object(handles, bytes(buf))
+    raw = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
+    capi.check(L.ksn_comm_p2p_init(raw, world, rank), "ksn_comm_p2p_init")
+    dist.barrier()                      # nobody starts a round before every rank has mapped every mailbox
+
+
+def init_comm_from_torch(rank: int, world: int, backend: str | None = None) -> str:
+    """Pick the collective backend for a one-process-per-GPU run: KSN_COMM=p2p|nccl (default p2p, falling back to
+    NCCL when the GPUs cannot map each other's memory).  Returns the backend in use."""
+    import os
+    backend = backend or os.environ.get("KSN_COMM", "p2p")
+    if backend == "p2p":
+        try:
+            init_p2p_from_torch(rank, world)
+            return "p2p"
+        except RuntimeError as e:      # all ranks fail alike (same box): fall back together
+            import sys
+            print(f"[ksn] peer-memory backend unavailable ({e}); using NCCL", file=sys.stderr)
+    init_nccl_from_torch(rank, world)
+    return "nccl"
+
+
 _host_cb_keepalive = []
 
 

@@ -1,6 +1,7 @@
-"""Slab-sharded run over several GPUs of one box (one process per GPU, the library's own NCCL all-reduce of the
-bin sums): every rank must end up with the 1-rank answer -- mode counts exactly, P(k)/delta_nu/grid to 1e-10.
-Skipped when fewer than 2 GPUs are visible."""
+"""Slab-sharded run over several GPUs of one box, one process per GPU, with either collective backend -- the library's own
+NCCL all-reduce of the bin sums, or the peer-memory exchange fused into the final-reduce kernel (csrc/ksn_p2p.cuh): every
+rank must end up with the 1-rank answer -- mode counts exactly, P(k)/delta_nu/grid to 1e-10 -- and, with the peer-memory
+backend, with the SAME BITS on every rank.  Skipped when fewer than 2 GPUs are visible."""
 import os
 import subprocess
 import sys
@@ -22,7 +23,16 @@ torch.cuda.set_device(local)
 L = capi.lib()
 capi.check(L.ksn_init(local))
 dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
-host.init_nccl_from_torch(rank, world)
+backend = os.environ["KSN_TEST_COMM"]
+if backend == "p2p":
+    host.init_p2p_from_torch(rank, world)          # no fall-back here: the test is about this backend
+else:
+    host.init_nccl_from_torch(rank, world)
+assert L.ksn_comm_size() == world and L.ksn_comm_rank() == rank
+# the stand-alone all-reduce of the active backend (host buffer in, host buffer out), longer than one mailbox slot
+v = np.arange(40000, dtype=np.float64) * (rank + 1)
+capi.check(L.ksn_comm_allreduce_host(refs.dptr(v), v.size))
+assert np.array_equal(v, np.arange(40000, dtype=np.float64) * (world * (world + 1) // 2))
 n = 64
 g = refs.random_grid(n, seed=2024)
 slab = host.slab_partition(n, world)[rank]
@@ -36,6 +46,16 @@ nw = o.orc_total_powerspectrum(n, g.ctypes.data_as(C.c_void_p), 1, n // 2, 0, n,
 assert nret == nw and np.array_equal(Cn[:nret], cw[:nw])
 np.testing.assert_allclose(P[:nret], pw[:nw], rtol=1e-10)
 np.testing.assert_allclose(K[:nret], kw[:nw], rtol=1e-10)
+if backend == "p2p":
+    # contributions are added in rank order on every rank: identical bits everywhere, also when the reduce is not fused
+    mine = torch.from_numpy(P.copy()).cuda()
+    everyone = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(everyone, mine)
+    assert all(torch.equal(e, mine) for e in everyone)
+    os.environ["KSN_P2P_UNFUSED"] = "1"
+    nret2, P2, Cn2, K2 = refs.total_powerspectrum(L, sub, n // 2, startslab=slab.start, nslab=slab.count, fn="total_powerspectrum_f64")
+    del os.environ["KSN_P2P_UNFUSED"]
+    assert nret2 == nret and np.array_equal(P2, P)
 # whole step, device-resident slab, several PM steps
 sim = host.KspaceNeutrinos(host.Cosmology(transfer_file=host.default_transfer_file(), mnu=(0.15, 0.15, 0.15), hybrid_neutrinos_on=1), n, rank=rank)
 dev = refs.DeviceBuffer(L, sub)
@@ -62,14 +82,15 @@ def _ngpus():
         return 0
 
 
+@pytest.mark.parametrize("backend", ["nccl", "p2p"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_slab_sharded_step_matches_single_rank(world, tmp_path):
+def test_slab_sharded_step_matches_single_rank(world, backend, tmp_path):
     if _ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, KSN_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
-    port = 29700 + (os.getpid() % 1000) + world
+    env = dict(os.environ, KSN_ROOT=ROOT, MASTER_ADDR="127.0.0.1", KSN_TEST_COMM=backend)
+    port = 29700 + (os.getpid() % 1000) + world + (50 if backend == "p2p" else 0)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                         "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                        capture_output=True, text=True, env=env, timeout=600)

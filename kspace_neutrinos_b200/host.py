@@ -194,17 +194,51 @@ def init_p2p_from_torch(rank: int, world: int) -> None:
 
 
 def init_comm_from_torch(rank: int, world: int, backend: str | None = None) -> str:
-    """Pick the collective backend for a one-process-per-GPU run: KSN_COMM=p2p|nccl (default p2p, falling back to
-    NCCL when the GPUs cannot map each other's memory).  Returns the backend in use."""
-    import os
+    """Pick the collective backend for a one-process-per-GPU run: KSN_COMM=p2p|nccl.  Default p2p (the cross-rank sum
+    fused into the final-reduce kernel over peer memory); it is kept only if EVERY rank could map every mailbox and a
+    trial all-reduce of a known vector came out right on every rank -- otherwise all ranks fall back to NCCL together.
+    Returns the backend in use."""
+    import sys
+    import torch
+    import torch.distributed as dist
     backend = backend or os.environ.get("KSN_COMM", "p2p")
     if backend == "p2p":
+        L = capi.lib()
+
+        def everyone(flag: bool) -> bool:          # collective: did it work on every rank?
+            t = torch.tensor([1 if flag else 0], dtype=torch.int32, device="cuda" if torch.cuda.is_available() else "cpu")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return int(t.item()) == 1
+
+        why = ""
+        handle = b""
         try:
-            init_p2p_from_torch(rank, world)
-            return "p2p"
-        except RuntimeError as e:      # all ranks fail alike (same box): fall back together
-            import sys
-            print(f"[ksn] peer-memory backend unavailable ({e}); using NCCL", file=sys.stderr)
+            buf = (C.c_ubyte * 64)()
+            capi.check(L.ksn_comm_p2p_export(buf), "ksn_comm_p2p_export")
+            handle = bytes(buf)
+        except RuntimeError as e:
+            why = str(e)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle)    # every rank takes part, whatever happened above
+        ok = all(len(h) == 64 for h in handles)
+        if ok:
+            try:
+                raw = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
+                capi.check(L.ksn_comm_p2p_init(raw, world, rank), "ksn_comm_p2p_init")
+            except RuntimeError as e:
+                ok, why = False, str(e)
+        if everyone(ok):                           # (also the barrier: every mailbox is mapped before any round starts)
+            try:
+                v = np.full(1000, rank + 1.0)
+                capi.check(L.ksn_comm_allreduce_host(v.ctypes.data_as(capi.c_double_p), v.size), "trial all-reduce")
+                ok = bool(np.all(v == world * (world + 1) / 2))
+                why = "" if ok else "trial all-reduce returned wrong sums"
+            except RuntimeError as e:
+                ok, why = False, str(e)
+            if everyone(ok):
+                return "p2p"
+        if rank == 0:
+            print(f"[ksn] peer-memory backend not usable on every rank ({why or 'another rank failed'}); using NCCL", file=sys.stderr)
     init_nccl_from_torch(rank, world)
     return "nccl"
 

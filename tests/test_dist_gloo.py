@@ -61,3 +61,41 @@ def test_host_allreduce_backend_over_gloo(world, tmp_path):
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert r.stdout.count(" ok") == world
+
+
+FALLBACK_WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["KSN_ROOT"])
+import torch.distributed as dist
+from kspace_neutrinos_b200 import capi, host
+dist.init_process_group(backend="gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+# No GPU here: exporting a mailbox fails on every rank.  The choice of backend must stay COLLECTIVE (every rank goes
+# through the same gathers and agreements, nobody hangs) and end in the NCCL branch -- which, without a device, fails loudly.
+calls = []
+host.init_nccl_from_torch = lambda r, w: calls.append((r, w))
+got = host.init_comm_from_torch(rank, world)
+assert got == "nccl" and calls == [(rank, world)], (got, calls)
+assert capi.lib().ksn_comm_size() == 1            # nothing half-initialised is left behind
+# asked for NCCL outright: no peer-memory attempt at all
+calls.clear()
+assert host.init_comm_from_torch(rank, world, backend="nccl") == "nccl" and calls == [(rank, world)]
+dist.barrier()
+dist.destroy_process_group()
+print(f"rank {rank}/{world} ok")
+'''
+
+
+def test_backend_choice_is_collective_and_falls_back(tmp_path):
+    """host.init_comm_from_torch on a box without usable peer memory (here: no GPU at all): every rank must take the same
+    path through the gathers/agreements and fall back to NCCL together."""
+    script = tmp_path / "worker.py"
+    script.write_text(FALLBACK_WORKER)
+    env = dict(os.environ, KSN_ROOT=ROOT, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    port = 29500 + (os.getpid() % 2000) + 7
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count(" ok") == 2
+    assert "peer-memory backend not usable on every rank" in r.stderr

@@ -179,7 +179,7 @@ constexpr int K3_TMA_THREADS = 128;        // <= 1152 modes (one 2048^3 row) per
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
 
-template <typename real, bool ONE_ROW>
+template <typename real, bool ONE_ROW, bool SPLIT>
 __global__ void __launch_bounds__(K3_TMA_THREADS, 8)
 k3_scale_tma_kernel(C2<real> *__restrict__ grid, int nrows, int rows_per_cta, int N, long long plane0,
                     const double *__restrict__ tab, const K3Params prm, const K3Greens gr, int segs, int seg_len)
@@ -194,10 +194,13 @@ k3_scale_tma_kernel(C2<real> *__restrict__ grid, int nrows, int rows_per_cta, in
     // seg_len modes when a row does not fit one CTA (PMGRID = 4096: two pieces of 1025 and 1024 modes).  Otherwise a
     // block of rows_per_cta whole rows.
     int row0, nel, z0 = 0;
-    if (ONE_ROW) {
+    if (ONE_ROW && SPLIT) {
         row0 = (int) (blockIdx.x / (unsigned) segs);
         z0 = (int) (blockIdx.x - (unsigned) row0 * (unsigned) segs) * seg_len;
         nel = min(seg_len, L - z0);
+    } else if (ONE_ROW) {
+        row0 = blockIdx.x;
+        nel = L;
     } else {
         row0 = blockIdx.x * rows_per_cta;
         nel = min(rows_per_cta, nrows - row0) * L;
@@ -387,7 +390,8 @@ int k3_launch(void *dgrid, int real_bytes, int dims, long long plane0_global, lo
             kern<<<nct, K3_TMA_THREADS, smem, c.stream>>>((C2<double> *) dgrid, nrows, rpc, dims, plane0_global, c.d_k3tab, g_k3prm, gr, segs, seg_len);
             return KSN_OK;
         };
-        const int rcl = rpc == 1 ? go(k3_scale_tma_kernel<double, true>) : go(k3_scale_tma_kernel<double, false>);
+        const int rcl = segs > 1 ? go(k3_scale_tma_kernel<double, true, true>)
+                      : rpc == 1 ? go(k3_scale_tma_kernel<double, true, false>) : go(k3_scale_tma_kernel<double, false, false>);
         if (rcl) return rcl;
         c.launches++;
         KSN_CUDA(cudaGetLastError());

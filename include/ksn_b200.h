@@ -155,6 +155,10 @@ typedef struct ksn_delta_nu_args {
 /* out: nspecies*nk doubles, species-major.  n_evals (may be NULL): integrand evaluations. */
 int ksn_delta_nu_integrate(const ksn_delta_nu_args *args, double *out, unsigned long long *n_evals);
 
+/* the tile shape K1's tile kernel takes for (dims, nrbins) on a device with smem_budget bytes of opt-in shared memory per
+ * CTA and `sms` SMs (host arithmetic only): warps per CTA, modes per lane, stages, tiles per row, first bin kept in shared
+ * memory (0 = all).  Returns 0 when no tile shape fits. */
+int ksn_k1_tile_plan(int dims, int nrbins, size_t smem_budget, int sms, int *warps, int *chunk, int *stages, int *tiles_per_row, int *hot_lo);
 /* which K1 kernel (and tile configuration) the most recent power-spectrum sweep launched */
 const char *ksn_last_k1_kernel(void);
 /* integrand evaluations of the most recent ksn_delta_nu_integrate call (fslength table included) */

@@ -726,6 +726,26 @@ static bool k1_tile_config(int L, int nrbins, size_t budget, int ctas, K1TileCfg
     return best->W > 0;
 }
 
+}  // namespace ksn
+
+// Which tile shape the K1 tile kernel would take for (dims, nrbins) on a device with `smem_budget` bytes of opt-in shared
+// memory per CTA and `sms` SMs -- pure host arithmetic (no device needed), exported so that the choice can be pinned by a
+// CPU test.  Returns 1 and fills warps / modes per lane / stages / tiles per row / first bin kept in shared memory
+// (0 = all of them), or 0 when no tile shape fits (the scan-based kernel runs then).
+extern "C" int ksn_k1_tile_plan(int dims, int nrbins, size_t smem_budget, int sms, int *warps, int *chunk, int *stages, int *tiles_per_row, int *hot_lo)
+{
+    ksn::K1TileCfg tc;
+    if (dims < 2 || nrbins < 1 || !ksn::k1_tile_config(dims / 2 + 1, nrbins, smem_budget, sms, &tc)) return 0;
+    if (warps) *warps = tc.W;
+    if (chunk) *chunk = tc.C;
+    if (stages) *stages = tc.S;
+    if (tiles_per_row) *tiles_per_row = tc.T;
+    if (hot_lo) *hot_lo = tc.hot_lo;
+    return 1;
+}
+
+namespace ksn {
+
 template <typename real, bool FULL>
 __global__ void __launch_bounds__(K1_MAX_WARPS * 32, 1)
 k1_bin_kernel(const Cplx<real> *__restrict__ grid, int nrows, int N, int nrbins, long long plane0,

@@ -191,3 +191,30 @@ def test_slab_partition():
         for a, b in zip(slabs[:-1], slabs[1:]):
             assert b.start == a.start + a.count and a.count - b.count in (0, 1)
     assert host.modes_in_slab(2048, host.Slab(0, 2048)) == 4299161600
+
+
+def test_k1_tile_plan_for_the_named_grids(monkeypatch):
+    """The tile shape K1 takes is host arithmetic over the shared-memory budget (227 KB opt-in, 148 SMs on B200): pin it
+    for the BASELINE grids -- 2048: eight warps, 17 modes per lane, all 1024 bins in shared memory; 4096: the bin window
+    (bins >= 1024 of 2048 in shared memory) is what keeps eight warps, six without it."""
+    import ctypes as C
+    from kspace_neutrinos_b200 import capi
+    L = capi.lib()
+
+    def plan(n):
+        v = [C.c_int() for _ in range(5)]
+        assert L.ksn_k1_tile_plan(n, n // 2, 232448, 148, *[C.byref(x) for x in v]) == 1
+        return tuple(x.value for x in v)
+
+    for k in ("KSN_K1_WIN", "KSN_K1_TILE"):
+        monkeypatch.delenv(k, raising=False)
+    assert plan(2048) == (8, 17, 2, 2, 0)
+    assert plan(4096) == (8, 17, 2, 4, 1024)
+    assert plan(1024)[4] == 0 and plan(256)[4] == 0            # never a window where everything fits
+    monkeypatch.setenv("KSN_K1_WIN", "0")
+    assert plan(4096) == (6, 17, 2, 4, 0)
+    monkeypatch.setenv("KSN_K1_WIN", "2")                      # the tests' forced quarter window
+    assert plan(256) == (8, 9, 4, 1, 64)
+    monkeypatch.delenv("KSN_K1_WIN")
+    monkeypatch.setenv("KSN_K1_TILE", "4,9,3")
+    assert plan(256)[:3] == (4, 9, 3)

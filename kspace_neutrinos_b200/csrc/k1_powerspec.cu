@@ -988,6 +988,29 @@ int k1_finish(int real_bytes, int dims, int nrbins, bool full, int ctas, int str
     return KSN_OK;
 }
 
+// The tables depend on (dims, nrbins) only, and a PM run passes the same ones every step: remember what sits in
+// c.d_thr / c.d_iw (by content hash, not by host address) and skip the three uploads and the stream sync they cost.
+// Opt-in (KSN_K1_TABLE_CACHE=1) until it has been through the GPU parity suite: it was written after this round's
+// GPU minutes were spent.
+struct K1TabKey { bool valid; int dims, nrbins; unsigned long long h_thr, h_iw; const void *d_thr, *d_iw; };
+static K1TabKey g_k1_tab = { false, 0, 0, 0, 0, nullptr, nullptr };
+void k1_tables_invalidate() { g_k1_tab.valid = false; }
+
+static unsigned long long hash_words(const void *p, size_t bytes)
+{
+    const unsigned char *b = (const unsigned char *) p;
+    unsigned long long h = 0x9E3779B97F4A7C15ull ^ bytes;
+    size_t i = 0;
+    for (; i + 8 <= bytes; i += 8) {
+        unsigned long long w;
+        memcpy(&w, b + i, 8);
+        h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 29;
+    }
+    for (; i < bytes; i++) { h = (h ^ b[i]) * 0x100000001B3ull; }
+    return h;
+}
+
 static int k1_upload_tables(int dims, int nrbins, const unsigned int *thresholds, const double *invwin)
 {
     // From which k^2 on can one step along z (k^2 -> k^2 + 2z+1 <= k^2 + 2 sqrt(k^2) + 1) cross at most ONE bin threshold?
@@ -1005,6 +1028,16 @@ static int k1_upload_tables(int dims, int nrbins, const unsigned int *thresholds
     // d_iw = [ iw[0..L) | m_z iw[z]^4 for z in [0, L), then K1_WZ_PAD zeros (lanes walk past the row end with weight 0) ]
     rc = ensure_device_buffer((void **) &c.d_iw, &c.iw_cap, (size_t) (2 * L + K1_WZ_PAD) * sizeof(double));
     if (rc) return rc;
+    rc = ensure_device_buffer((void **) &c.d_red, &c.red_cap, (size_t) (3 * nrbins + 1) * sizeof(double));
+    if (rc) return rc;
+    rc = ensure_pinned_buffer((void **) &c.h_red, &c.h_red_cap, (size_t) (3 * nrbins + 1) * sizeof(double));
+    if (rc) return rc;
+    const unsigned long long h_thr = hash_words(thresholds, (size_t) nrbins * sizeof(unsigned));
+    const unsigned long long h_iw = hash_words(invwin, (size_t) L * sizeof(double));
+    if (g_k1_tab.valid && g_k1_tab.dims == dims && g_k1_tab.nrbins == nrbins && g_k1_tab.h_thr == h_thr && g_k1_tab.h_iw == h_iw &&
+        g_k1_tab.d_thr == c.d_thr && g_k1_tab.d_iw == c.d_iw && getenv("KSN_K1_TABLE_CACHE"))
+        return KSN_OK;
+    g_k1_tab.valid = false;
     {
         double *wz = (double *) calloc((size_t) L + K1_WZ_PAD, sizeof(double));
         if (!wz) return set_error(KSN_ENOMEM, "K1: out of host memory");
@@ -1019,10 +1052,7 @@ static int k1_upload_tables(int dims, int nrbins, const unsigned int *thresholds
     }
     KSN_CUDA(cudaMemcpyAsync(c.d_thr, thresholds, (size_t) nrbins * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
     KSN_CUDA(cudaMemcpyAsync(c.d_iw, invwin, (size_t) L * sizeof(double), cudaMemcpyHostToDevice, c.stream));
-    rc = ensure_device_buffer((void **) &c.d_red, &c.red_cap, (size_t) (3 * nrbins + 1) * sizeof(double));
-    if (rc) return rc;
-    rc = ensure_pinned_buffer((void **) &c.h_red, &c.h_red_cap, (size_t) (3 * nrbins + 1) * sizeof(double));
-    if (rc) return rc;
+    g_k1_tab = { true, dims, nrbins, h_thr, h_iw, c.d_thr, c.d_iw };
     return KSN_OK;
 }
 

@@ -351,6 +351,7 @@ static int k3_set_greens(int dims, const double *invwin, double asmth2)
         const double w2 = invwin[z] * invwin[z];
         gz[z] = exp(-(double) (z * z) * asmth2) * (w2 * w2);
     }
+    k1_tables_invalidate();                 // c.d_iw is K1's table buffer: it must re-upload its own next time
     cudaError_t e = cudaMemcpyAsync(c.d_iw, invwin, L * sizeof(double), cudaMemcpyHostToDevice, c.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_gz, gz, L * sizeof(double), cudaMemcpyHostToDevice, c.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);       // gz is about to be freed

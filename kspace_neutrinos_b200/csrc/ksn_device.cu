@@ -361,6 +361,7 @@ void ksn_shutdown(void)
     cudaSetDevice(c.device);
     cudaDeviceSynchronize();
     drop_comm();
+    k1_tables_invalidate();
     for (auto &kv : g_registered) cudaHostUnregister((void *) kv.first);
     g_registered.clear();
     cudaFree(c.d_partial); cudaFree(c.d_red); cudaFreeHost(c.h_red); cudaFree(c.d_thr); cudaFree(c.d_iw);

@@ -92,6 +92,7 @@ int stage_plan(int real_bytes, int dims, long long nslab, StagePlan *plan);   //
 int k1_launch(const void *dgrid, int real_bytes, int dims, int nrbins, long long plane0_global, long long nplanes,
               bool full, bool accumulate, int *ctas_out, int *stride_out);
 int k1_finish(int real_bytes, int dims, int nrbins, bool full, int ctas, int stride, const void *origin_elem, bool fuse_p2p);
+void k1_tables_invalidate();   // somebody else wrote c.d_iw / c.d_thr, or the context is gone
 int k3_launch(void *dgrid, int real_bytes, int dims, long long plane0_global, long long nplanes, int nknots);
 int k3_upload_table(int dims, double boxsize, const double *logkk, const double *ratio, int nbins, double norm);
 

@@ -53,8 +53,25 @@ extern "C" {
 #endif
 
 /* ------------------------------------------------------------------ grid element
- * powerspectrum.h:5-14 takes fftw_complex from FFTW2's headers.  If the host has not
- * included FFTW, provide the identical layout. */
+ * powerspectrum.h:5-14 takes fftw_complex from FFTW2's headers (<fftw.h>, <dfftw.h> or <sfftw.h>
+ * by NOTYPEPREFIX_FFTW / DOUBLEPRECISION_FFTW).  Do the same where the host's include path has
+ * them, so that a source which includes FFTW *after* this header (powerspectrum_test.c:7-15)
+ * still sees one definition; otherwise provide the identical layout. */
+#if !defined(FFTW_H) && !defined(KSN_HAVE_FFTW_TYPES) && defined(__has_include)
+#if defined(NOTYPEPREFIX_FFTW)
+#if __has_include(<fftw.h>)
+#include <fftw.h>
+#endif
+#elif defined(DOUBLEPRECISION_FFTW)
+#if __has_include(<dfftw.h>)
+#include <dfftw.h>
+#endif
+#else
+#if __has_include(<sfftw.h>)
+#include <sfftw.h>
+#endif
+#endif
+#endif
 #if !defined(FFTW_H) && !defined(KSN_HAVE_FFTW_TYPES)
 #define KSN_HAVE_FFTW_TYPES
 #ifdef DOUBLEPRECISION_FFTW
@@ -121,6 +138,8 @@ double rho_nu(_rho_nu_single *rho_nu_tab, const double a, const double kT);     
 void init_hybrid_nu(_hybrid_nu *const hybnu, const double mnu[], const double vcrit, const double light, const double nu_crit_time, const double kBtnu); /* :76 */
 double particle_nu_fraction(const _hybrid_nu *const hybnu, const double a, int i);              /* :85 */
 double nufrac_low(const double qc);                                                             /* :88 */
+double rho_nu_int(double q, void *params);      /* omega_nu_single.c:89 (undeclared there; omega_nu_single_test.c:72); params = {a*mnu, kT} */
+double get_rho_nu_conversion(void);              /* omega_nu_single.c:100 (omega_nu_single_test.c:68) */
 void init_omega_nu(_omega_nu *const omnu, const double MNu[], const double a0, const double HubbleParam, const double tcmb0); /* :116 */
 double get_omega_nu(const _omega_nu *const omnu, const double a);                               /* :119 */
 double get_omega_nu_nopart(const _omega_nu *const omnu, const double a);                        /* :122 */

@@ -131,6 +131,8 @@ PROTOTYPES = {
     "init_hybrid_nu": (None, [C.POINTER(HybridNu), c_double_p, C.c_double, C.c_double, C.c_double, C.c_double]),
     "particle_nu_fraction": (C.c_double, [C.POINTER(HybridNu), C.c_double, C.c_int]),
     "nufrac_low": (C.c_double, [C.c_double]),
+    "rho_nu_int": (C.c_double, [C.c_double, c_double_p]),       # params = {a*mnu, kT} (omega_nu_single.c:89)
+    "get_rho_nu_conversion": (C.c_double, []),
     "init_omega_nu": (None, [C.POINTER(OmegaNu), c_double_p, C.c_double, C.c_double, C.c_double]),
     "get_omega_nu": (C.c_double, [C.POINTER(OmegaNu), C.c_double]),
     "get_omega_nu_nopart": (C.c_double, [C.POINTER(OmegaNu), C.c_double]),

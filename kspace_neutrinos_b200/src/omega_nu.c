@@ -36,6 +36,21 @@ static double energy_density_kernel(double q, void *vp)
     return q * q * sqrt(q * q + p->amnu * p->amnu) / (exp(q / p->kT) + 1);
 }
 
+/* The reference leaves these two external although no header declares them, and its own
+ * omega_nu_single_test.c:68-85 links them to integrate the density exactly; params = {a m_nu, kT}
+ * (omega_nu_single.c:89-96,100-115). */
+double rho_nu_int(double q, void *params)
+{
+    const double *p = params;
+    const struct fd_ctx c = { p[0], p[1] };
+    return energy_density_kernel(q, (void *) &c);
+}
+
+double get_rho_nu_conversion(void)
+{
+    return rho_unit();
+}
+
 void rho_nu_init(_rho_nu_single *tab, double a0, const double mnu, const double HubbleParam, const double kBtnu)
 {
     (void) HubbleParam;

@@ -23,3 +23,37 @@ def test_two_rank_mpi_build_of_the_host_layer(tmp_path):
     assert r.returncode == 0, r.stderr[-3000:]
     r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "ics_transfer_99.dat")], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "MPI HOST FLOW OK" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
+
+
+def test_slab_split_pm_steps_over_mini_mpi(tmp_path):
+    """add_nu_power_to_rhogrid on x-slabs over 1, 2 and 3 (uneven) ranks: host layer (-DKSN_HAVE_MPI) + the test-only CPU
+    stand-in for the device entry points.  Same integrator state on every rank, same corrected grid for every split."""
+    import numpy as np
+    exe = str(tmp_path / "mpi_host_step")
+    srcs = sorted(glob.glob(os.path.join(PKG, "src", "*.c")))
+    orc = [os.path.join(ROOT, "oracle", f) for f in ("ksn_oracle.c", "mini_gsl.c", "mini_mpi.c")]
+    cmd = ["gcc", "-O2", "-g", "-Wall", "-DKSN_HAVE_MPI", "-DDOUBLEPRECISION_FFTW",
+           "-I", os.path.join(ROOT, "oracle", "shim"), "-I", os.path.join(ROOT, "oracle"), "-I", os.path.join(ROOT, "include"),
+           "-I", os.path.join(PKG, "src"),
+           os.path.join(ROOT, "tests", "mpi_host_step.c"), os.path.join(ROOT, "tests", "device_standin.c"), *srcs, *orc,
+           "-lm", "-lpthread", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = {}
+    for ranks in (1, 2, 3):
+        out = str(tmp_path / f"out{ranks}.bin")
+        r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "ics_transfer_99.dat"), str(ranks), out], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "MPI HOST STEP OK" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
+        raw = open(out, "rb").read()
+        n, nk, ia = np.frombuffer(raw[:12], dtype=np.int32)
+        dnu = np.frombuffer(raw[12:12 + 8 * nk], dtype=np.float64)
+        grid = np.frombuffer(raw[12 + 8 * nk:], dtype=np.float64)
+        assert grid.size == 2 * n * n * (n // 2 + 1)
+        res[ranks] = (int(nk), int(ia), dnu, grid)
+    assert res[1][0] > 0 and res[1][1] == 4                     # 0.0205 is too close to 0.02 to be kept (delta_tot_table.c:229)
+    for ranks in (2, 3):
+        assert res[ranks][:2] == res[1][:2]
+        # the cross-rank sum adds the slab sums in a different order than one rank's sweep: last-bit differences only
+        np.testing.assert_allclose(res[ranks][2], res[1][2], rtol=1e-12)
+        np.testing.assert_allclose(res[ranks][3], res[1][3], rtol=1e-12)
+    assert not np.array_equal(res[1][3][2:], np.zeros_like(res[1][3][2:]))

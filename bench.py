@@ -232,7 +232,10 @@ def ours(args):
     sim.add_nu_power_to_rhogrid(cosmo.time_transfer, grid.ptr, slab)
     sim.seed_history(98)
     a = 0.98
-    da = 0.001                                   # < 0.009: the row is integrated every step but not kept -> steady state
+    # < 0.009: the row is integrated every step but not kept -> steady state; and never past a = 1 (TimeMax), however
+    # many steps the caller asks for
+    n_calls = max(3, args.warmup) + args.steps + (0 if args.no_e2e else args.e2e_steps + 1) + 2
+    da = min(0.001, (0.9995 - a) / n_calls)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()                          # nvidia-smi needs ~1 s to deliver its first sample
@@ -306,28 +309,41 @@ def ours(args):
     # ---- end to end: the same call on HOST buffers (pinned), H2D + D2H inside the timed region
     e2e = None
     if not args.no_e2e and args.e2e_steps > 0:
+        pin, err = None, None
         try:
             pin = host.PinnedGrid(n, slab)
             capi.check(L.ksn_memcpy_d2h(pin.ptr, grid.ptr, grid.nbytes))
-            a += da
-            sim.add_nu_power_to_rhogrid(a, pin.ptr, slab)          # warm-up (allocates the staging buffer)
-            barrier()
-            te = time.perf_counter()
-            for _ in range(args.e2e_steps):
-                a += da
-                sim.add_nu_power_to_rhogrid(a, pin.ptr, slab)
-            barrier()
-            e_ms = (time.perf_counter() - te) * 1e3
-            te_t = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
-            if world > 1:
-                dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
-            e_step = te_t.item() / args.e2e_steps
-            e2e = {"value": modes_total / (e_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": grid.nbytes * world,
-                   "d2h_bytes_per_step": grid.nbytes * world, "ms_per_step": e_step, "steps": args.e2e_steps,
-                   "note": "add_nu_power_to_rhogrid on pinned HOST slabs: upload, K1, K2, K3, download, every step"}
-            pin.free()
         except capi.KsnError as exc:
-            e2e = {"value": None, "unit": UNIT, "error": str(exc)}
+            err = str(exc)
+        # page-locking tens of GB takes seconds and varies by rank; a rank that failed must not leave the others waiting
+        ok = torch.tensor([0.0 if err else 1.0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() < 1.0:
+            e2e = {"value": None, "unit": UNIT, "error": err or "another rank could not allocate its pinned host slab"}
+        else:
+            try:
+                barrier()
+                a += da
+                sim.add_nu_power_to_rhogrid(a, pin.ptr, slab)          # warm-up (allocates the staging buffer)
+                barrier()
+                te = time.perf_counter()
+                for _ in range(args.e2e_steps):
+                    a += da
+                    sim.add_nu_power_to_rhogrid(a, pin.ptr, slab)
+                barrier()
+                e_ms = (time.perf_counter() - te) * 1e3
+                te_t = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
+                if world > 1:
+                    dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
+                e_step = te_t.item() / args.e2e_steps
+                e2e = {"value": modes_total / (e_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": grid.nbytes * world,
+                       "d2h_bytes_per_step": grid.nbytes * world, "ms_per_step": e_step, "steps": args.e2e_steps,
+                       "note": "add_nu_power_to_rhogrid on pinned HOST slabs: upload, K1, K2, K3, download, every step"}
+            except capi.KsnError as exc:
+                e2e = {"value": None, "unit": UNIT, "error": str(exc)}
+        if pin is not None:
+            pin.free()
 
     if rank != 0:
         return

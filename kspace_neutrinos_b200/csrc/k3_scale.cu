@@ -341,9 +341,7 @@ static int k3_set_greens(int dims, const double *invwin, double asmth2)
     const size_t L = (size_t) dims / 2 + 1;
     int rc = ensure_device_buffer((void **) &c.d_iw, &c.iw_cap, (2 * L + K1_WZ_PAD) * sizeof(double));   // K1's layout: iw | z weights
     if (rc) return rc;
-    static double *d_gz = nullptr;
-    static size_t gz_cap = 0;
-    rc = ensure_device_buffer((void **) &d_gz, &gz_cap, L * sizeof(double));
+    rc = ensure_device_buffer((void **) &c.d_gz, &c.gz_cap, L * sizeof(double));
     if (rc) return rc;
     double *gz = (double *) malloc(L * sizeof(double));
     if (!gz) return set_error(KSN_ENOMEM, "K3: out of host memory");
@@ -353,14 +351,14 @@ static int k3_set_greens(int dims, const double *invwin, double asmth2)
     }
     k1_tables_invalidate();                 // c.d_iw is K1's table buffer: it must re-upload its own next time
     cudaError_t e = cudaMemcpyAsync(c.d_iw, invwin, L * sizeof(double), cudaMemcpyHostToDevice, c.stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_gz, gz, L * sizeof(double), cudaMemcpyHostToDevice, c.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c.d_gz, gz, L * sizeof(double), cudaMemcpyHostToDevice, c.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);       // gz is about to be freed
     free(gz);
     KSN_CUDA(e);
     g_k3greens.on = 1;
     g_k3greens.asmth2 = asmth2;
     g_k3greens.iw = c.d_iw;
-    g_k3greens.gz = d_gz;
+    g_k3greens.gz = c.d_gz;
     return KSN_OK;
 }
 

@@ -365,7 +365,7 @@ void ksn_shutdown(void)
     for (auto &kv : g_registered) cudaHostUnregister((void *) kv.first);
     g_registered.clear();
     cudaFree(c.d_partial); cudaFree(c.d_red); cudaFreeHost(c.h_red); cudaFree(c.d_thr); cudaFree(c.d_iw);
-    cudaFree(c.d_k3tab); cudaFreeHost(c.h_k3tab); cudaFree(c.d_stage); cudaFree(c.d_bg);
+    cudaFree(c.d_k3tab); cudaFreeHost(c.h_k3tab); cudaFree(c.d_gz); cudaFree(c.d_stage); cudaFree(c.d_bg);
     cudaFree(c.d_k2); cudaFreeHost(c.h_k2);
     free(c.geom.keff); free(c.geom.count);
     for (int i = 0; i < PH_COUNT; i++) for (int j = 0; j < 2; j++) cudaEventDestroy(c.ev[i][j]);

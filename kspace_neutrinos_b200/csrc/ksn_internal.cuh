@@ -43,6 +43,7 @@ struct Ctx {
              unsigned long long epoch = 0; double *keff = nullptr; long long *count = nullptr; size_t cap = 0; } geom;
     // K3 workspace
     double *d_k3tab = nullptr; size_t k3tab_cap = 0; double *h_k3tab = nullptr; size_t h_k3tab_cap = 0;
+    double *d_gz = nullptr; size_t gz_cap = 0;             // z factor of the fused Green's function (k3_set_greens)
     // staging buffer for host-resident grids
     void *d_stage = nullptr; size_t stage_cap = 0;
     bool stage_streaming = false;        // the slab did not fit: d_stage is a ring of chunks, K3 re-uploads (stage_plan)

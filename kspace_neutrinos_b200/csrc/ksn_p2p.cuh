@@ -21,7 +21,9 @@ namespace ksn {
 
 constexpr int KSN_P2P_MAX_RANKS = 16;
 constexpr size_t KSN_P2P_SLOT = 16384;          // doubles per (parity, source) slot: 3 * nrbins + 1 up to PMGRID = 8192
-constexpr long long KSN_P2P_TIMEOUT_CYCLES = 8000000000LL;   // ~4 s: a peer that never arrives is an error, not a hang
+// ~20 s at 1.9 GHz: a peer that never arrives is an error, not a hang -- but ranks of a real run may reach the step seconds
+// apart (page-locking a host slab, a snapshot being written), and that must not be one
+constexpr long long KSN_P2P_TIMEOUT_CYCLES = 40000000000LL;
 
 struct P2PDev {
     double *box[KSN_P2P_MAX_RANKS];   // every rank's mailbox as mapped in this process (box[rank] is this rank's own)

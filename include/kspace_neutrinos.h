@@ -242,6 +242,8 @@ int particle_nu_active(double a);                                               
  * complex values, row-major, caller-owned, modified in place.  The pointer may be host
  * memory (staged through the GPU) or device/managed memory (used in place). */
 int set_kspace_vars(char tag[][50], void *addr[], int id[], int nt);                            /* interface_gadget.h:45 */
+/* the reference picks the neutrino-aware variant with -DKSPACE_NEUTRINOS_2 (interface_gadget.c:199-219); this library
+ * picks it at run time: once the integrator has been initialised by a PM step */
 int save_total_power(const double Time, const int snapnum, const char *OutputDir);              /* :57 */
 
 int total_powerspectrum_f64(const int dims, void *outfield, const int nrbins, const int startslab, const int nslab, double *power, long long int *count, double *keffs, const MPI_Comm MYMPI_COMM_WORLD);

@@ -136,3 +136,90 @@ def test_get_and_set_nu_state(standin, ref):
     assert res["got"][0] == res["ref"][0] == ia.value + 1
     np.testing.assert_allclose(res["got"][1], res["ref"][1], rtol=1e-10)
     np.testing.assert_allclose(res["got"][2], res["ref"][2], rtol=1e-10)
+
+
+def test_config1_like_transfer_at_a_0p1_host_flow(standin, ref):
+    """BASELINE.json configs[1] in miniature (3 x 0.1 eV, CAMB ics_transfer_0.1.dat, TimeTransfer = 0.1; 32^3 instead of
+    256^3): init step, a kept row, a dropped row."""
+    n = 32
+    tfile = os.path.join(refs.GOLDEN, "camb_ics_transfer_0.1.dat")
+    g = refs.random_grid(n, seed=256)
+    times = (0.1, 0.12, 0.1205)
+    kw = dict(masses=(0.1, 0.1, 0.1), time_transfer=0.1, transfer=tfile)
+    want = _run(ref, "add_nu_power_to_rhogrid", g, times, False, **kw)
+    got = _run(standin, "add_nu_power_to_rhogrid_f64", g, times, False, **kw)
+    assert [w[0] for w in want] == [1, 2, 2]
+    for (ia_r, nk_r, g_r, dn_r), (ia_g, nk_g, g_g, dn_g) in zip(want, got):
+        assert (ia_r, nk_r) == (ia_g, nk_g)
+        np.testing.assert_allclose(dn_g, dn_r, rtol=1e-10, atol=0)
+        np.testing.assert_allclose(g_g, g_r, rtol=1e-10, atol=0)
+
+
+def test_float_grid_host_flow(standin):
+    """The float-grid build of the reference (no DOUBLEPRECISION_FFTW) against the product's _f32 entry through the host
+    layer: 1e-5 (north-star tolerance for a float grid)."""
+    ref_s = refs.ref_lib(False)
+    if ref_s is None:
+        pytest.skip("oracle/_ref not built")
+    n = 32
+    g = refs.random_grid(n, seed=9, dtype=np.float32)
+    times = (0.01, 0.03, 0.0305, 0.1)
+    want = _run(ref_s, "add_nu_power_to_rhogrid", g, times, False)
+    got = _run(standin, "add_nu_power_to_rhogrid_f32", g, times, False)
+    for (ia_r, nk_r, g_r, dn_r), (ia_g, nk_g, g_g, dn_g) in zip(want, got):
+        assert (ia_r, nk_r) == (ia_g, nk_g)
+        np.testing.assert_allclose(dn_g, dn_r, rtol=1e-5, atol=0)
+        np.testing.assert_allclose(g_g, g_r, rtol=1e-5, atol=0)
+
+
+def test_total_power_and_output_files_host_flow(standin, ref, tmp_path):
+    """compute_total_power_spectrum + save_total_power + save_neutrino_power (interface_gadget.c:114-144,196-224,
+    delta_tot_table.c:355-374).  save_total_power's KSPACE_NEUTRINOS_2 switch is a compile-time one in the reference
+    (:199-219; oracle/_ref is built without it, as the reference's own Makefile builds); the product decides at run time:
+    integrator initialised -> the KSPACE_NEUTRINOS_2 branch (total = get_delta_tot(delta_nu_last, delta_cdm_last)),
+    otherwise the plain branch.  Both are checked: the plain one byte for byte against the reference's file, the other
+    against the reference's own get_delta_tot on the reference's state."""
+    n = 32
+    g = refs.random_grid(n, seed=8)
+    out = {}
+    # (a) no neutrino steps taken: plain branch on both sides
+    for name, libh, tot in (("ref", ref, "compute_total_power_spectrum"), ("got", standin, "compute_total_power_spectrum_f64")):
+        refs.init_module(libh, n)
+        # init_module forgets delta_cdm_last; the reference writes through it unconditionally here (:136): give it one
+        keep = (C.c_double * (n // 2))()
+        C.c_void_p.in_dll(libh, "delta_cdm_last").value = C.addressof(keep)
+        gg = g.copy()
+        getattr(libh, tot)(0.02, refs.BOX, gg.ctypes.data_as(C.c_void_p), n, 0, n, 0)
+        C.c_void_p.in_dll(libh, "delta_cdm_last").value = None
+        d = tmp_path / (name + "_plain")
+        d.mkdir()
+        assert libh.save_total_power(0.02, 3, str(d).encode()) == 0
+        out[name] = (d / "powerspec_tot_003.txt").read_bytes()
+    assert len(out["ref"]) > 100 and out["got"] == out["ref"]
+    # (b) after two PM steps
+    for name, libh, step, tot in (("ref", ref, "add_nu_power_to_rhogrid", "compute_total_power_spectrum"),
+                                  ("got", standin, "add_nu_power_to_rhogrid_f64", "compute_total_power_spectrum_f64")):
+        om, dt = refs.init_module(libh, n)
+        gg = g.copy()
+        p = gg.ctypes.data_as(C.c_void_p)
+        getattr(libh, step)(0.01, refs.BOX, p, n, 0, n, 0)
+        getattr(libh, step)(0.02, refs.BOX, p, n, 0, n, 0)
+        d = tmp_path / name
+        d.mkdir()
+        assert libh.save_neutrino_power(0.02, 7, str(d).encode()) == 0
+        getattr(libh, tot)(0.02, refs.BOX, p, n, 0, n, 0)
+        assert libh.save_total_power(0.02, 3, str(d).encode()) == 0
+        out[name] = ((d / "powerspec_nu_007.txt").read_bytes(), (d / "powerspec_tot_003.txt").read_bytes())
+        assert libh.save_neutrino_power(0.02, 8, str(d / "no" / "such" / "dir").encode()) == -1      # fopen failure -> -1
+        if name == "ref":
+            # what a -DKSPACE_NEUTRINOS_2 build of the reference would have written (interface_gadget.c:199-219)
+            last = C.POINTER(C.c_double).in_dll(libh, "delta_cdm_last")
+            OmegaNua3 = libh.OmegaNu_nopart(0.02) * 0.02 ** 3
+            rows = out[name][1].decode().split("\n")
+            want = rows[:3]
+            for i in range(dt.nk):
+                tot_i = libh.get_delta_tot(dt.delta_nu_last[i], last[i], OmegaNua3, dt.Omeganonu, libh.OmegaNu(1.0), 0.0)
+                want.append("%s %s" % (rows[3 + i].split()[0], "%g" % (tot_i * tot_i)))
+            want_tot = ("\n".join(want) + "\n").encode()
+    assert len(out["ref"][0]) > 100 and out["got"][0] == out["ref"][0]
+    assert out["got"][1] == want_tot

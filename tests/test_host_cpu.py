@@ -218,3 +218,67 @@ def test_k1_tile_plan_for_the_named_grids(monkeypatch):
     monkeypatch.delenv("KSN_K1_WIN")
     monkeypatch.setenv("KSN_K1_TILE", "4,9,3")
     assert plan(256)[:3] == (4, 9, 3)
+
+
+def _golden_geometry(n):
+    g = np.load(os.path.join(refs.GOLDEN, "geometry_counts.npz"))
+    return g[f"count_{n}"], g[f"keffsum_{n}"]
+
+
+@pytest.mark.parametrize("n", [1024, 2048, 4096])
+def test_bin_thresholds_at_the_baseline_sizes(L, n):
+    """At BASELINE.json's PMGRIDs the reference cannot be swept here; tests/golden/geometry_counts.npz holds its data-independent
+    outputs (tools/make_golden_geometry.py: integer multiplicity histogram + the reference's bin expression, checked
+    against the compiled reference at the sizes it can do).  The thresholds K1 searches on the device must sit exactly on
+    the bin edges of that expression (this machine's libm), and the golden vector must be consistent with them."""
+    nrbins = n // 2
+    cnt, ksum = _golden_geometry(n)
+    assert cnt.sum() == n ** 3 - 1 and len(cnt) == nrbins
+    thr = C.POINTER(C.c_uint)()
+    iw = capi.c_double_p()
+    assert L.ksn_bin_tables(n, nrbins, C.byref(thr), C.byref(iw)) == 0
+    t = np.array([thr[i] for i in range(nrbins)], dtype=np.int64)
+    libm = C.CDLL("libm.so.6")
+    libm.log.restype = C.c_double
+    libm.log.argtypes = [C.c_double]
+    hb = 0.5 * ((nrbins - 1) / libm.log(n * 0.8660254037844386))
+    k2max = 3 * (n // 2) ** 2
+    for b in range(1, nrbins):
+        if t[b] > k2max:
+            assert cnt[b:].sum() == 0 or t[b] == k2max + 1
+            continue
+        assert math.floor(hb * libm.log(float(t[b]))) >= b
+        assert math.floor(hb * libm.log(float(t[b] - 1))) < b if t[b] > 1 else True
+    # an empty golden bin <=> no integer k2 = a^2+b^2+c^2 (a, b, c <= N/2) between its thresholds; cheap necessary check:
+    # bins whose threshold interval is empty must be empty in the golden vector
+    width = np.diff(np.append(t, k2max + 1))
+    assert np.all(cnt[width <= 0] == 0)
+    assert cnt[np.searchsorted(t, k2max, side="right") - 1] >= 1          # the corner mode's bin
+    assert np.all(ksum[cnt > 0] / cnt[cnt > 0] >= np.sqrt(np.maximum(t[cnt > 0], 1)) * (1 - 1e-12))
+    assert np.all(ksum[cnt > 0] / cnt[cnt > 0] < np.sqrt(t[cnt > 0] + width[cnt > 0].astype(float)))
+
+
+@pytest.mark.parametrize("n", [1024, 2048])
+def test_golden_counts_from_thresholds(L, n):
+    """PMGRID = 1024 and 2048 (BASELINE configs[2], [3]): mode counts recomputed here from the product's thresholds and a
+    numpy multiplicity histogram equal the golden vector bin for bin."""
+    nrbins, H = n // 2, n // 2
+    cnt, ksum = _golden_geometry(n)
+    thr = C.POINTER(C.c_uint)()
+    iw = capi.c_double_p()
+    assert L.ksn_bin_tables(n, nrbins, C.byref(thr), C.byref(iw)) == 0
+    t = np.array([thr[i] for i in range(nrbins)], dtype=np.int64)
+    w1 = np.where((np.arange(H + 1) == 0) | (np.arange(H + 1) == H), 1, 2).astype(np.int64)
+    sq = np.arange(H + 1, dtype=np.int64) ** 2
+    ab = (sq[:, None] + sq[None, :]).ravel()
+    wab = (w1[:, None] * w1[None, :]).ravel()
+    r2 = np.bincount(ab, weights=wab, minlength=2 * H * H + 1).astype(np.int64)     # pairs (i, j) per kx^2+ky^2
+    nz = np.nonzero(r2)[0]
+    got = np.zeros(nrbins, dtype=np.int64)
+    for c in range(H + 1):
+        b = np.searchsorted(t, nz + c * c, side="right") - 1
+        add = np.bincount(b, weights=r2[nz] * w1[c], minlength=nrbins).astype(np.int64)
+        if c == 0:
+            add[0] -= 1                                                 # k = 0 is not a mode (powerspectrum.c:65)
+        got += add
+    assert np.array_equal(got, cnt)

@@ -19,7 +19,7 @@ struct world {
     pthread_barrier_t bar;
     int size;
     pid_t pids[256];
-    unsigned char bounce[];      /* size * BOUNCE_BYTES */
+    _Alignas(64) unsigned char bounce[];      /* size * BOUNCE_BYTES; aligned for the typed reads of MPI_Allreduce */
 };
 
 static struct world *W;

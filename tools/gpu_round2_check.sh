@@ -17,3 +17,11 @@ tail -n 1 $O/r2_bench_tabcache.log | cut -c1-400
 timeout 200 python -m pytest tests -q -m gpu -x > $O/r2_pytest_gpu.log 2>&1
 echo "suite exit $?" | tee -a $O/r2_pytest_gpu.log
 tail -n 4 $O/r2_pytest_gpu.log
+# 4. compute-sanitizer over the kernels added after profiles/r1_sanitizer.txt was taken: K2 with bisections ahead of time,
+#    K1 bin window, K3 row pieces (small cases only: the tools slow kernels down 10-50x)
+CS=/usr/local/cuda/bin/compute-sanitizer
+timeout 600 $CS --tool memcheck python -m pytest tests/test_k2_gpu.py -q -k "speculative" > $O/r2_memcheck_k2spec.log 2>&1
+timeout 600 $CS --tool memcheck python -m pytest tests/test_k1_gpu.py -q -k "bin_window and 256" > $O/r2_memcheck_k1win.log 2>&1
+timeout 600 $CS --tool racecheck python -m pytest tests/test_k2_gpu.py -q -k "speculative and not True" > $O/r2_racecheck_k2spec.log 2>&1
+timeout 600 $CS --tool racecheck python -m pytest tests/test_k1_gpu.py -q -k "bin_window and 256-100" > $O/r2_racecheck_k1win.log 2>&1
+grep -h "ERROR SUMMARY\|RACECHECK SUMMARY\|passed\|failed" $O/r2_memcheck_*.log $O/r2_racecheck_*.log

@@ -37,6 +37,8 @@ void ksn_shutdown(void);
 const char *ksn_last_error(void);
 /* 1 if a CUDA device is usable from this process, else 0 (never fails). */
 int ksn_device_available(void);
+/* number of CUDA devices visible to this process (0 if there is none or no driver; never fails) */
+int ksn_device_count(void);
 /* device selected by ksn_init, -1 before */
 int ksn_device(void);
 

@@ -79,6 +79,7 @@ PROTOTYPES = {
     "ksn_shutdown": (None, []),
     "ksn_last_error": (C.c_char_p, []),
     "ksn_device_available": (C.c_int, []),
+    "ksn_device_count": (C.c_int, []),
     "ksn_device": (C.c_int, []),
     "ksn_comm_single": (C.c_int, []),
     "ksn_comm_nccl_unique_id": (C.c_int, [C.c_void_p]),

@@ -386,6 +386,14 @@ int ksn_device_available(void)
     return n > 0;
 }
 
+int ksn_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
 int ksn_device(void) { return g_ctx.inited ? g_ctx.device : -1; }
 
 int ksn_comm_single(void) { drop_comm(); return KSN_OK; }

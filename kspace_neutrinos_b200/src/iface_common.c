@@ -8,6 +8,8 @@
  * (small) input files itself, which yields the same state on every rank. */
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 #include "ksn_host.h"
 
 struct __kspace_params kspace_params;
@@ -24,18 +26,99 @@ double OmegaNu(double a) { return get_omega_nu(&omeganu_table, a); }
 double OmegaNu_nopart(double a) { return get_omega_nu_nopart(&omeganu_table, a); }
 
 #ifdef KSN_HAVE_MPI
+#include <unistd.h>
 static int mpi_allreduce_cb(double *buf, size_t n, void *user)
 {
     return MPI_Allreduce(MPI_IN_PLACE, buf, (int) n, MPI_DOUBLE, MPI_SUM, *(MPI_Comm *) user) != MPI_SUCCESS;
 }
 static MPI_Comm the_comm;
+
+/* collective: did it work on EVERY rank?  (a backend is kept only then -- half the ranks on another one would hang) */
+static int all_ok(MPI_Comm comm, int ok)
+{
+    int bad = !ok, nbad = 0;
+    MPI_Allreduce(&bad, &nbad, 1, MPI_INT, MPI_SUM, comm);
+    return nbad == 0;
+}
+
+/* The ranks of this rank's box, by host name: its index among them, and whether the communicator lives on one box. */
+static void box_layout(MPI_Comm comm, int rank, int size, int *local_rank, int *one_box)
+{
+    char mine[64], *all = malloc((size_t) 64 * size);
+    if (!all) terminate(1, "Could not allocate temporary memory for the host names of %d ranks\n", size);
+    memset(mine, 0, sizeof mine);
+    gethostname(mine, sizeof mine - 1);
+    MPI_Allgather(mine, 64, MPI_BYTE, all, 64, MPI_BYTE, comm);
+    *local_rank = 0;
+    *one_box = 1;
+    for (int r = 0; r < size; r++) {
+        const int same = !memcmp(all + (size_t) 64 * r, mine, 64);
+        if (same && r < rank) (*local_rank)++;
+        if (!same) *one_box = 0;
+    }
+    free(all);
+}
+
+/* The one exchange step of the path (powerspectrum.c:91-95) on the communicator the host passes in.  One MPI rank per
+ * GPU; the first call picks, collectively, the first of these that works on every rank ($KSN_COMM = p2p | nccl | mpi
+ * starts further down the list):
+ *   p2p   all ranks on one box and able to map each other's HBM: the sum happens inside the final-reduce kernel over
+ *         NVLink peer memory (handles exchanged with MPI_Allgather, a trial sum checked on every rank);
+ *   nccl  ncclAllReduce on a communicator bootstrapped with MPI_Bcast of the unique id;
+ *   mpi   the sums go to the host and through MPI_Allreduce, as the reference does.
+ * A host that has already bound a backend itself (ksn_comm_*) is left alone. */
 static void bind_comm(MPI_Comm comm)
 {
     int rank, size;
     the_comm = comm;
     MPI_Comm_rank(comm, &rank);
     MPI_Comm_size(comm, &size);
-    if (size > 1 && ksn_comm_size() == 1) ksn_comm_host_callback(mpi_allreduce_cb, &the_comm, size, rank);
+    if (size <= 1 || ksn_comm_size() != 1) return;
+    const char *want = getenv("KSN_COMM");
+    const int from_p2p = !want || !strcmp(want, "p2p"), from_nccl = from_p2p || !strcmp(want, "nccl");
+    int local_rank, one_box;
+    box_layout(comm, rank, size, &local_rank, &one_box);
+    /* unless the host chose a device (ksn_init, $KSN_DEVICE, $LOCAL_RANK): rank i of a box takes GPU i */
+    const int ndev = ksn_device_count();
+    if (ndev > 0 && ksn_device() < 0 && !getenv("KSN_DEVICE") && !getenv("LOCAL_RANK")) ksn_init(local_rank % ndev);
+    if (from_p2p && one_box && size <= 16) {
+        unsigned char mine[64], *all = malloc((size_t) 64 * size);
+        int ok = all != NULL && ndev > 0 && ksn_comm_p2p_export(mine) == 0;
+        if (all_ok(comm, ok)) {
+            MPI_Allgather(mine, 64, MPI_BYTE, all, 64, MPI_BYTE, comm);
+            ok = ksn_comm_p2p_init(all, size, rank) == 0;
+            if (all_ok(comm, ok)) {                   /* (also the barrier: every mailbox is mapped before a round starts) */
+                double v[8];
+                for (int i = 0; i < 8; i++) v[i] = (rank + 1) + 100. * i;
+                ok = ksn_comm_allreduce_host(v, 8) == 0;
+                for (int i = 0; i < 8; i++) ok = ok && v[i] == size * (size + 1) / 2. + 100. * i * size;
+                if (all_ok(comm, ok)) {
+                    free(all);
+                    message(0, "kspace-neutrinos: bin sums are reduced through NVLink peer memory (%d ranks)\n", size);
+                    return;
+                }
+            }
+        }
+        free(all);
+        ksn_comm_single();                            /* every rank forgets the half-built backend */
+    }
+    if (from_nccl) {
+        unsigned char id[128], probe[128];
+        /* every rank: is there a device, can libnccl be loaded here?  (a rank that failed later would leave the others
+         * waiting inside ncclCommInitRank) */
+        int ok = ndev > 0 && ksn_comm_nccl_unique_id(rank == 0 ? id : probe) == 0;
+        if (all_ok(comm, ok)) {
+            MPI_Bcast(id, 128, MPI_BYTE, 0, comm);
+            ok = ksn_comm_nccl_init(id, size, rank) == 0;
+            if (all_ok(comm, ok)) {
+                message(0, "kspace-neutrinos: bin sums are reduced with NCCL (%d ranks)\n", size);
+                return;
+            }
+            ksn_comm_single();
+        }
+    }
+    ksn_comm_host_callback(mpi_allreduce_cb, &the_comm, size, rank);
+    message(0, "kspace-neutrinos: bin sums are reduced with MPI_Allreduce on the host (%d ranks)\n", size);
 }
 #else
 static void bind_comm(MPI_Comm comm) { (void) comm; }

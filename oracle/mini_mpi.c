@@ -103,6 +103,22 @@ int MPI_Bcast(void *buf, int count, MPI_Datatype type, int root, MPI_Comm comm)
     return MPI_SUCCESS;
 }
 
+int MPI_Allgather(const void *sendbuf, int sendcount, MPI_Datatype sendtype, void *recvbuf, int recvcount, MPI_Datatype recvtype, MPI_Comm comm)
+{
+    (void) comm; (void) recvcount; (void) recvtype;
+    const size_t n = (size_t) sendcount * tsize(sendtype);
+    if (n > BOUNCE_BYTES) { fprintf(stderr, "mini_mpi: MPI_Allgather of %zu bytes per rank\n", n); _exit(99); }
+    if (my_size == 1) {
+        if (sendbuf != recvbuf) memcpy(recvbuf, sendbuf, n);
+        return MPI_SUCCESS;
+    }
+    memcpy(W->bounce + (size_t) my_rank * BOUNCE_BYTES, sendbuf, n);
+    pthread_barrier_wait(&W->bar);
+    for (int r = 0; r < my_size; r++) memcpy((char *) recvbuf + (size_t) r * n, W->bounce + (size_t) r * BOUNCE_BYTES, n);
+    pthread_barrier_wait(&W->bar);
+    return MPI_SUCCESS;
+}
+
 int MPI_Allreduce(const void *sendbuf, void *recvbuf, int count, MPI_Datatype type, MPI_Op op, MPI_Comm comm)
 {
     (void) comm; (void) op;

@@ -2,7 +2,8 @@
  * /root/reference compile unmodified in an image with no MPI.  Implemented in
  * oracle/mini_mpi.c: rank/size come from ksn_minimpi_fork(); with one rank every
  * collective degenerates to a copy.  Only the calls the reference makes are declared
- * (powerspectrum.c:91-95, interface_common.c:56-73,186, interface_gadget.c:189). */
+ * (powerspectrum.c:91-95, interface_common.c:56-73,186, interface_gadget.c:189), plus MPI_Allgather for the
+ * product's own host layer (kspace_neutrinos_b200/src/iface_common.c: backend bootstrap). */
 #ifndef KSN_ORACLE_MPI_SHIM_H
 #define KSN_ORACLE_MPI_SHIM_H
 #include <stddef.h>
@@ -23,6 +24,7 @@ int MPI_Abort(MPI_Comm comm, int code);
 int MPI_Barrier(MPI_Comm comm);
 int MPI_Bcast(void *buf, int count, MPI_Datatype type, int root, MPI_Comm comm);
 int MPI_Allreduce(const void *sendbuf, void *recvbuf, int count, MPI_Datatype type, MPI_Op op, MPI_Comm comm);
+int MPI_Allgather(const void *sendbuf, int sendcount, MPI_Datatype sendtype, void *recvbuf, int recvcount, MPI_Datatype recvtype, MPI_Comm comm);
 int MPI_Comm_rank(MPI_Comm comm, int *rank);
 int MPI_Comm_size(MPI_Comm comm, int *size);
 /* oracle-only: fork nranks-1 children sharing a MAP_SHARED scratch; returns this

@@ -1,8 +1,8 @@
 /* TEST INFRASTRUCTURE -- NOT PART OF THE PRODUCT, never linked into libkspace_neutrinos_b200.so.
  *
- * A CPU stand-in for the six device entry points the product's HOST layer calls (include/ksn_b200.h:
+ * A CPU stand-in for the device entry points the product's HOST layer calls (include/ksn_b200.h:
  * ksn_set_background, ksn_delta_nu_integrate, ksn_powerspectrum_sums, ksn_step_staged, ksn_step_staged_greens,
- * ksn_last_error), written on top of the CPU oracle (oracle/ksn_oracle.c, oracle/mini_gsl.c).  CPU tests link it with
+ * ksn_last_error, and the ksn_comm_* / ksn_init family the -DKSN_HAVE_MPI build uses to pick its collective), written on top of the CPU oracle (oracle/ksn_oracle.c, oracle/mini_gsl.c).  CPU tests link it with
  * kspace_neutrinos_b200/src/ *.c -- instead of the CUDA objects -- so that the host layer's own logic (the per-step
  * state machine of get_delta_nu_update, the table layout, save/resume files, the glue either side of the kernels) can be
  * run in a container with no GPU, e.g. under the reference's own cmocka programs (tests/test_reference_programs.py).
@@ -25,14 +25,65 @@
 static char errbuf[256] = "";
 const char *ksn_last_error(void) { return errbuf; }
 
-/* collective: only the host call-back backend (what iface_common.c binds under -DKSN_HAVE_MPI) */
+/* There is no device here: everything that needs one says so (the host layer's backend bootstrap under -DKSN_HAVE_MPI
+ * must then fall back, collectively, to the host call-back).  KSN_STANDIN_P2P=1 lets the peer-memory entry points
+ * "succeed" instead -- the sums then travel through the MPI shim -- so that the bootstrap's handshake (handles gathered,
+ * trial sum, all-ranks verdicts) can be walked through on the CPU; KSN_STANDIN_P2P_FAIL_RANK=r makes rank r alone fail. */
+#ifdef KSN_HAVE_MPI
+#include <mpi.h>
+#endif
 static ksn_allreduce_fn comm_fn;
 static void *comm_user;
-static int comm_n = 1, comm_r = 0;
-int ksn_comm_host_callback(ksn_allreduce_fn fn, void *user, int nranks, int rank) { comm_fn = fn; comm_user = user; comm_n = nranks; comm_r = rank; return KSN_OK; }
-int ksn_comm_allreduce_host(double *buf, size_t n) { return comm_n > 1 && comm_fn ? comm_fn(buf, n, comm_user) : KSN_OK; }
+static int comm_n = 1, comm_r = 0, fake_p2p = 0, exported = 0;
+static int nodev(const char *what) { snprintf(errbuf, sizeof errbuf, "%s: no CUDA device (CPU stand-in)", what); return KSN_ENODEV; }
+static int standin_p2p(void)
+{
+#ifdef KSN_HAVE_MPI
+    const char *e = getenv("KSN_STANDIN_P2P"), *f = getenv("KSN_STANDIN_P2P_FAIL_RANK");
+    int rank = 0;
+    MPI_Comm_rank(MPI_COMM_WORLD, &rank);
+    return e && atoi(e) && !(f && atoi(f) == rank);
+#else
+    return 0;
+#endif
+}
+int ksn_init(int device) { (void) device; return nodev("ksn_init"); }
+int ksn_device(void) { return -1; }
+int ksn_device_available(void) { return standin_p2p(); }
+int ksn_device_count(void) { return standin_p2p() ? 1 : 0; }
+int ksn_comm_single(void) { comm_fn = NULL; comm_user = NULL; comm_n = 1; comm_r = 0; fake_p2p = 0; return KSN_OK; }
+int ksn_comm_nccl_unique_id(void *id128) { (void) id128; return nodev("ksn_comm_nccl_unique_id"); }
+int ksn_comm_nccl_init(const void *id128, int nranks, int rank) { (void) id128; (void) nranks; (void) rank; return nodev("ksn_comm_nccl_init"); }
+int ksn_comm_p2p_export(void *handle64)
+{
+    if (!standin_p2p()) return nodev("ksn_comm_p2p_export");
+    memset(handle64, 0, 64);
+    strcpy((char *) handle64, "standin mailbox");
+    exported = 1;
+    return KSN_OK;
+}
+int ksn_comm_p2p_init(const void *handles, int nranks, int rank)
+{
+    if (!exported) { snprintf(errbuf, sizeof errbuf, "ksn_comm_p2p_init: call ksn_comm_p2p_export first"); return KSN_EINVAL; }
+    for (int r = 0; r < nranks; r++)
+        if (strcmp((const char *) handles + 64 * r, "standin mailbox")) { snprintf(errbuf, sizeof errbuf, "ksn_comm_p2p_init: bad handle of rank %d", r); return KSN_ECOMM; }
+    ksn_comm_single();
+    comm_n = nranks; comm_r = rank; fake_p2p = 1;
+    return KSN_OK;
+}
+int ksn_comm_host_callback(ksn_allreduce_fn fn, void *user, int nranks, int rank) { ksn_comm_single(); comm_fn = fn; comm_user = user; comm_n = nranks; comm_r = rank; return KSN_OK; }
+int ksn_comm_allreduce_host(double *buf, size_t n)
+{
+    if (comm_n <= 1) return KSN_OK;
+#ifdef KSN_HAVE_MPI
+    if (fake_p2p) return MPI_Allreduce(MPI_IN_PLACE, buf, (int) n, MPI_DOUBLE, MPI_SUM, MPI_COMM_WORLD) == MPI_SUCCESS ? KSN_OK : KSN_ECOMM;
+#endif
+    return comm_fn ? comm_fn(buf, n, comm_user) : KSN_ECOMM;
+}
 int ksn_comm_size(void) { return comm_n; }
 int ksn_comm_rank(void) { return comm_r; }
+/* which backend the host layer ended up with (tests): 0 none, 1 host call-back, 2 the pretended peer memory */
+int ksn_standin_backend(void) { return comm_n <= 1 ? 0 : fake_p2p ? 2 : 1; }
 
 static ksn_hubble_fn bg_hub;
 static void *bg_user;

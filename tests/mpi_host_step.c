@@ -18,6 +18,8 @@ void *ksn_minimpi_shared_alloc(size_t bytes);
 
 #define N 24
 
+int ksn_standin_backend(void);
+
 int main(int argc, char **argv)
 {
     if (argc < 4) { fprintf(stderr, "usage: %s transfer_file nranks out\n", argv[0]); return 2; }
@@ -52,7 +54,7 @@ int main(int argc, char **argv)
     const int start = (int) ((long long) rank * N / R), end = rank == R - 1 ? N : (int) ((long long) (rank + 1) * N / R);
     const double times[] = { 0.01, 0.02, 0.0205, 0.05, 0.2 };
     for (size_t t = 0; t < sizeof times / sizeof times[0]; t++)
-        add_nu_power_to_rhogrid(times[t], Box, grid + start * plane, N, start, end - start, MPI_COMM_WORLD);
+        add_nu_power_to_rhogrid_f64(times[t], Box, grid + start * plane, N, start, end - start, MPI_COMM_WORLD);
     /* every rank must hold the same integrator state */
     double chk = 0;
     for (int k = 0; k < delta_tot_table.nk; k++) chk += delta_tot_table.delta_nu_last[k] * (k + 1);
@@ -60,6 +62,11 @@ int main(int argc, char **argv)
     MPI_Barrier(MPI_COMM_WORLD);
     int bad = 0;
     for (int r = 0; r < R; r++) if (verdict[r] != verdict[0]) bad = 1;
+    /* which collective the bootstrap (iface_common.c: bind_comm) settled on -- it must be the same one on every rank */
+    verdict[32 + rank] = ksn_standin_backend();
+    MPI_Barrier(MPI_COMM_WORLD);
+    for (int r = 0; r < R; r++) if (verdict[32 + r] != verdict[32]) bad = 1;
+    if (rank == 0) printf("BACKEND %d\n", (int) verdict[32]);
     if (rank == 0) {
         FILE *f = fopen(argv[3], "wb");
         if (!f) { perror(argv[3]); bad = 1; }

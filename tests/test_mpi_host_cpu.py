@@ -14,7 +14,7 @@ def test_two_rank_mpi_build_of_the_host_layer(tmp_path):
     assert os.path.exists(lib), "build the product first (__graft_entry__.build())"
     exe = str(tmp_path / "mpi_host_flow")
     srcs = sorted(glob.glob(os.path.join(PKG, "src", "*.c")))
-    cmd = ["gcc", "-O1", "-g", "-Wall", "-DKSN_HAVE_MPI", "-DDOUBLEPRECISION_FFTW",
+    cmd = ["gcc", "-O1", "-g", "-Wall", "-Werror=implicit-function-declaration", "-DKSN_HAVE_MPI", "-DDOUBLEPRECISION_FFTW",
            "-I", os.path.join(ROOT, "oracle", "shim"), "-I", os.path.join(ROOT, "oracle"), "-I", os.path.join(ROOT, "include"),
            "-I", os.path.join(PKG, "src"),
            os.path.join(ROOT, "tests", "mpi_host_flow.c"), *srcs, os.path.join(ROOT, "oracle", "mini_mpi.c"),
@@ -32,7 +32,7 @@ def test_slab_split_pm_steps_over_mini_mpi(tmp_path):
     exe = str(tmp_path / "mpi_host_step")
     srcs = sorted(glob.glob(os.path.join(PKG, "src", "*.c")))
     orc = [os.path.join(ROOT, "oracle", f) for f in ("ksn_oracle.c", "mini_gsl.c", "mini_mpi.c")]
-    cmd = ["gcc", "-O2", "-g", "-Wall", "-DKSN_HAVE_MPI", "-DDOUBLEPRECISION_FFTW",
+    cmd = ["gcc", "-O2", "-g", "-Wall", "-Werror=implicit-function-declaration", "-DKSN_HAVE_MPI", "-DDOUBLEPRECISION_FFTW",
            "-I", os.path.join(ROOT, "oracle", "shim"), "-I", os.path.join(ROOT, "oracle"), "-I", os.path.join(ROOT, "include"),
            "-I", os.path.join(PKG, "src"),
            os.path.join(ROOT, "tests", "mpi_host_step.c"), os.path.join(ROOT, "tests", "device_standin.c"), *srcs, *orc,
@@ -40,10 +40,19 @@ def test_slab_split_pm_steps_over_mini_mpi(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     res = {}
+    # the backend bootstrap (iface_common.c bind_comm): no device -> host call-back (1) on every rank; pretended peer
+    # memory -> (2) after the handle exchange and the trial sum; one rank failing -> all ranks fall back together
+    for env, ranks, want in (({"KSN_STANDIN_P2P": "1"}, 3, 2), ({"KSN_STANDIN_P2P": "1", "KSN_STANDIN_P2P_FAIL_RANK": "1"}, 3, 1),
+                             ({"KSN_STANDIN_P2P": "1", "KSN_COMM": "mpi"}, 2, 1), ({"KSN_STANDIN_P2P": "1", "KSN_COMM": "nccl"}, 2, 1)):
+        out = str(tmp_path / "boot.bin")
+        r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "ics_transfer_99.dat"), str(ranks), out], capture_output=True, text=True,
+                           timeout=300, env={**os.environ, **env})
+        assert r.returncode == 0 and "MPI HOST STEP OK" in r.stdout and f"BACKEND {want}" in r.stdout, (env, r.stdout[-1000:] + r.stderr[-2000:])
     for ranks in (1, 2, 3):
         out = str(tmp_path / f"out{ranks}.bin")
         r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "ics_transfer_99.dat"), str(ranks), out], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and "MPI HOST STEP OK" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
+        assert f"BACKEND {0 if ranks == 1 else 1}" in r.stdout, r.stdout[-1000:]
         raw = open(out, "rb").read()
         n, nk, ia = np.frombuffer(raw[:12], dtype=np.int32)
         dnu = np.frombuffer(raw[12:12 + 8 * nk], dtype=np.float64)

@@ -439,9 +439,16 @@ __device__ __forceinline__ double queue_get(unsigned addr)
 // 4096) touch only the upper part of the bin range: with WIN a warp keeps the bins >= hot_lo in shared memory and the
 // rarely used ones below in a global-memory array of its own (`cold`, read and written through L1 by this warp only, in
 // the same fixed order), which makes room for eight warps again.
-template <int CT, bool WIN>
+//
+// real = float (opt-in, KSN_K1_F32_TILE=1: written after this round's GPU minutes were spent, not yet run on a B200): a
+// float row is (N/2+1)*8 bytes, so every other row -- and with it every tile of that row -- starts 8 bytes off the
+// 16-byte granule of a bulk copy.  Such a tile is copied from one mode earlier (`sh` = 1) and to an even mode count; the
+// lanes read their chunks `sh` modes into the stage, and the one or two foreign modes at the ends are either never read
+// or walked with weight 0 like everything past a row's end.  |F|^2 is formed in float as the reference's float build does
+// (powerspectrum.c:68 with fftw_real = float), the window stays the separable double one (float-grid tolerance 1e-5).
+template <typename real, int CT, bool WIN>
 __global__ void __launch_bounds__((CT == 5 || CT == 9 ? K1T_MAXW : 8) * 32, 1)
-k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbins, long long plane0, float binscale,
+k1_tile_kernel(const Cplx<real> *__restrict__ grid, int nrows, int N, int nrbins, long long plane0, float binscale,
                const unsigned *__restrict__ thr, const double *__restrict__ iw, double *__restrict__ partial, int accumulate,
                int Crt, int T, int S, int stage_bytes, unsigned k2_single, int log2N, int hot_lo, double *__restrict__ cold)
 {
@@ -485,9 +492,14 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
 
     auto issue = [&](int r, int t, int s) {         // lane 0: bulk copy of tile t of row r into stage s
         const int z0 = t * TE, len = min(TE, L - z0);
-        const unsigned bytes = (unsigned) len * 16u;
+        unsigned bytes = (unsigned) len * 16u;
         const unsigned bar = bar0 + 8u * s, dst = smem_addr(mystage + (size_t) s * stage_bytes);
-        const Cplx<double> *src = grid + (size_t) r * L + z0;
+        const Cplx<real> *src = grid + (size_t) r * L + z0;
+        if constexpr (sizeof(real) == 4) {
+            const unsigned sh = (unsigned) (((size_t) r * L + z0) & 1);    // slab-relative mode index of the tile's first mode: odd?
+            bytes = (((unsigned) len + sh + 1u) & ~1u) * 8u;               // (the host took this kernel only for an even mode total)
+            src -= sh;
+        }
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -538,7 +550,8 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
         const int spread = __reduce_max_sync(0xffffffffu, be - fbin);      // most runs any lane will close in this tile
         const bool single = (unsigned) c + (unsigned) z0 * (unsigned) z0 >= k2_single;
         merge_first_runs();                                            // of the previous tile
-        const Cplx<double> *chunk = (const Cplx<double> *) (mystage + (size_t) s * stage_bytes) + lane * C;
+        const Cplx<real> *chunk = (const Cplx<real> *) (mystage + (size_t) s * stage_bytes) + lane * C;
+        if constexpr (sizeof(real) == 4) chunk += ((size_t) r * L + z0) & 1;     // the copy started one mode early
         const double *wz = iwz_g + zl;
         if (CT > 0 && t != t_loaded) {             // (a warp keeps the same tile-of-row whenever T divides its stride)
 #pragma unroll
@@ -562,8 +575,9 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
 #pragma unroll
             for (int i = 1; i < R - 1; i++) nx[i] = thr_s[min(b + 1 + i, nrbins + 2)];
             unsigned qa = q0;
-            auto step = [&](const Cplx<double> v, double w) {
-                const double pp = fma(v.im, v.im, v.re * v.re);
+            auto step = [&](const Cplx<real> v, double w) {
+                double pp;
+                if constexpr (sizeof(real) == 8) pp = fma(v.im, v.im, v.re * v.re); else pp = (double) fmaf(v.im, v.im, v.re * v.re);
                 const bool ch = k2 >= nx[0];
                 queue_push_if(ch, qa, acc);
                 qa += ch ? 256u : 0u;
@@ -580,14 +594,14 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
 #pragma unroll
                 for (int e = 1; e < (CT > 0 ? CT : 1); e++) step(chunk[e], wreg[e]);
             } else {
-                Cplx<double> vc[4];
+                Cplx<real> vc[4];
                 double wc[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) { vc[u] = chunk[u]; wc[u] = __ldg(wz + u); }
                 wc[0] *= worigin;
 #pragma unroll 2
                 for (int e = 0; e + 4 < C; e += 4) {           // C = 4q+1: q blocks of four, then one mode
-                    Cplx<double> vn[4];
+                    Cplx<real> vn[4];
                     double wn[4];
 #pragma unroll
                     for (int u = 0; u < 4; u++) { vn[u] = chunk[e + 4 + u]; wn[u] = __ldg(wz + e + 4 + u); }
@@ -620,8 +634,9 @@ k1_tile_kernel(const Cplx<double> *__restrict__ grid, int nrows, int N, int nrbi
         } else {
             // GENERAL tile (the low-k corner, where bins are narrower than a step in k^2): finished runs go straight to the bins
             facc = 0.0;
-            auto step = [&](const Cplx<double> v, double w) {
-                const double pp = fma(v.im, v.im, v.re * v.re);
+            auto step = [&](const Cplx<real> v, double w) {
+                double pp;
+                if constexpr (sizeof(real) == 8) pp = fma(v.im, v.im, v.re * v.re); else pp = (double) fmaf(v.im, v.im, v.re * v.re);
                 if (k2 >= nxt) {
                     if (b == fbin) facc = acc; else { double *bp = binp(b); *bp = fma(acc, wxy, *bp); }
                     acc = 0.0;
@@ -664,10 +679,10 @@ static char g_k1_last[192] = "none";
 struct K1TileCfg { int W, C, S, T, stage_bytes, hot_lo; size_t smem, inflight; };
 
 // nhot: bins a warp keeps in shared memory (all nrbins of them without the bin window)
-static size_t k1_tile_smem(int L, int nrbins, int nhot, int W, int C, int S, int *T_out, int *stage_out)
+static size_t k1_tile_smem(int L, int nrbins, int nhot, int W, int C, int S, int *T_out, int *stage_out, int esz = 16)
 {
     const int TE = 32 * C, T = (L + TE - 1) / TE;
-    const int stage = (int) ((((size_t) TE + 8) * 16 + 127) & ~(size_t) 127);
+    const int stage = (int) ((((size_t) TE + 8) * esz + 127) & ~(size_t) 127);      // esz: bytes per mode (16 double, 8 float)
     if (T_out) *T_out = T;
     if (stage_out) *stage_out = stage;
     return (size_t) W * S * stage + (size_t) W * nhot * 8 + (size_t) W * K1T_QRUNS * 32 * 8 + (size_t) W * S * 8 +
@@ -680,7 +695,7 @@ static int k1_tile_max_warps(int C) { return (C == 5 || C == 9) ? K1T_MAXW : 8; 
 // goes as warps x C/(C+10) (the per-tile bookkeeping costs about ten modes' worth) -- fitted to probes at 1024^3, 2048^3
 // and 4096^3 slabs (tools/k1_tile_probe.py); shared memory (bins: 8 nrbins bytes per warp) decides how many warps fit.
 // KSN_K1_TILE="W,C,S" overrides.
-static bool k1_tile_config(int L, int nrbins, size_t budget, int ctas, K1TileCfg *best)
+static bool k1_tile_config(int L, int nrbins, size_t budget, int ctas, K1TileCfg *best, int esz = 16)
 {
     best->W = 0;
     best->hot_lo = 0;
@@ -696,20 +711,20 @@ static bool k1_tile_config(int L, int nrbins, size_t budget, int ctas, K1TileCfg
             for (int S = 1; S <= 4; S++) {
                 if (fw ? (W != fw || C != fc || S != fs) : S < 2) continue;
                 int T, stage;
-                size_t smem = k1_tile_smem(L, nrbins, nrbins, W, C, S, &T, &stage);
+                size_t smem = k1_tile_smem(L, nrbins, nrbins, W, C, S, &T, &stage, esz);
                 const bool compile_time = C == 5 || C == 9 || C == 13 || C == 17;
                 int hot_lo = 0;
                 if (smem > budget || window == 2) {
                     // bin window (k1_tile_kernel<CT, true>): only where all the bins fit for fewer than eight warps, only
                     // up to eight warps, and with at least a quarter of the bins (the upper e-fold and more) in shared memory
                     if (!window || !compile_time || C < 9 || W > 8) continue;
-                    const size_t rest = k1_tile_smem(L, nrbins, 0, W, C, S, nullptr, nullptr);
+                    const size_t rest = k1_tile_smem(L, nrbins, 0, W, C, S, nullptr, nullptr, esz);
                     if (rest >= budget) continue;
                     int nhot = (int) ((budget - rest) / ((size_t) W * 8)) & ~31;
                     if (window == 2) nhot = std::min(nhot, std::max(64, (nrbins / 4) & ~31));
                     if (nhot < nrbins / 4 || nhot < 64 || nhot >= nrbins) continue;
                     hot_lo = nrbins - nhot;
-                    smem = k1_tile_smem(L, nrbins, nhot, W, C, S, nullptr, nullptr);
+                    smem = k1_tile_smem(L, nrbins, nhot, W, C, S, nullptr, nullptr, esz);
                 }
                 const int TE = 32 * C;
                 if (T > 1 && C < 5) continue;                             // tiny tiles only for tiny rows
@@ -720,7 +735,7 @@ static bool k1_tile_config(int L, int nrbins, size_t budget, int ctas, K1TileCfg
                     best_score = score;
                     best->W = W; best->C = C; best->S = S; best->T = T; best->stage_bytes = stage; best->smem = smem;
                     best->hot_lo = hot_lo;
-                    best->inflight = (size_t) W * S * TE * 16;
+                    best->inflight = (size_t) W * S * TE * esz;
                 }
             }
     return best->W > 0;
@@ -898,8 +913,12 @@ static int k1_launch_t(const void *dgrid, int dims, int nrbins, long long plane0
         return KSN_OK;
     };
     K1TileCfg tc;
-    if (!FULL && sizeof(real) == 8 && !getenv("KSN_K1_PAIR") && !getenv("KSN_K1_NOPAIR") && ((uintptr_t) dgrid & 15) == 0 &&
-        k1_tile_config(dims / 2 + 1, nrbins, c.smem_optin, c.num_sms, &tc)) {
+    // float rows through the tile kernel: opt-in until it has been through the GPU parity suite (see the kernel); it needs
+    // an even number of modes in the slab (the last bulk copy is rounded up to a mode pair)
+    const char *f32tile = getenv("KSN_K1_F32_TILE");
+    const bool tile_ok = sizeof(real) == 8 || (f32tile && atoi(f32tile) > 0 && ((long long) nrows * (dims / 2 + 1)) % 2 == 0);
+    if (!FULL && tile_ok && !getenv("KSN_K1_PAIR") && !getenv("KSN_K1_NOPAIR") && ((uintptr_t) dgrid & 15) == 0 &&
+        k1_tile_config(dims / 2 + 1, nrbins, c.smem_optin, c.num_sms, &tc, (int) (2 * sizeof(real)))) {
         int log2N = -1;
         if ((dims & (dims - 1)) == 0) { log2N = 0; while ((1 << log2N) < dims) log2N++; }
         static double *d_cold = nullptr;          // per-warp bins below the window (bin window only)
@@ -910,30 +929,31 @@ static int k1_launch_t(const void *dgrid, int dims, int nrbins, long long plane0
         }
         auto go = [&](auto kern) -> int {
             KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc.smem));
-            kern<<<ctas, tc.W * 32, tc.smem, c.stream>>>((const Cplx<double> *) dgrid, nrows, dims, nrbins, plane0, binscale,
+            kern<<<ctas, tc.W * 32, tc.smem, c.stream>>>((const Cplx<real> *) dgrid, nrows, dims, nrbins, plane0, binscale,
                                                          c.d_thr, c.d_iw, c.d_partial, accumulate ? 1 : 0, tc.C, tc.T, tc.S, tc.stage_bytes,
                                                          g_k1_k2_single, log2N, tc.hot_lo, d_cold);
             return KSN_OK;
         };
         int rct;
         switch (tc.hot_lo ? -tc.C : tc.C) {
-        case 5: rct = go(k1_tile_kernel<5, false>); break;
-        case 9: rct = go(k1_tile_kernel<9, false>); break;
-        case 13: rct = go(k1_tile_kernel<13, false>); break;
-        case 17: rct = go(k1_tile_kernel<17, false>); break;
-        case -9: rct = go(k1_tile_kernel<9, true>); break;
-        case -13: rct = go(k1_tile_kernel<13, true>); break;
-        case -17: rct = go(k1_tile_kernel<17, true>); break;
-        default: rct = go(k1_tile_kernel<0, false>); break;
+        case 5: rct = go(k1_tile_kernel<real, 5, false>); break;
+        case 9: rct = go(k1_tile_kernel<real, 9, false>); break;
+        case 13: rct = go(k1_tile_kernel<real, 13, false>); break;
+        case 17: rct = go(k1_tile_kernel<real, 17, false>); break;
+        case -9: rct = go(k1_tile_kernel<real, 9, true>); break;
+        case -13: rct = go(k1_tile_kernel<real, 13, true>); break;
+        case -17: rct = go(k1_tile_kernel<real, 17, true>); break;
+        default: rct = go(k1_tile_kernel<real, 0, false>); break;
         }
         if (rct) return rct;
         c.launches++;
         KSN_CUDA(cudaGetLastError());
         if (tc.hot_lo)
-            snprintf(g_k1_last, sizeof g_k1_last, "k1_tile_kernel (%d warps x %d modes per lane, %d stages, %d tiles per row, bins >= %d of %d in shared memory)",
-                     tc.W, tc.C, tc.S, tc.T, tc.hot_lo, nrbins);
+            snprintf(g_k1_last, sizeof g_k1_last, "k1_tile_kernel%s (%d warps x %d modes per lane, %d stages, %d tiles per row, bins >= %d of %d in shared memory)",
+                     sizeof(real) == 4 ? "<float>" : "", tc.W, tc.C, tc.S, tc.T, tc.hot_lo, nrbins);
         else
-            snprintf(g_k1_last, sizeof g_k1_last, "k1_tile_kernel (%d warps x %d modes per lane, %d stages, %d tiles per row)", tc.W, tc.C, tc.S, tc.T);
+            snprintf(g_k1_last, sizeof g_k1_last, "k1_tile_kernel%s (%d warps x %d modes per lane, %d stages, %d tiles per row)",
+                     sizeof(real) == 4 ? "<float>" : "", tc.W, tc.C, tc.S, tc.T);
         *ctas_out = ctas;
         *stride_out = NV * nrbins;
         return KSN_OK;

@@ -277,6 +277,88 @@ k3_scale_tma_kernel(C2<real> *__restrict__ grid, int nrows, int rows_per_cta, in
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Float grids (opt-in, KSN_K3_F32_TMA=1: written after this round's GPU minutes were spent, not yet run on a B200).
+// A float row is (N/2+1)*8 bytes -- 8200 at PMGRID = 2048 -- so every other row starts 8 bytes off the 16-byte granule
+// bulk copies need.  The slab is therefore cut into FLAT chunks of an even number of modes (two whole rows where they
+// fit one CTA: 2050 modes = 16400 B at 2048, the double kernel's block size), ignoring row boundaries; a thread finds
+// row and z of its modes from the chunk's first mode.  Same three phases as above: bulk copy in, factors while it is in
+// flight, scale in shared memory, bulk store.  256 threads x 9 modes.
+constexpr int K3_FLAT_THREADS = 256;
+
+template <typename real>
+__global__ void __launch_bounds__(K3_FLAT_THREADS, 4)
+k3_scale_tma_flat_kernel(C2<real> *__restrict__ grid, long long total, int chunk, int N, long long plane0,
+                         const double *__restrict__ tab, const K3Params prm, const K3Greens gr)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bar;
+    C2<real> *buf = (C2<real> *) smem_raw;
+    const K3Seg *seg = (const K3Seg *) tab;
+    const unsigned short *cellv = (const unsigned short *) (seg + prm.n + 1);
+    const int L = N / 2 + 1;
+    const long long e0 = (long long) blockIdx.x * chunk;           // first mode of this CTA's chunk (slab-relative, even)
+    const int nel = (int) min((long long) chunk, total - e0);      // even: chunk and total are
+    const unsigned bytes = (unsigned) nel * (unsigned) sizeof(C2<real>);
+    C2<real> *base = grid + e0;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(buf)), "l"(base), "r"(bytes), "r"(smem_u32(&bar)) : "memory");
+    }
+    // (plane, row-in-plane, z) of the chunk's first mode
+    const long long r0 = e0 / L;
+    const int zb = (int) (e0 - r0 * L);
+    const long long pl0 = r0 / N;
+    const int j0 = (int) (r0 - pl0 * N);
+    double smth[K3_EPT];
+#pragma unroll
+    for (int k = 0; k < K3_EPT; k++) {
+        const int e = threadIdx.x + K3_FLAT_THREADS * k;
+        smth[k] = 1.0;
+        if (e < nel) {
+            int z = zb + e, j = j0;
+            long long gi = plane0 + pl0;
+            if (z >= L) {                                          // the chunk's second row (two-row chunks end here)
+                z -= L; j++;
+                if (z >= L) { const int q = z / L; z -= q * L; j += q; }
+            }
+            if (j >= N) { const int q = j / N; j -= q * N; gi += q; }
+            const int ki = gi <= N / 2 ? (int) gi : (int) (gi - N);
+            const int kj = j <= N / 2 ? j : j - N;
+            const int k2i = ki * ki + kj * kj + z * z;
+            if (k2i > 0) smth[k] = k3_factor<real>(k2i, seg, cellv, prm);     // F(0,0,0) keeps factor 1 ...
+            if (gr.on) smth[k] = k2i > 0 ? smth[k] * k3_greens(gr, k2i, k3_greens_row(gr, ki, kj), z) : 0.0;   // ... or is zeroed
+        }
+    }
+    __syncthreads();                       // the barrier was initialised before anyone polls it
+    {
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(&bar)) : "memory");
+    }
+#pragma unroll
+    for (int k = 0; k < K3_EPT; k++) {
+        const int e = threadIdx.x + K3_FLAT_THREADS * k;
+        if (e < nel) {
+            C2<real> v = buf[e];
+            v.re = (real) ((double) v.re * smth[k]);               // interface_gadget.c:185-186: fftw_real *= double
+            v.im = (real) ((double) v.im * smth[k]);
+            buf[e] = v;
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the bulk store
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(base), "r"(smem_u32(buf)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the read
+    }
+}
+
 static size_t k3_tab_doubles(int n, int cells) { return (size_t) 4 * (n + 1) + ((size_t) cells * sizeof(unsigned short) + 7) / 8; }
 static K3Params g_k3prm;
 
@@ -395,6 +477,27 @@ int k3_launch(void *dgrid, int real_bytes, int dims, long long plane0_global, lo
         c.launches++;
         KSN_CUDA(cudaGetLastError());
         return KSN_OK;
+    }
+    {
+        // float grids through bulk copies: opt-in until it has been through the GPU parity suite (see the kernel)
+        const long long total = (long long) nrows * L;
+        const char *f32tma = getenv("KSN_K3_F32_TMA");
+        if (real_bytes == 4 && f32tma && atoi(f32tma) > 0 && total % 2 == 0 && ((uintptr_t) dgrid & 15) == 0) {
+            const int capf = K3_FLAT_THREADS * K3_EPT, pair = 2 * L;
+            // whole row pairs (~16-18 KB of them) where a pair fits one CTA, else the largest even piece
+            const int chunk = pair <= capf ? pair * max(1, min(capf / pair, (int) (18432 / ((size_t) pair * 8)))) : (capf & ~1);
+            const long long nct = (total + chunk - 1) / chunk;
+            if (nct <= 0x7fffffffLL) {
+                const size_t smem = (size_t) chunk * 8 + 128;
+                auto kern = k3_scale_tma_flat_kernel<float>;
+                KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+                KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 58));
+                kern<<<(unsigned) nct, K3_FLAT_THREADS, smem, c.stream>>>((C2<float> *) dgrid, total, chunk, dims, plane0_global, c.d_k3tab, g_k3prm, gr);
+                c.launches++;
+                KSN_CUDA(cudaGetLastError());
+                return KSN_OK;
+            }
+        }
     }
     // one CTA per ~1024 modes: a single row for large grids, several short rows otherwise
     const int rows_per_cta = L >= K3_THREADS * U ? 1 : (K3_THREADS * U) / L;

@@ -1,0 +1,133 @@
+"""Opt-in float-grid kernels written after round 1's GPU minutes were spent (K3: KSN_K3_F32_TMA=1, flat bulk-copy chunks;
+K1: KSN_K1_F32_TILE=1, the tile kernel on float rows).  They have NOT run on a B200 yet, so these tests are skipped unless
+KSN_TEST_UNVERIFIED=1 (tools/gpu_round2_check.sh sets it); the default float path stays the verified one until then.
+Each test compares the opt-in kernel with the numpy restatement / the reference AND, bit for bit where the arithmetic is
+the same, with the default float kernel."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from tests import refs
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("KSN_TEST_UNVERIFIED") != "1", reason="opt-in kernels: set KSN_TEST_UNVERIFIED=1")]
+
+
+def _table(n, box, nk=40, seed=0):
+    rng = np.random.default_rng(seed)
+    kmin, kmax = 2 * np.pi / box, 2 * np.pi / box * np.sqrt(3) * n / 2
+    logkk = np.sort(np.log(kmin) + (np.log(kmax) - np.log(kmin)) * rng.random(nk))
+    return logkk, 0.01 + 0.1 * rng.random(nk), 0.8
+
+
+class _env:
+    def __init__(self, **kv):
+        self.kv = kv
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kv}
+        for k, v in self.kv.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("n,start,nslab", [(4, 0, 4), (6, 0, 6), (64, 0, 64), (64, 5, 17), (126, 120, 6), (256, 0, 256), (2048, 1000, 6), (4096, 3000, 2)])
+def test_k3_float_bulk_copy_kernel_equals_the_plain_float_kernel(gpu, n, start, nslab):
+    """Same factor arithmetic, same narrowing to float: the two kernels must agree bit for bit; and with numpy to the
+    float-grid tolerance."""
+    from kspace_neutrinos_b200 import capi
+    box = refs.BOX
+    rng = np.random.default_rng(n + start)
+    g = rng.standard_normal((nslab, n, n // 2 + 1, 2)).astype(np.float32)
+    logkk, ratio, norm = _table(n, box, nk=min(40, max(3, n // 2)))
+    outs = []
+    for knob in (None, "1"):
+        with _env(KSN_K3_F32_TMA=knob):
+            d = refs.DeviceBuffer(gpu, g)
+            capi.check(gpu.ksn_scale_modes(d.ptr, 4, n, start, nslab, box, refs.dptr(logkk), refs.dptr(ratio), len(logkk), norm))
+            outs.append(d.download(g))
+            d.free()
+    np.testing.assert_array_equal(outs[1], outs[0])
+    if n <= 256:
+        np.testing.assert_allclose(outs[1], refs.k3_numpy(g, start, box, logkk, ratio, norm), rtol=1e-5, atol=0)
+
+
+def test_k3_float_bulk_copy_kernel_with_the_greens_function(gpu):
+    from kspace_neutrinos_b200 import capi
+    n, box = 64, refs.BOX
+    asmth2 = (2 * np.pi * 1.25 / n) ** 2
+    g = refs.random_grid(n, seed=77, dtype=np.float32)
+    logkk, ratio, norm = _table(n, box)
+    thr = C.POINTER(C.c_uint)()
+    iw = capi.c_double_p()
+    assert gpu.ksn_bin_tables(n, n // 2, C.byref(thr), C.byref(iw)) == 0
+    outs = []
+    for knob in (None, "1"):
+        with _env(KSN_K3_F32_TMA=knob):
+            d = refs.DeviceBuffer(gpu, g)
+            capi.check(gpu.ksn_scale_modes_greens(d.ptr, 4, n, 0, n, box, refs.dptr(logkk), refs.dptr(ratio), len(logkk), norm, iw, asmth2))
+            outs.append(d.download(g))
+            d.free()
+    np.testing.assert_array_equal(outs[1], outs[0])
+    assert outs[1][0, 0, 0, 0] == 0 and outs[1][0, 0, 0, 1] == 0
+
+
+@pytest.mark.parametrize("n,nrbins", [(8, 4), (64, 32), (96, 48), (128, 64), (256, 128)])
+def test_k1_float_tile_kernel_matches_the_pair_kernel_and_the_reference(gpu, n, nrbins):
+    """K1 on float rows through the tile kernel: counts bit-exact, power within the north star's float-grid tolerance of
+    the reference's float build, and within 3e-6 of the default float kernel (the tile kernel does not reproduce the
+    reference's float roundings of the window product, the pair kernel does)."""
+    g = refs.random_grid(n, seed=n + 1, dtype=np.float32)
+    res = {}
+    for knob in (None, "1"):
+        with _env(KSN_K1_F32_TILE=knob):
+            d = refs.DeviceBuffer(gpu, g)
+            refs.total_powerspectrum(gpu, g, nrbins, fn="total_powerspectrum_f32", pointer=d.ptr)      # first sweep: geometry
+            res[knob] = refs.total_powerspectrum(gpu, g, nrbins, fn="total_powerspectrum_f32", pointer=d.ptr)
+            name = gpu.ksn_last_k1_kernel()
+            d.free()
+            if knob:
+                assert b"k1_tile_kernel" in name and b"float" in name, name
+    (n0, p0, c0, k0), (n1, p1, c1, k1) = res[None], res["1"]
+    assert n0 == n1 and np.array_equal(c0[:n0], c1[:n1])
+    np.testing.assert_array_equal(k1[:n1], k0[:n0])
+    np.testing.assert_allclose(p1[:n1], p0[:n0], rtol=3e-6)
+    ref = refs.ref_lib(False)
+    if ref is not None:
+        r_n, r_p, r_c, r_k = refs.total_powerspectrum(ref, g, nrbins)
+        assert r_n == n1 and np.array_equal(r_c[:r_n], c1[:n1])
+        np.testing.assert_allclose(p1[:n1], r_p[:r_n], rtol=1e-5)
+
+
+def test_k1_float_tile_kernel_on_odd_slab_offsets_and_thin_slabs(gpu):
+    """Odd rows of a float grid start 8 bytes off the bulk-copy granule (the kernel copies from one mode earlier): slabs
+    that start on any plane, one plane thin, at PMGRID 2048 and 4096 (bin window)."""
+    from tests.test_k1_gpu import _sums
+    for n, start, nslab in ((64, 3, 1), (64, 0, 64), (2048, 1029, 2), (4096, 3, 1)):
+        rng = np.random.default_rng(n)
+        sub = rng.standard_normal((nslab, n, n // 2 + 1, 2)).astype(np.float32)
+        nrbins = n // 2
+        out = {}
+        for knob in (None, "1"):
+            with _env(KSN_K1_F32_TILE=knob):
+                class G:                                    # _sums slices g[start:start+nslab] and reads g.shape[1], g.dtype
+                    shape = (start + nslab, n, n // 2 + 1, 2)
+                    dtype = sub.dtype
+
+                    def __getitem__(self, sl):
+                        return sub
+                _sums(gpu, G(), nrbins, start, nslab)       # first call per geometry
+                out[knob] = _sums(gpu, G(), nrbins, start, nslab)
+        assert np.array_equal(out[None][2], out["1"][2])
+        np.testing.assert_allclose(out["1"][0], out[None][0], rtol=3e-6)

@@ -14,14 +14,15 @@ from kspace_neutrinos_b200 import capi  # noqa: E402
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+    rb = int(sys.argv[3]) if len(sys.argv) > 3 else 8            # bytes per real: 8 (double grid) or 4 (float grid)
     L = capi.lib()
     capi.check(L.ksn_init(-1))
     L.ksn_set_quiet(1)
     nrbins = n // 2
     nel = n * n * (n // 2 + 1)
     ptr = C.c_void_p()
-    capi.check(L.ksn_device_malloc(C.byref(ptr), nel * 16))
-    capi.check(L.ksn_fill_synthetic_grid(ptr, 8, n, 0, n, 20261017, -1.0))
+    capi.check(L.ksn_device_malloc(C.byref(ptr), nel * 2 * rb))
+    capi.check(L.ksn_fill_synthetic_grid(ptr, rb, n, 0, n, 20261017, -1.0))
     thr = C.POINTER(C.c_uint)()
     iw = capi.c_double_p()
     L.ksn_bin_tables(n, nrbins, C.byref(thr), C.byref(iw))
@@ -34,17 +35,17 @@ def main():
     for label in ("K1 full (first call, geometry)", "K1 fast"):
         for r in range(reps if label == "K1 fast" else 1):
             L.ksn_timing_reset()
-            capi.check(L.ksn_powerspectrum_sums(ptr, 8, n, nrbins, 0, n, thr, iw, dp(power), dp(keff),
+            capi.check(L.ksn_powerspectrum_sums(ptr, rb, n, nrbins, 0, n, thr, iw, dp(power), dp(keff),
                                                 count.ctypes.data_as(capi.c_longlong_p), C.byref(m2)))
             L.ksn_timing_get(C.byref(t))
-            print(f"{label}: k1 {t.k1_ms:.3f} ms  reduce {t.k1_reduce_ms:.3f} ms  -> {nel * 16 / t.k1_ms / 1e6:.1f} GB/s", flush=True)
+            print(f"{label}: k1 {t.k1_ms:.3f} ms  reduce {t.k1_reduce_ms:.3f} ms  -> {nel * 2 * rb / t.k1_ms / 1e6:.1f} GB/s  [{L.ksn_last_k1_kernel().decode()}]", flush=True)
     logkk = np.log(np.geomspace(1.0, n * 0.86, nrbins) * 2 * np.pi / 512000.0)   # log-spaced knots like keff of log-k bins
     ratio = np.linspace(0.9, 0.1, nrbins)
     for r in range(reps):
         L.ksn_timing_reset()
-        capi.check(L.ksn_scale_modes(ptr, 8, n, 0, n, 512000.0, dp(logkk), dp(ratio), nrbins, 0.01))
+        capi.check(L.ksn_scale_modes(ptr, rb, n, 0, n, 512000.0, dp(logkk), dp(ratio), nrbins, 0.01))
         L.ksn_timing_get(C.byref(t))
-        print(f"K3: {t.k3_ms:.3f} ms -> {nel * 32 / t.k3_ms / 1e6:.1f} GB/s", flush=True)
+        print(f"K3: {t.k3_ms:.3f} ms -> {nel * 4 * rb / t.k3_ms / 1e6:.1f} GB/s", flush=True)
     print("sum count", count.sum(), n ** 3 - 1)
 
 

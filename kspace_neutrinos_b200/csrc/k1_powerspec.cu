@@ -921,17 +921,15 @@ static int k1_launch_t(const void *dgrid, int dims, int nrbins, long long plane0
         k1_tile_config(dims / 2 + 1, nrbins, c.smem_optin, c.num_sms, &tc, (int) (2 * sizeof(real)))) {
         int log2N = -1;
         if ((dims & (dims - 1)) == 0) { log2N = 0; while ((1 << log2N) < dims) log2N++; }
-        static double *d_cold = nullptr;          // per-warp bins below the window (bin window only)
-        static size_t cold_cap = 0;
-        if (tc.hot_lo) {
-            rc = ensure_device_buffer((void **) &d_cold, &cold_cap, (size_t) ctas * tc.W * tc.hot_lo * sizeof(double));
+        if (tc.hot_lo) {                          // per-warp bins below the window (bin window only)
+            rc = ensure_device_buffer((void **) &c.d_cold, &c.cold_cap, (size_t) ctas * tc.W * tc.hot_lo * sizeof(double));
             if (rc) return rc;
         }
         auto go = [&](auto kern) -> int {
             KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc.smem));
             kern<<<ctas, tc.W * 32, tc.smem, c.stream>>>((const Cplx<real> *) dgrid, nrows, dims, nrbins, plane0, binscale,
                                                          c.d_thr, c.d_iw, c.d_partial, accumulate ? 1 : 0, tc.C, tc.T, tc.S, tc.stage_bytes,
-                                                         g_k1_k2_single, log2N, tc.hot_lo, d_cold);
+                                                         g_k1_k2_single, log2N, tc.hot_lo, c.d_cold);
             return KSN_OK;
         };
         int rct;

@@ -364,7 +364,7 @@ void ksn_shutdown(void)
     k1_tables_invalidate();
     for (auto &kv : g_registered) cudaHostUnregister((void *) kv.first);
     g_registered.clear();
-    cudaFree(c.d_partial); cudaFree(c.d_red); cudaFreeHost(c.h_red); cudaFree(c.d_thr); cudaFree(c.d_iw);
+    cudaFree(c.d_partial); cudaFree(c.d_red); cudaFreeHost(c.h_red); cudaFree(c.d_thr); cudaFree(c.d_iw); cudaFree(c.d_cold);
     cudaFree(c.d_k3tab); cudaFreeHost(c.h_k3tab); cudaFree(c.d_gz); cudaFree(c.d_stage); cudaFree(c.d_bg);
     cudaFree(c.d_k2); cudaFreeHost(c.h_k2);
     free(c.geom.keff); free(c.geom.count);

@@ -38,6 +38,7 @@ struct Ctx {
     double *d_red = nullptr;     size_t red_cap = 0;       // power | mass2 | keff | count
     double *h_red = nullptr;     size_t h_red_cap = 0;     // pinned mirror of d_red
     unsigned int *d_thr = nullptr; double *d_iw = nullptr; size_t thr_cap = 0, iw_cap = 0;
+    double *d_cold = nullptr; size_t cold_cap = 0;         // per-warp bins below the bin window (k1_tile_kernel<.., true>)
     // geometry cache (global sums over all ranks)
     struct { bool valid = false; int dims = 0, nrbins = 0; long long startslab = 0, nslab = 0;
              unsigned long long epoch = 0; double *keff = nullptr; long long *count = nullptr; size_t cap = 0; } geom;

@@ -137,18 +137,20 @@ def test_set_kspace_vars(L):
     assert addr[3] == C.addressof(capi.kspace_params()) + capi.KspaceParams.TimeTransfer.offset
 
 
-@pytest.mark.parametrize("n,nrbins", [(4, 15), (16, 8), (64, 32), (128, 64), (256, 128), (96, 200), (192, 96)])
+@pytest.mark.parametrize("n,nrbins", [(4, 15), (16, 8), (64, 32), (128, 64), (256, 128), (96, 200), (192, 96), (5, 4), (9, 8), (15, 7), (33, 16)])
 def test_bin_thresholds_reproduce_reference_counts(L, n, nrbins):
     """The host-libm integer thresholds K1 searches on the device give exactly the reference's mode counts
     (checked with the oracle's K1 on a constant grid, whose counts are data independent, and -- where the reference
     sources are compiled here -- with the reference binary itself; 192 is a size where the corner mode's bin depends on
-    how the -ffast-math build evaluates floor(binsperunit*log(kk)))."""
+    how the -ffast-math build evaluates floor(binsperunit*log(kk))).  Odd sizes: the reference counts the z = dims/2 column
+    once although it has a distinct conjugate there (powerspectrum.c:70-78), so its counts sum to less than n^3 - 1; the
+    product follows it."""
     thr = C.POINTER(C.c_uint)()
     iw = capi.c_double_p()
     assert L.ksn_bin_tables(n, nrbins, C.byref(thr), C.byref(iw)) == 0
     t = np.array([thr[i] for i in range(nrbins)], dtype=np.int64)
     assert t[0] == 0 and np.all(np.diff(t) >= 0)
-    k = np.fft.fftfreq(n, 1.0 / n).astype(np.int64)
+    k = np.fft.fftfreq(n, 1.0 / n).round().astype(np.int64)
     kz = np.arange(n // 2 + 1)
     k2 = (k[:, None, None] ** 2 + k[None, :, None] ** 2 + kz[None, None, :] ** 2)
     mult = np.where((kz == 0) | (kz == n // 2), 1, 2)[None, None, :] * np.ones_like(k2)
@@ -160,7 +162,7 @@ def test_bin_thresholds_reproduce_reference_counts(L, n, nrbins):
     c = np.zeros(nrbins, dtype=np.int64)
     m2 = C.c_double()
     o.orc_powerspectrum_sums(n, g.ctypes.data_as(C.c_void_p), 1, nrbins, 0, n, refs.dptr(p), refs.dptr(kk), c.ctypes.data_as(capi.c_longlong_p), C.byref(m2))
-    assert np.array_equal(cnt, c) and c.sum() == n ** 3 - 1
+    assert np.array_equal(cnt, c) and (n % 2 or c.sum() == n ** 3 - 1)
     ref = refs.ref_lib(True)
     if ref is not None and n <= 192:
         r_n, _, r_c, _ = refs.total_powerspectrum(ref, g, nrbins)

@@ -2,7 +2,8 @@
 K1: KSN_K1_F32_TILE=1, the tile kernel on float rows).  They have NOT run on a B200 yet, so these tests are skipped unless
 KSN_TEST_UNVERIFIED=1 (tools/gpu_round2_check.sh sets it); the default float path stays the verified one until then.
 Each test compares the opt-in kernel with the numpy restatement / the reference AND, bit for bit where the arithmetic is
-the same, with the default float kernel."""
+the same, with the default float kernel.  Also here, for the same reason: odd PMGRID on the device (default kernels, a
+case the GPU suite did not cover in round 1)."""
 import ctypes as C
 import os
 
@@ -131,3 +132,26 @@ def test_k1_float_tile_kernel_on_odd_slab_offsets_and_thin_slabs(gpu):
                 out[knob] = _sums(gpu, G(), nrbins, start, nslab)
         assert np.array_equal(out[None][2], out["1"][2])
         np.testing.assert_allclose(out["1"][0], out[None][0], rtol=3e-6)
+
+
+@pytest.mark.parametrize("n,nrbins", [(5, 4), (9, 8), (15, 7), (33, 16)])
+def test_odd_pmgrid_double_matches_the_reference(gpu, n, nrbins):
+    """Odd PMGRID (legal, if unusual: the reference then counts the z = dims/2 column once, powerspectrum.c:70-78).  The
+    CPU side is pinned in tests/test_host_cpu.py; this is the device side, not yet run on a B200 -- hence in this file."""
+    ref = refs.ref_lib(True)
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    g = refs.random_grid(n, seed=n)
+    r_n, r_p, r_c, r_k = refs.total_powerspectrum(ref, g, nrbins)
+    d = refs.DeviceBuffer(gpu, g)
+    for sweep in ("first", "cached"):
+        m_n, m_p, m_c, m_k = refs.total_powerspectrum(gpu, g, nrbins, fn="total_powerspectrum_f64", pointer=d.ptr)
+        assert m_n == r_n and np.array_equal(m_c[:m_n], r_c[:r_n]), sweep
+        np.testing.assert_allclose(m_p[:m_n], r_p[:r_n], rtol=1e-10, atol=0, err_msg=sweep)
+        np.testing.assert_allclose(m_k[:m_n], r_k[:r_n], rtol=1e-10, atol=0, err_msg=sweep)
+    from kspace_neutrinos_b200 import capi
+    logkk, ratio, norm = _table(n, refs.BOX, nk=max(3, n // 2))
+    capi.check(gpu.ksn_scale_modes(d.ptr, 8, n, 0, n, refs.BOX, refs.dptr(logkk), refs.dptr(ratio), len(logkk), norm))
+    got = d.download(g)
+    d.free()
+    np.testing.assert_allclose(got, refs.k3_numpy(g, 0, refs.BOX, logkk, ratio, norm), rtol=1e-10, atol=0)

@@ -446,7 +446,13 @@ __device__ __forceinline__ double queue_get(unsigned addr)
 // lanes read their chunks `sh` modes into the stage, and the one or two foreign modes at the ends are either never read
 // or walked with weight 0 like everything past a row's end.  |F|^2 is formed in float as the reference's float build does
 // (powerspectrum.c:68 with fftw_real = float), the window stays the separable double one (float-grid tolerance 1e-5).
-template <typename real, int CT, bool WIN>
+// WIN == 2 (opt-in, KSN_K1_WIN=3: written after this round's GPU minutes were spent, not yet run on a B200): the same layout
+// as WIN == 1, but the choice between the two homes of a bin is made once per TILE instead of once per update.  A tile whose
+// first mode already lies in bin hot_lo or above (k^2 grows along z, so then all of it does) walks with shared-memory-only
+// bin accesses -- LDS/STS, no generic-address loads and no per-update branches, the instruction stream of the kernel
+// without a window; the few cold tiles (rows within ~60 grid units of the axis) take the general walk with the
+// two-homed accesses.  Same bins, same update order: bit-identical sums to WIN == 1.
+template <typename real, int CT, int WIN>
 __global__ void __launch_bounds__((CT == 5 || CT == 9 ? K1T_MAXW : 8) * 32, 1)
 k1_tile_kernel(const Cplx<real> *__restrict__ grid, int nrows, int N, int nrbins, long long plane0, float binscale,
                const unsigned *__restrict__ thr, const double *__restrict__ iw, double *__restrict__ partial, int accumulate,
@@ -518,10 +524,18 @@ k1_tile_kernel(const Cplx<real> *__restrict__ grid, int nrows, int N, int nrbins
     // tile k is issued together with the set-up arithmetic of tile k+1, so that the two latency chains overlap.
     int p_fbin = 0x7fffffff;               // previous tile's first-run bin / sum / row factor (none yet)
     double p_facc = 0.0, p_wxy = 0.0;
+    auto binp_hot = [&](int idx) -> double * { return mybins + (idx - hot_lo); };     // WIN == 2, hot tiles only
     auto merge_first_runs = [&]() {
         double v1[1] = { p_facc };
         const unsigned tails = segmented_sum<1>(p_fbin, v1, lane, le_mask);
-        if (((tails >> lane) & 1u) && p_fbin != 0x7fffffff) { double *bp = binp(p_fbin); *bp = fma(v1[0], p_wxy, *bp); }
+        if (((tails >> lane) & 1u) && p_fbin != 0x7fffffff) {
+            if constexpr (WIN == 2) {                   // typed accesses under a branch instead of a generic pointer
+                if (p_fbin >= hot_lo) { double *bp = mybins + (p_fbin - hot_lo); *bp = fma(v1[0], p_wxy, *bp); }
+                else { double *bp = mycold + p_fbin; *bp = fma(v1[0], p_wxy, *bp); }
+            } else {
+                double *bp = binp(p_fbin); *bp = fma(v1[0], p_wxy, *bp);
+            }
+        }
         __syncwarp();
     };
     double wreg[CT > 0 ? CT : 1];
@@ -568,7 +582,7 @@ k1_tile_kernel(const Cplx<real> *__restrict__ grid, int nrows, int N, int nrbins
         // than R-1 runs (so the thresholds it will meet sit in R-1 registers): the walk has no branch and no dependent
         // load; a closed run is pushed onto the lane's queue by one predicated store.  R = 4 for most tiles, 8 near the
         // k_x = k_y = 0 axis where bins are narrow along z.
-        auto fast_walk = [&](auto RT) {
+        auto fast_walk = [&](auto RT, auto bp_of) {
             constexpr int R = decltype(RT)::value;
             unsigned nx[R - 1];
             nx[0] = nxt;
@@ -621,24 +635,20 @@ k1_tile_kernel(const Cplx<real> *__restrict__ grid, int nrows, int N, int nrbins
             double g[R - 1], m[R - 1];
 #pragma unroll
             for (int i = 1; i < R; i++)
-                if (i <= closed) { g[i - 1] = queue_get(q0 + 256u * i); m[i - 1] = *binp(fbin + i); }
+                if (i <= closed) { g[i - 1] = queue_get(q0 + 256u * i); m[i - 1] = *bp_of(fbin + i); }
 #pragma unroll
             for (int i = 1; i < R; i++)
-                if (i <= closed) *binp(fbin + i) = fma(g[i - 1], wxy, m[i - 1]);
+                if (i <= closed) *bp_of(fbin + i) = fma(g[i - 1], wxy, m[i - 1]);
             facc = queue_get(q0);
         };
-        if (single && spread <= 3) {
-            fast_walk(std::integral_constant<int, 4>());
-        } else if (single && spread <= K1T_QRUNS - 1) {
-            fast_walk(std::integral_constant<int, K1T_QRUNS>());
-        } else {
-            // GENERAL tile (the low-k corner, where bins are narrower than a step in k^2): finished runs go straight to the bins
+        // GENERAL tile (the low-k corner, where bins are narrower than a step in k^2): finished runs go straight to the bins
+        auto general_walk = [&](auto bp_of) {
             facc = 0.0;
             auto step = [&](const Cplx<real> v, double w) {
                 double pp;
                 if constexpr (sizeof(real) == 8) pp = fma(v.im, v.im, v.re * v.re); else pp = (double) fmaf(v.im, v.im, v.re * v.re);
                 if (k2 >= nxt) {
-                    if (b == fbin) facc = acc; else { double *bp = binp(b); *bp = fma(acc, wxy, *bp); }
+                    if (b == fbin) facc = acc; else { double *bp = bp_of(b); *bp = fma(acc, wxy, *bp); }
                     acc = 0.0;
                     do { b++; nxt = thr_s[b + 1]; } while (k2 >= nxt);
                 }
@@ -649,9 +659,43 @@ k1_tile_kernel(const Cplx<real> *__restrict__ grid, int nrows, int N, int nrbins
             step(chunk[0], __ldg(wz) * worigin);
 #pragma unroll 1
             for (int e = 1; e < C; e++) step(chunk[e], __ldg(wz + e));
-            if (b == fbin) facc = acc; else { double *bp = binp(b); *bp = fma(acc, wxy, *bp); }
+            if (b == fbin) facc = acc; else { double *bp = bp_of(b); *bp = fma(acc, wxy, *bp); }
             __syncwarp();
             if (lane == 0 && ri < nrows) issue(ri, ti, s);
+        };
+        if constexpr (WIN == 2) {
+            if ((unsigned) c + (unsigned) z0 * (unsigned) z0 < thr_s[hot_lo]) general_walk(binp);     // cold tile: some bins live in the global array
+            else if (single && spread <= 3) fast_walk(std::integral_constant<int, 4>(), binp_hot);
+            else if (single && spread <= K1T_QRUNS - 1) fast_walk(std::integral_constant<int, K1T_QRUNS>(), binp_hot);
+            else general_walk(binp_hot);
+        } else {
+            if (single && spread <= 3) {
+                fast_walk(std::integral_constant<int, 4>(), binp);
+            } else if (single && spread <= K1T_QRUNS - 1) {
+                fast_walk(std::integral_constant<int, K1T_QRUNS>(), binp);
+            } else {
+                // (the general walk once more, in line: as a call of the lambda above it compiles to the same instructions
+                // in another register allocation, and these instantiations are the ones measured on the B200)
+                facc = 0.0;
+                auto step = [&](const Cplx<real> v, double w) {
+                    double pp;
+                    if constexpr (sizeof(real) == 8) pp = fma(v.im, v.im, v.re * v.re); else pp = (double) fmaf(v.im, v.im, v.re * v.re);
+                    if (k2 >= nxt) {
+                        if (b == fbin) facc = acc; else { double *bp = binp(b); *bp = fma(acc, wxy, *bp); }
+                        acc = 0.0;
+                        do { b++; nxt = thr_s[b + 1]; } while (k2 >= nxt);
+                    }
+                    acc = fma(pp, w, acc);
+                    k2 += dz;
+                    dz += 2u;
+                };
+                step(chunk[0], __ldg(wz) * worigin);
+#pragma unroll 1
+                for (int e = 1; e < C; e++) step(chunk[e], __ldg(wz + e));
+                if (b == fbin) facc = acc; else { double *bp = binp(b); *bp = fma(acc, wxy, *bp); }
+                __syncwarp();
+                if (lane == 0 && ri < nrows) issue(ri, ti, s);
+            }
         }
         __syncwarp();                                                  // every lane is done with the bins
         p_fbin = fbin; p_facc = facc; p_wxy = wxy;                     // merged at the top of the next tile
@@ -703,9 +747,11 @@ static bool k1_tile_config(int L, int nrbins, size_t budget, int ctas, K1TileCfg
     int fw = 0, fc = 0, fs = 0;
     const char *env = getenv("KSN_K1_TILE");
     if (env && sscanf(env, "%d,%d,%d", &fw, &fc, &fs) != 3) fw = 0;
-    // bin window: "0" off, "1" where all the bins do not fit for eight warps, "2" (tests) always, with a quarter of the bins
+    // bin window: "0" off, "1" where all the bins do not fit for eight warps, "2" (tests) always, with a quarter of the bins;
+    // "3" / "4": as "1" / "2" with the kernel that chooses a bin's home per tile (k1_tile_kernel<.., 2>, opt-in)
     const char *wenv = getenv("KSN_K1_WIN");
-    const int window = wenv ? atoi(wenv) : KSN_K1_WIN_DEFAULT;
+    const int wval = wenv ? atoi(wenv) : KSN_K1_WIN_DEFAULT;
+    const int window = wval == 3 ? 1 : wval == 4 ? 2 : wval;                  // 3 / 4: as 1 / 2, other kernel (k1_launch_t)
     for (int C = 1; C <= 65; C += 4)
         for (int W = 4; W <= k1_tile_max_warps(C); W++)
             for (int S = 1; S <= 4; S++) {
@@ -932,23 +978,26 @@ static int k1_launch_t(const void *dgrid, int dims, int nrbins, long long plane0
                                                          g_k1_k2_single, log2N, tc.hot_lo, c.d_cold);
             return KSN_OK;
         };
+        // KSN_K1_WIN=3: the bin window with the home of a bin chosen per tile (k1_tile_kernel<.., 2>; opt-in, see the kernel)
+        const char *wenv3 = getenv("KSN_K1_WIN");
+        const bool tile_choice = wenv3 && (atoi(wenv3) == 3 || atoi(wenv3) == 4);       // 4: with the forced window of the tests
         int rct;
         switch (tc.hot_lo ? -tc.C : tc.C) {
-        case 5: rct = go(k1_tile_kernel<real, 5, false>); break;
-        case 9: rct = go(k1_tile_kernel<real, 9, false>); break;
-        case 13: rct = go(k1_tile_kernel<real, 13, false>); break;
-        case 17: rct = go(k1_tile_kernel<real, 17, false>); break;
-        case -9: rct = go(k1_tile_kernel<real, 9, true>); break;
-        case -13: rct = go(k1_tile_kernel<real, 13, true>); break;
-        case -17: rct = go(k1_tile_kernel<real, 17, true>); break;
-        default: rct = go(k1_tile_kernel<real, 0, false>); break;
+        case 5: rct = go(k1_tile_kernel<real, 5, 0>); break;
+        case 9: rct = go(k1_tile_kernel<real, 9, 0>); break;
+        case 13: rct = go(k1_tile_kernel<real, 13, 0>); break;
+        case 17: rct = go(k1_tile_kernel<real, 17, 0>); break;
+        case -9: rct = tile_choice ? go(k1_tile_kernel<real, 9, 2>) : go(k1_tile_kernel<real, 9, 1>); break;
+        case -13: rct = tile_choice ? go(k1_tile_kernel<real, 13, 2>) : go(k1_tile_kernel<real, 13, 1>); break;
+        case -17: rct = tile_choice ? go(k1_tile_kernel<real, 17, 2>) : go(k1_tile_kernel<real, 17, 1>); break;
+        default: rct = go(k1_tile_kernel<real, 0, 0>); break;
         }
         if (rct) return rct;
         c.launches++;
         KSN_CUDA(cudaGetLastError());
         if (tc.hot_lo)
-            snprintf(g_k1_last, sizeof g_k1_last, "k1_tile_kernel%s (%d warps x %d modes per lane, %d stages, %d tiles per row, bins >= %d of %d in shared memory)",
-                     sizeof(real) == 4 ? "<float>" : "", tc.W, tc.C, tc.S, tc.T, tc.hot_lo, nrbins);
+            snprintf(g_k1_last, sizeof g_k1_last, "k1_tile_kernel%s (%d warps x %d modes per lane, %d stages, %d tiles per row, bins >= %d of %d in shared memory%s)",
+                     sizeof(real) == 4 ? "<float>" : "", tc.W, tc.C, tc.S, tc.T, tc.hot_lo, nrbins, tile_choice ? ", home chosen per tile" : "");
         else
             snprintf(g_k1_last, sizeof g_k1_last, "k1_tile_kernel%s (%d warps x %d modes per lane, %d stages, %d tiles per row)",
                      sizeof(real) == 4 ? "<float>" : "", tc.W, tc.C, tc.S, tc.T);

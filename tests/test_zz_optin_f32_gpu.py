@@ -1,5 +1,6 @@
-"""Opt-in float-grid kernels written after round 1's GPU minutes were spent (K3: KSN_K3_F32_TMA=1, flat bulk-copy chunks;
-K1: KSN_K1_F32_TILE=1, the tile kernel on float rows).  They have NOT run on a B200 yet, so these tests are skipped unless
+"""Opt-in kernels written after round 1's GPU minutes were spent (float grids -- K3: KSN_K3_F32_TMA=1, flat bulk-copy
+chunks; K1: KSN_K1_F32_TILE=1, the tile kernel on float rows; and the K1 bin window with a bin's home chosen per tile,
+KSN_K1_WIN=3).  They have NOT run on a B200 yet, so these tests are skipped unless
 KSN_TEST_UNVERIFIED=1 (tools/gpu_round2_check.sh sets it); the default float path stays the verified one until then.
 Each test compares the opt-in kernel with the numpy restatement / the reference AND, bit for bit where the arithmetic is
 the same, with the default float kernel.  Also here, for the same reason: odd PMGRID on the device (default kernels, a
@@ -155,3 +156,30 @@ def test_odd_pmgrid_double_matches_the_reference(gpu, n, nrbins):
     got = d.download(g)
     d.free()
     np.testing.assert_allclose(got, refs.k3_numpy(g, 0, refs.BOX, logkk, ratio, norm), rtol=1e-10, atol=0)
+
+
+@pytest.mark.parametrize("n,start,nslab", [(256, 0, 256), (256, 100, 7), (512, 0, 40), (4096, 0, 6), (4096, 2040, 12)])
+def test_k1_bin_window_with_the_home_chosen_per_tile_is_bit_identical(gpu, n, start, nslab):
+    """KSN_K1_WIN=3 / 4 (k1_tile_kernel<.., 2>): same bins, same update order as the window kernel that chooses per update
+    (KSN_K1_WIN=1 / 2, verified in round 1) -- the sums must be bit-identical.  Small grids force a quarter-size window
+    (values 2 / 4); slabs at 4096 include the one with the k_x = k_y = 0 axis, whose rows reach the cold bins."""
+    from kspace_neutrinos_b200 import capi
+    from tests.test_k1_gpu import _sums
+    nrbins = n // 2
+    ptr = C.c_void_p()
+    capi.check(gpu.ksn_device_malloc(C.byref(ptr), nslab * n * (n // 2 + 1) * 16))
+    capi.check(gpu.ksn_fill_synthetic_grid(ptr, 8, n, start, nslab, 13, -1.0))
+    shape = np.empty((nslab, n, 1, 1))
+    _sums(gpu, shape, nrbins, start, nslab, pointer=ptr)                 # geometry
+    per_update, per_tile = ("2", "4") if n < 4096 else ("1", "3")
+    with _env(KSN_K1_WIN=per_update):
+        a = _sums(gpu, shape, nrbins, start, nslab, pointer=ptr)
+        assert b"in shared memory" in gpu.ksn_last_k1_kernel() and b"per tile" not in gpu.ksn_last_k1_kernel()
+    with _env(KSN_K1_WIN=per_tile):
+        b = _sums(gpu, shape, nrbins, start, nslab, pointer=ptr)
+        assert b"home chosen per tile" in gpu.ksn_last_k1_kernel(), gpu.ksn_last_k1_kernel()
+        b2 = _sums(gpu, shape, nrbins, start, nslab, pointer=ptr)
+    gpu.ksn_device_free(ptr)
+    np.testing.assert_array_equal(b[0], a[0])
+    np.testing.assert_array_equal(b2[0], b[0])
+    assert np.array_equal(a[2], b[2]) and a[3] == b[3]

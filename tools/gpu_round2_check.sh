@@ -19,13 +19,16 @@ echo "suite exit $?" | tee -a $O/r2_pytest_gpu.log
 tail -n 4 $O/r2_pytest_gpu.log
 # 3b. float-grid kernels written after round 1's GPU minutes were spent (opt-in): parity tests, then timings at 2048^3
 #     (float grid = 34.4 GB): default float path, K3 through bulk copies, K1 through the tile kernel
-KSN_TEST_UNVERIFIED=1 timeout 300 python -m pytest tests/test_zz_optin_f32_gpu.py -q > $O/r2_optin_f32.log 2>&1
+KSN_TEST_UNVERIFIED=1 timeout 400 python -m pytest tests/test_zz_optin_f32_gpu.py -q > $O/r2_optin_f32.log 2>&1
 echo "opt-in float kernels exit $?" | tee -a $O/r2_optin_f32.log
 tail -n 3 $O/r2_optin_f32.log
 timeout 120 python tools/quick_bench.py 2048 5 4 > $O/r2_f32_default.log 2>&1
 KSN_K3_F32_TMA=1 KSN_K1_F32_TILE=1 timeout 120 python tools/quick_bench.py 2048 5 4 > $O/r2_f32_optin.log 2>&1
 grep -h "K1 fast\|K3" $O/r2_f32_default.log | tail -n 2
 grep -h "K1 fast\|K3" $O/r2_f32_optin.log | tail -n 2
+# 3c. K1 bin window at PMGRID 4096 (384-plane slab, 51.6 GB): home of a bin chosen per update (default) / per tile (opt-in)
+timeout 300 python tools/pm4096_probe.py 384 > $O/r2_pm4096_probe.log 2>&1
+grep -h "^K1" $O/r2_pm4096_probe.log | cut -c1-200
 # 4. compute-sanitizer over the kernels added after profiles/r1_sanitizer.txt was taken: K2 with bisections ahead of time,
 #    K1 bin window, K3 row pieces (small cases only: the tools slow kernels down 10-50x)
 CS=/usr/local/cuda/bin/compute-sanitizer

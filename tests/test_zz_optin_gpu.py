@@ -1,6 +1,6 @@
 """Opt-in kernels written after round 1's GPU minutes were spent (float grids -- K3: KSN_K3_F32_TMA=1, flat bulk-copy
-chunks; K1: KSN_K1_F32_TILE=1, the tile kernel on float rows; and the K1 bin window with a bin's home chosen per tile,
-KSN_K1_WIN=3).  They have NOT run on a B200 yet, so these tests are skipped unless
+chunks; K1: KSN_K1_F32_TILE=1, the tile kernel on float rows; the K1 bin window with a bin's home chosen per tile,
+KSN_K1_WIN=3; K2 with one k bin per thread-block cluster, KSN_K2_CLUSTER=2|3|4).  They have NOT run on a B200 yet, so these tests are skipped unless
 KSN_TEST_UNVERIFIED=1 (tools/gpu_round2_check.sh sets it); the default float path stays the verified one until then.
 Each test compares the opt-in kernel with the numpy restatement / the reference AND, bit for bit where the arithmetic is
 the same, with the default float kernel.  Also here, for the same reason: odd PMGRID on the device (default kernels, a
@@ -183,3 +183,33 @@ def test_k1_bin_window_with_the_home_chosen_per_tile_is_bit_identical(gpu, n, st
     np.testing.assert_array_equal(b[0], a[0])
     np.testing.assert_array_equal(b2[0], b[0])
     assert np.array_equal(a[2], b[2]) and a[3] == b[3]
+
+
+@pytest.mark.parametrize("hybrid", [True, False])
+@pytest.mark.parametrize("masses", [(0.1, 0.1, 0.1), (0.2, 0.1, 0.3)])
+def test_k2_one_bin_per_cluster_is_bit_identical(gpu, masses, hybrid):
+    """k2_delta_nu_cluster_kernel<M> (KSN_K2_CLUSTER=2|3|4): the M groups of a speculative pass are the M CTAs of a
+    thread-block cluster, the interval list sits in CTA 0's shared memory.  Same arithmetic and the same replay as the
+    one-CTA kernels, so delta_nu, the rule count and the table row count must equal the sequential kernel's bit for bit."""
+    from tests.test_k2_gpu import _benchmark_state
+    om = refs.make_omnu(gpu, masses)
+    if hybrid:
+        gpu.init_hybrid_nu(C.byref(om.hybnu), (C.c_double * 3)(*masses), 500.0, 2.99792458e10 / 1e5, 0.333, om.kBtnu)
+    refs.set_background(gpu, om)
+    runs = {}
+    for cl in (0, 2, 3, 4):
+        with _env(KSN_K2_SPEC="1", KSN_K2_CLUSTER=str(cl) if cl else None):
+            d, kk, dcdm, tr = _benchmark_state(gpu, om)
+            outs = []
+            for a in (0.981, 0.982, 0.9915):
+                g = np.zeros(len(kk))
+                gpu.get_delta_nu_update(C.byref(d), a, len(kk), refs.dptr(kk), refs.dptr(dcdm), refs.dptr(g), C.byref(tr))
+                outs.append((g.copy(), gpu.ksn_last_k2_max_passes(), gpu.ksn_last_k2_max_trips(), d.ia))
+            runs[cl] = outs
+    if hybrid:
+        assert max(p for _, p, _, _ in runs[0]) > 60
+    for cl in (2, 3, 4):
+        for (g1, p1, t1, ia1), (gm, pm, tm, iam) in zip(runs[0], runs[cl]):
+            assert ia1 == iam and p1 == pm, (cl, p1, pm)
+            assert np.array_equal(g1, gm), (cl, float(np.max(np.abs(gm / g1 - 1))))
+            assert tm <= t1                       # fewer passes through the integrand than sequential bisections

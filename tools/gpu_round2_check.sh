@@ -19,7 +19,7 @@ echo "suite exit $?" | tee -a $O/r2_pytest_gpu.log
 tail -n 4 $O/r2_pytest_gpu.log
 # 3b. float-grid kernels written after round 1's GPU minutes were spent (opt-in): parity tests, then timings at 2048^3
 #     (float grid = 34.4 GB): default float path, K3 through bulk copies, K1 through the tile kernel
-KSN_TEST_UNVERIFIED=1 timeout 400 python -m pytest tests/test_zz_optin_f32_gpu.py -q > $O/r2_optin_f32.log 2>&1
+KSN_TEST_UNVERIFIED=1 timeout 400 python -m pytest tests/test_zz_optin_gpu.py -q > $O/r2_optin_f32.log 2>&1
 echo "opt-in float kernels exit $?" | tee -a $O/r2_optin_f32.log
 tail -n 3 $O/r2_optin_f32.log
 timeout 120 python tools/quick_bench.py 2048 5 4 > $O/r2_f32_default.log 2>&1
@@ -29,6 +29,15 @@ grep -h "K1 fast\|K3" $O/r2_f32_optin.log | tail -n 2
 # 3c. K1 bin window at PMGRID 4096 (384-plane slab, 51.6 GB): home of a bin chosen per update (default) / per tile (opt-in)
 timeout 300 python tools/pm4096_probe.py 384 > $O/r2_pm4096_probe.log 2>&1
 grep -h "^K1" $O/r2_pm4096_probe.log | cut -c1-200
+# 3d. K2 with one k bin per cluster of M CTAs (opt-in): K2 phase per cluster size next to the one-CTA kernels
+: > $O/r2_k2_cluster.txt
+for cl in 0 2 3 4; do
+  for cfg in "788 1" "788 1 nondegenerate" "788 0"; do
+    echo "--- KSN_K2_CLUSTER=$cl  k2_bench.py $cfg" >> $O/r2_k2_cluster.txt
+    KSN_K2_CLUSTER=$cl timeout 120 python tools/k2_bench.py $cfg 2>&1 | tail -n 3 >> $O/r2_k2_cluster.txt
+  done
+done
+cat $O/r2_k2_cluster.txt
 # 4. compute-sanitizer over the kernels added after profiles/r1_sanitizer.txt was taken: K2 with bisections ahead of time,
 #    K1 bin window, K3 row pieces (small cases only: the tools slow kernels down 10-50x)
 CS=/usr/local/cuda/bin/compute-sanitizer
@@ -36,6 +45,6 @@ timeout 600 $CS --tool memcheck python -m pytest tests/test_k2_gpu.py -q -k "spe
 timeout 600 $CS --tool memcheck python -m pytest tests/test_k1_gpu.py -q -k "bin_window and 256" > $O/r2_memcheck_k1win.log 2>&1
 timeout 600 $CS --tool racecheck python -m pytest tests/test_k2_gpu.py -q -k "speculative and not True" > $O/r2_racecheck_k2spec.log 2>&1
 timeout 600 $CS --tool racecheck python -m pytest tests/test_k1_gpu.py -q -k "bin_window and 256-100" > $O/r2_racecheck_k1win.log 2>&1
-KSN_TEST_UNVERIFIED=1 timeout 600 $CS --tool memcheck python -m pytest tests/test_zz_optin_f32_gpu.py -q -k "not 2048 and not 4096" > $O/r2_memcheck_f32.log 2>&1
-KSN_TEST_UNVERIFIED=1 timeout 600 $CS --tool racecheck python -m pytest tests/test_zz_optin_f32_gpu.py -q -k "64 and not 2048 and not 4096" > $O/r2_racecheck_f32.log 2>&1
+KSN_TEST_UNVERIFIED=1 timeout 600 $CS --tool memcheck python -m pytest tests/test_zz_optin_gpu.py -q -k "not 2048 and not 4096" > $O/r2_memcheck_f32.log 2>&1
+KSN_TEST_UNVERIFIED=1 timeout 600 $CS --tool racecheck python -m pytest tests/test_zz_optin_gpu.py -q -k "64 and not 2048 and not 4096" > $O/r2_racecheck_f32.log 2>&1
 grep -h "ERROR SUMMARY\|RACECHECK SUMMARY\|passed\|failed" $O/r2_memcheck_*.log $O/r2_racecheck_*.log

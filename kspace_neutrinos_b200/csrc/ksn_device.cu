@@ -5,6 +5,7 @@
 #include "ksn_p2p.cuh"
 
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -137,9 +138,38 @@ int stage_plan(int real_bytes, int dims, long long nslab, StagePlan *plan)
 }
 
 // ---------------------------------------------------------------- timing
+// Every phase is also an NVTX range (host side, header-only NVTX 3: a few ns when no tool is attached), so that a
+// profiler can be told to look at one phase only (ncu --nvtx --nvtx-include "ksn/K3/").  Phases overlap (uploads run
+// beside K1), hence start/end ranges rather than push/pop.
+static const char *const kPhaseName[PH_COUNT] = { "K1", "K1 reduce", "collective", "K2", "K3", "H2D", "D2H" };
+static nvtxRangeId_t g_range[PH_COUNT];
+static bool g_range_open[PH_COUNT];
+static nvtxDomainHandle_t nvtx_domain()
+{
+    static nvtxDomainHandle_t d = nvtxDomainCreateA("ksn");
+    return d;
+}
+static void range_begin(Phase p)
+{
+    if (g_range_open[p]) nvtxDomainRangeEnd(nvtx_domain(), g_range[p]);
+    nvtxEventAttributes_t a = {};
+    a.version = NVTX_VERSION;
+    a.size = NVTX_EVENT_ATTRIB_STRUCT_SIZE;
+    a.messageType = NVTX_MESSAGE_TYPE_ASCII;
+    a.message.ascii = kPhaseName[p];
+    g_range[p] = nvtxDomainRangeStartEx(nvtx_domain(), &a);
+    g_range_open[p] = true;
+}
+static void range_end(Phase p)
+{
+    if (g_range_open[p]) nvtxDomainRangeEnd(nvtx_domain(), g_range[p]);
+    g_range_open[p] = false;
+}
+
 void phase_begin(Phase p)
 {
     Ctx &c = g_ctx;
+    range_begin(p);
     if (!c.timing) return;
     if (c.ev_used[p]) {   // fold the previous interval of this phase before reusing its events
         float ms = 0;
@@ -153,6 +183,7 @@ void phase_begin(Phase p)
 void phase_end(Phase p)
 {
     Ctx &c = g_ctx;
+    range_end(p);
     if (!c.timing) return;
     cudaEventRecord(c.ev[p][1], (p == PH_H2D || p == PH_D2H) ? c.copy_stream : c.stream);
     c.ev_used[p] = true;

@@ -161,6 +161,8 @@ int ksn_delta_nu_integrate(const ksn_delta_nu_args *args, double *out, unsigned 
  * CTA and `sms` SMs (host arithmetic only): warps per CTA, modes per lane, stages, tiles per row, first bin kept in shared
  * memory (0 = all).  Returns 0 when no tile shape fits. */
 int ksn_k1_tile_plan(int dims, int nrbins, size_t smem_budget, int sms, int *warps, int *chunk, int *stages, int *tiles_per_row, int *hot_lo);
+/* the same for a grid of real_bytes-wide reals (8: as above; 4: float rows, KSN_K1_F32_TILE) */
+int ksn_k1_tile_plan_ex(int dims, int nrbins, size_t smem_budget, int sms, int real_bytes, int *warps, int *chunk, int *stages, int *tiles_per_row, int *hot_lo);
 /* which K1 kernel (and tile configuration) the most recent power-spectrum sweep launched */
 const char *ksn_last_k1_kernel(void);
 /* integrand evaluations of the most recent ksn_delta_nu_integrate call (fslength table included) */

@@ -758,12 +758,12 @@ static bool k1_tile_config(int L, int nrbins, size_t budget, int ctas, K1TileCfg
                 if (fw ? (W != fw || C != fc || S != fs) : S < 2) continue;
                 int T, stage;
                 size_t smem = k1_tile_smem(L, nrbins, nrbins, W, C, S, &T, &stage, esz);
-                const bool compile_time = C == 5 || C == 9 || C == 13 || C == 17;
+                const bool compile_time = C == 5 || C == 9 || C == 13 || C == 17 || (esz == 8 && C == 33);   // 33: a whole 2048 float row is one tile
                 int hot_lo = 0;
                 if (smem > budget || window == 2) {
                     // bin window (k1_tile_kernel<CT, true>): only where all the bins fit for fewer than eight warps, only
                     // up to eight warps, and with at least a quarter of the bins (the upper e-fold and more) in shared memory
-                    if (!window || !compile_time || C < 9 || W > 8) continue;
+                    if (!window || !compile_time || C < 9 || C > 17 || W > 8) continue;
                     const size_t rest = k1_tile_smem(L, nrbins, 0, W, C, S, nullptr, nullptr, esz);
                     if (rest >= budget) continue;
                     int nhot = (int) ((budget - rest) / ((size_t) W * 8)) & ~31;
@@ -793,16 +793,22 @@ static bool k1_tile_config(int L, int nrbins, size_t budget, int ctas, K1TileCfg
 // memory per CTA and `sms` SMs -- pure host arithmetic (no device needed), exported so that the choice can be pinned by a
 // CPU test.  Returns 1 and fills warps / modes per lane / stages / tiles per row / first bin kept in shared memory
 // (0 = all of them), or 0 when no tile shape fits (the scan-based kernel runs then).
-extern "C" int ksn_k1_tile_plan(int dims, int nrbins, size_t smem_budget, int sms, int *warps, int *chunk, int *stages, int *tiles_per_row, int *hot_lo)
+extern "C" int ksn_k1_tile_plan_ex(int dims, int nrbins, size_t smem_budget, int sms, int real_bytes, int *warps, int *chunk, int *stages, int *tiles_per_row, int *hot_lo)
 {
     ksn::K1TileCfg tc;
-    if (dims < 2 || nrbins < 1 || !ksn::k1_tile_config(dims / 2 + 1, nrbins, smem_budget, sms, &tc)) return 0;
+    if (dims < 2 || nrbins < 1 || (real_bytes != 4 && real_bytes != 8) ||
+        !ksn::k1_tile_config(dims / 2 + 1, nrbins, smem_budget, sms, &tc, 2 * real_bytes)) return 0;
     if (warps) *warps = tc.W;
     if (chunk) *chunk = tc.C;
     if (stages) *stages = tc.S;
     if (tiles_per_row) *tiles_per_row = tc.T;
     if (hot_lo) *hot_lo = tc.hot_lo;
     return 1;
+}
+
+extern "C" int ksn_k1_tile_plan(int dims, int nrbins, size_t smem_budget, int sms, int *warps, int *chunk, int *stages, int *tiles_per_row, int *hot_lo)
+{
+    return ksn_k1_tile_plan_ex(dims, nrbins, smem_budget, sms, 8, warps, chunk, stages, tiles_per_row, hot_lo);
 }
 
 namespace ksn {
@@ -987,6 +993,10 @@ static int k1_launch_t(const void *dgrid, int dims, int nrbins, long long plane0
         case 9: rct = go(k1_tile_kernel<real, 9, 0>); break;
         case 13: rct = go(k1_tile_kernel<real, 13, 0>); break;
         case 17: rct = go(k1_tile_kernel<real, 17, 0>); break;
+        case 33:
+            if constexpr (sizeof(real) == 4) rct = go(k1_tile_kernel<real, 33, 0>);
+            else rct = go(k1_tile_kernel<real, 0, 0>);
+            break;
         case -9: rct = tile_choice ? go(k1_tile_kernel<real, 9, 2>) : go(k1_tile_kernel<real, 9, 1>); break;
         case -13: rct = tile_choice ? go(k1_tile_kernel<real, 13, 2>) : go(k1_tile_kernel<real, 13, 1>); break;
         case -17: rct = tile_choice ? go(k1_tile_kernel<real, 17, 2>) : go(k1_tile_kernel<real, 17, 1>); break;

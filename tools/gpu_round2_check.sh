@@ -27,7 +27,7 @@ KSN_K3_F32_TMA=1 KSN_K1_F32_TILE=1 timeout 120 python tools/quick_bench.py 2048 
 grep -h "K1 fast\|K3" $O/r2_f32_default.log | tail -n 2
 grep -h "K1 fast\|K3" $O/r2_f32_optin.log | tail -n 2
 # tile shapes for float rows at 2048^3: the model's choice (15 warps x 9), the double grid's shape, a whole row as one tile
-for shape in "8,17,2" "8,33,2" "8,33,3" "12,13,2"; do
+for shape in "8,17,2" "8,33,2" "8,33,3" "12,9,3"; do
   KSN_K1_TILE=$shape KSN_K3_F32_TMA=1 KSN_K1_F32_TILE=1 timeout 120 python tools/quick_bench.py 2048 4 4 2>&1 | grep "K1 fast" | tail -n 1 | cut -c1-200
 done
 # 3c. K1 bin window at PMGRID 4096 (384-plane slab, 51.6 GB): home of a bin chosen per update (default) / per tile (opt-in)

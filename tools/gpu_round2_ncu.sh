@@ -13,7 +13,9 @@ KSN_K1_F32_TILE=1 KSN_K3_F32_TMA=1 timeout 300 $NCU -k regex:k3_scale_tma_flat -
 timeout 300 $NCU -k regex:k1_pair_kernel -s 2 -c 1 -o $O/r2_k1_pair_f32_1024 python tools/quick_bench.py 1024 3 4 > $O/r2_ncu_k1_pair_f32.log 2>&1
 timeout 300 $NCU -k regex:k3_scale_kernel -s 1 -c 1 -o $O/r2_k3_plain_f32_1024 python tools/quick_bench.py 1024 3 4 > $O/r2_ncu_k3_plain_f32.log 2>&1
 # PMGRID 4096, 96-plane slab (12.9 GB): the bin window with a bin's home chosen per update / per tile
-KSN_NCU_WIN=1 timeout 400 $NCU -k regex:k1_tile_kernel -s 6 -c 1 -o $O/r2_k1_win1_4096 python tools/pm4096_probe.py 96 > $O/r2_ncu_k1_win1.log 2>&1
+# (the probe launches the tile kernel 4 times to warm up, then 6 times each with KSN_K1_WIN = 0, 1, 3)
+timeout 400 $NCU -k regex:k1_tile_kernel -s 10 -c 1 -o $O/r2_k1_win1_4096 python tools/pm4096_probe.py 96 > $O/r2_ncu_k1_win1.log 2>&1
+timeout 400 $NCU -k regex:k1_tile_kernel -s 16 -c 1 -o $O/r2_k1_win3_4096 python tools/pm4096_probe.py 96 > $O/r2_ncu_k1_win3.log 2>&1
 # K2 at the benchmark's shape: the width-3 one-CTA kernel and the cluster kernel
 timeout 240 $NCU -k regex:k2_delta_nu -s 2 -c 1 -o $O/r2_k2_spec3 python tools/k2_bench.py 788 1 > $O/r2_ncu_k2_spec.log 2>&1
 KSN_K2_CLUSTER=3 timeout 240 $NCU -k regex:k2_delta_nu_cluster -s 2 -c 1 -o $O/r2_k2_cluster3 python tools/k2_bench.py 788 1 > $O/r2_ncu_k2_cluster.log 2>&1

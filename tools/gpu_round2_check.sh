@@ -42,3 +42,7 @@ for cl in 0 2 3 4; do
   done
 done
 cat $O/r2_k2_cluster.txt
+# 3e. K1 / K3 alone at the smaller BASELINE grids (configs[1], [2]): GB/s per kernel, double grids
+for n in 256 512 1024; do
+  timeout 120 python tools/quick_bench.py $n 5 8 2>&1 | grep "K1 fast\|^K3" | tail -n 2 | sed "s/^/PMGRID $n: /" | cut -c1-200
+done | tee $O/r2_small_grids.txt

@@ -284,10 +284,13 @@ k3_scale_tma_kernel(C2<real> *__restrict__ grid, int nrows, int rows_per_cta, in
 // fit one CTA: 2050 modes = 16400 B at 2048, the double kernel's block size), ignoring row boundaries; a thread finds
 // row and z of its modes from the chunk's first mode.  Same three phases as above: bulk copy in, factors while it is in
 // flight, scale in shared memory, bulk store.  256 threads x 9 modes.
+// The same kernel serves double grids whose rows are short enough for several to share a CTA (PMGRID <= 1150, opt-in
+// KSN_K3_FLAT=1, 128 threads): k3_scale_tma_kernel<double, false, false> divides by the row length for every mode, this one
+// once per thread.
 constexpr int K3_FLAT_THREADS = 256;
 
-template <typename real>
-__global__ void __launch_bounds__(K3_FLAT_THREADS, 4)
+template <typename real, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 k3_scale_tma_flat_kernel(C2<real> *__restrict__ grid, long long total, int chunk, int N, long long plane0,
                          const double *__restrict__ tab, const K3Params prm, const K3Greens gr)
 {
@@ -316,7 +319,7 @@ k3_scale_tma_flat_kernel(C2<real> *__restrict__ grid, long long total, int chunk
     double smth[K3_EPT];
 #pragma unroll
     for (int k = 0; k < K3_EPT; k++) {
-        const int e = threadIdx.x + K3_FLAT_THREADS * k;
+        const int e = threadIdx.x + THREADS * k;
         smth[k] = 1.0;
         if (e < nel) {
             int z = zb + e, j = j0;
@@ -342,7 +345,7 @@ k3_scale_tma_flat_kernel(C2<real> *__restrict__ grid, long long total, int chunk
     }
 #pragma unroll
     for (int k = 0; k < K3_EPT; k++) {
-        const int e = threadIdx.x + K3_FLAT_THREADS * k;
+        const int e = threadIdx.x + THREADS * k;
         if (e < nel) {
             C2<real> v = buf[e];
             v.re = (real) ((double) v.re * smth[k]);               // interface_gadget.c:185-186: fftw_real *= double
@@ -471,6 +474,17 @@ int k3_launch(void *dgrid, int real_bytes, int dims, long long plane0_global, lo
             kern<<<nct, K3_TMA_THREADS, smem, c.stream>>>((C2<double> *) dgrid, nrows, rpc, dims, plane0_global, c.d_k3tab, g_k3prm, gr, segs, seg_len);
             return KSN_OK;
         };
+        const char *flat = getenv("KSN_K3_FLAT");
+        if (segs == 1 && rpc > 1 && flat && atoi(flat) > 0 && ((uintptr_t) dgrid & 15) == 0) {
+            // several short rows per CTA: the flat-chunk kernel (opt-in until GPU-verified), same bytes per CTA
+            auto kern = k3_scale_tma_flat_kernel<double, K3_TMA_THREADS>;
+            KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 58));
+            kern<<<nct, K3_TMA_THREADS, smem, c.stream>>>((C2<double> *) dgrid, (long long) nrows * L, rpc * L, dims, plane0_global, c.d_k3tab, g_k3prm, gr);
+            c.launches++;
+            KSN_CUDA(cudaGetLastError());
+            return KSN_OK;
+        }
         const int rcl = segs > 1 ? go(k3_scale_tma_kernel<double, true, true>)
                       : rpc == 1 ? go(k3_scale_tma_kernel<double, true, false>) : go(k3_scale_tma_kernel<double, false, false>);
         if (rcl) return rcl;
@@ -489,7 +503,7 @@ int k3_launch(void *dgrid, int real_bytes, int dims, long long plane0_global, lo
             const long long nct = (total + chunk - 1) / chunk;
             if (nct <= 0x7fffffffLL) {
                 const size_t smem = (size_t) chunk * 8 + 128;
-                auto kern = k3_scale_tma_flat_kernel<float>;
+                auto kern = k3_scale_tma_flat_kernel<float, K3_FLAT_THREADS>;
                 KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
                 KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 58));
                 kern<<<(unsigned) nct, K3_FLAT_THREADS, smem, c.stream>>>((C2<float> *) dgrid, total, chunk, dims, plane0_global, c.d_k3tab, g_k3prm, gr);

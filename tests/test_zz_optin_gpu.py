@@ -213,3 +213,32 @@ def test_k2_one_bin_per_cluster_is_bit_identical(gpu, masses, hybrid):
             assert ia1 == iam and p1 == pm, (cl, p1, pm)
             assert np.array_equal(g1, gm), (cl, float(np.max(np.abs(gm / g1 - 1))))
             assert tm <= t1                       # fewer passes through the integrand than sequential bisections
+
+
+@pytest.mark.parametrize("n,start,nslab,greens", [(4, 0, 4, False), (64, 0, 64, False), (64, 7, 9, True), (96, 0, 96, False), (256, 0, 256, True),
+                                                   (1024, 500, 8, False), (1024, 0, 3, True)])
+def test_k3_flat_chunk_kernel_on_double_grids_with_short_rows_is_bit_identical(gpu, n, start, nslab, greens):
+    """KSN_K3_FLAT=1: where several rows share a CTA (PMGRID <= 1150) the flat-chunk kernel finds row and z of a mode
+    without a division per mode.  Same factor arithmetic as k3_scale_tma_kernel<double, false, false>: bit-identical."""
+    from kspace_neutrinos_b200 import capi
+    box = refs.BOX
+    rng = np.random.default_rng(3 * n + start)
+    g = rng.standard_normal((nslab, n, n // 2 + 1, 2))
+    logkk, ratio, norm = _table(n, box, nk=min(40, max(3, n // 2)))
+    thr = C.POINTER(C.c_uint)()
+    iw = capi.c_double_p()
+    assert gpu.ksn_bin_tables(n, n // 2, C.byref(thr), C.byref(iw)) == 0
+    asmth2 = (2 * np.pi * 1.25 / n) ** 2
+    outs = []
+    for knob in (None, "1"):
+        with _env(KSN_K3_FLAT=knob):
+            d = refs.DeviceBuffer(gpu, g)
+            if greens:
+                capi.check(gpu.ksn_scale_modes_greens(d.ptr, 8, n, start, nslab, box, refs.dptr(logkk), refs.dptr(ratio), len(logkk), norm, iw, asmth2))
+            else:
+                capi.check(gpu.ksn_scale_modes(d.ptr, 8, n, start, nslab, box, refs.dptr(logkk), refs.dptr(ratio), len(logkk), norm))
+            outs.append(d.download(g))
+            d.free()
+    np.testing.assert_array_equal(outs[1], outs[0])
+    if not greens and n <= 256:
+        np.testing.assert_allclose(outs[1], refs.k3_numpy(g, start, box, logkk, ratio, norm), rtol=1e-10, atol=0)

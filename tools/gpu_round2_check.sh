@@ -46,3 +46,7 @@ cat $O/r2_k2_cluster.txt
 for n in 256 512 1024; do
   timeout 120 python tools/quick_bench.py $n 5 8 2>&1 | grep "K1 fast\|^K3" | tail -n 2 | sed "s/^/PMGRID $n: /" | cut -c1-200
 done | tee $O/r2_small_grids.txt
+# 3f. K3 with several short rows per CTA (PMGRID <= 1150): the default kernel against the flat-chunk one (opt-in)
+for n in 512 1024; do
+  KSN_K3_FLAT=1 timeout 120 python tools/quick_bench.py $n 5 8 2>&1 | grep "^K3" | tail -n 1 | sed "s/^/PMGRID $n KSN_K3_FLAT=1: /" | cut -c1-200
+done | tee -a $O/r2_small_grids.txt

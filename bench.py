@@ -315,24 +315,43 @@ def ours(args):
             capi.check(L.ksn_memcpy_d2h(pin.ptr, grid.ptr, grid.nbytes))
         except capi.KsnError as exc:
             err = str(exc)
-        # page-locking tens of GB takes seconds and varies by rank; a rank that failed must not leave the others waiting
-        ok = torch.tensor([0.0 if err else 1.0], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if ok.item() < 1.0:
+        # page-locking tens of GB takes seconds and varies by rank; and whatever fails on one rank (allocation, a peer that
+        # never arrives) must not leave the others waiting in a collective: every rank takes the same sequence of
+        # torch.distributed calls, and the verdict after each step is shared
+        def everyone_ok(e):
+            ok = torch.tensor([0.0 if e else 1.0], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            return ok.item() >= 1.0
+
+        def host_step(a_now):
+            try:
+                sim.add_nu_power_to_rhogrid(a_now, pin.ptr, slab)
+                return None
+            except capi.KsnError as exc:
+                return str(exc)
+
+        if not everyone_ok(err):
             e2e = {"value": None, "unit": UNIT, "error": err or "another rank could not allocate its pinned host slab"}
         else:
-            try:
-                barrier()
-                a += da
-                sim.add_nu_power_to_rhogrid(a, pin.ptr, slab)          # warm-up (allocates the staging buffer)
+            barrier()
+            a += da
+            err = host_step(a)                                         # warm-up (allocates the staging buffer)
+            good = everyone_ok(err)
+            e_ms = 0.0
+            if good:
                 barrier()
                 te = time.perf_counter()
                 for _ in range(args.e2e_steps):
                     a += da
-                    sim.add_nu_power_to_rhogrid(a, pin.ptr, slab)
-                barrier()
-                e_ms = (time.perf_counter() - te) * 1e3
+                    err = host_step(a)
+                    good = everyone_ok(err)                            # (a few microseconds beside a step of seconds)
+                    if not good:
+                        break
+                if good:
+                    barrier()
+                    e_ms = (time.perf_counter() - te) * 1e3
+            if good:
                 te_t = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
                 if world > 1:
                     dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
@@ -340,8 +359,8 @@ def ours(args):
                 e2e = {"value": modes_total / (e_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": grid.nbytes * world,
                        "d2h_bytes_per_step": grid.nbytes * world, "ms_per_step": e_step, "steps": args.e2e_steps,
                        "note": "add_nu_power_to_rhogrid on pinned HOST slabs: upload, K1, K2, K3, download, every step"}
-            except capi.KsnError as exc:
-                e2e = {"value": None, "unit": UNIT, "error": str(exc)}
+            else:
+                e2e = {"value": None, "unit": UNIT, "error": err or "the step failed on another rank"}
         if pin is not None:
             pin.free()
 

@@ -1,6 +1,7 @@
 """Opt-in kernels written after round 1's GPU minutes were spent (float grids -- K3: KSN_K3_F32_TMA=1, flat bulk-copy
 chunks; K1: KSN_K1_F32_TILE=1, the tile kernel on float rows; the K1 bin window with a bin's home chosen per tile,
-KSN_K1_WIN=3; K2 with one k bin per thread-block cluster, KSN_K2_CLUSTER=2|3|4).  They have NOT run on a B200 yet, so these tests are skipped unless
+KSN_K1_WIN=3; K2 with one k bin per thread-block cluster, KSN_K2_CLUSTER=2|3|4; K3's flat-chunk kernel on double grids,
+KSN_K3_FLAT=1; the collective bootstrap of the -DKSN_HAVE_MPI host layer on two GPUs).  They have NOT run on a B200 yet, so these tests are skipped unless
 KSN_TEST_UNVERIFIED=1 (tools/gpu_round2_check.sh sets it); the default float path stays the verified one until then.
 Each test compares the opt-in kernel with the numpy restatement / the reference AND, bit for bit where the arithmetic is
 the same, with the default float kernel.  Also here, for the same reason: odd PMGRID on the device (default kernels, a
@@ -242,3 +243,41 @@ def test_k3_flat_chunk_kernel_on_double_grids_with_short_rows_is_bit_identical(g
     np.testing.assert_array_equal(outs[1], outs[0])
     if not greens and n <= 256:
         np.testing.assert_allclose(outs[1], refs.k3_numpy(g, start, box, logkk, ratio, norm), rtol=1e-10, atol=0)
+
+
+@pytest.mark.parametrize("comm", ["p2p", "nccl", "mpi"])
+def test_mpi_build_picks_its_collective_on_two_gpus(gpu, comm, tmp_path):
+    """The -DKSN_HAVE_MPI host layer chooses the collective for the bin sums on the communicator it is handed
+    (src/iface_common.c: bind_comm): two ranks of the fork-based mini-MPI (test infrastructure), one GPU each, linked to
+    the REAL device library, take PM steps on x-slabs with each starting point of the list (KSN_COMM) and must reproduce
+    the one-rank run."""
+    import glob
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    PKG = os.path.join(ROOT, "kspace_neutrinos_b200")
+    exe = str(tmp_path / "mpi_host_step_gpu")
+    srcs = sorted(glob.glob(os.path.join(PKG, "src", "*.c")))
+    cmd = ["gcc", "-O2", "-g", "-Wall", "-DKSN_HAVE_MPI", "-DDOUBLEPRECISION_FFTW",
+           "-I", os.path.join(ROOT, "oracle", "shim"), "-I", os.path.join(ROOT, "oracle"), "-I", os.path.join(ROOT, "include"),
+           "-I", os.path.join(PKG, "src"), os.path.join(ROOT, "tests", "mpi_host_step.c"), *srcs, os.path.join(ROOT, "oracle", "mini_mpi.c"),
+           "-L", PKG, "-lkspace_neutrinos_b200", f"-Wl,-rpath,{PKG}", "-lm", "-lpthread", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    env = {k: v for k, v in os.environ.items() if k not in ("LOCAL_RANK", "KSN_DEVICE", "RANK", "WORLD_SIZE")}
+    res = {}
+    for ranks in (1, 2):
+        out = str(tmp_path / f"out{ranks}.bin")
+        r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "ics_transfer_99.dat"), str(ranks), out], capture_output=True, text=True,
+                           timeout=300, env={**env, "KSN_COMM": comm})
+        assert r.returncode == 0 and "MPI HOST STEP OK" in r.stdout, r.stdout[-1500:] + r.stderr[-2500:]
+        if ranks == 2:
+            assert "BACKEND 102" in r.stdout, r.stdout[-500:]
+        raw = open(out, "rb").read()
+        n, nk, ia = np.frombuffer(raw[:12], dtype=np.int32)
+        res[ranks] = (int(nk), int(ia), np.frombuffer(raw[12:12 + 8 * nk], dtype=np.float64), np.frombuffer(raw[12 + 8 * nk:], dtype=np.float64))
+    assert res[1][:2] == res[2][:2]
+    np.testing.assert_allclose(res[2][2], res[1][2], rtol=1e-10)
+    np.testing.assert_allclose(res[2][3], res[1][3], rtol=1e-10)

@@ -1,6 +1,8 @@
 #!/bin/bash
 # One gpurun call for the start of the next round: everything written after round 1's GPU minutes were spent.
 #   gpurun --timeout 1500 -- 'bash tools/gpu_round2_check.sh'      (then tools/gpu_round2_sanitize.sh in a call of its own)
+# and, on two GPUs, the collective bootstrap of the -DKSN_HAVE_MPI build plus the e2e leg with the peer-memory backend:
+#   gpurun --gpus 2 --timeout 600 -- 'KSN_TEST_UNVERIFIED=1 python -m pytest tests/test_zz_optin_gpu.py -q -k mpi_build; python -m pytest tests/test_multi_gpu.py -q -m gpu; python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 10 --warmup 3 | tail -n 1 > gpurun_out/r2_bench_2gpu_e2e.json'
 mkdir -p gpurun_out
 O=gpurun_out
 # 1. the reference's own cmocka programs against the product on the GPU (tests/test_zz_reference_programs_gpu.py)

@@ -66,7 +66,7 @@ static int do_init(int device)
     cudaDeviceProp p;
     KSN_CUDA(cudaGetDeviceProperties(&p, device));
     if (p.major < 10)
-        return set_error(KSN_ENODEV, "device %d is sm_%d%d; this build carries sm_100a code only", device, p.major, p.minor);
+        return set_error(KSN_ENODEV, "device %d is sm_%d%d, this build carries sm_100a code only; this library has no CPU path", device, p.major, p.minor);
     c.device = device;
     c.num_sms = p.multiProcessorCount;
     c.smem_optin = p.sharedMemPerBlockOptin;

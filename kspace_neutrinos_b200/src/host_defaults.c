@@ -69,6 +69,6 @@ void ksn_fatal_device(int rc, const char *where)
     /* new codes beyond the reference's list: 3001 no device, 3002 CUDA/comm failure;
      * quadrature failures keep the reference's GSL-handler code 2001 (delta_tot_table.c:70-73) */
     if (rc == KSN_EQUAD) terminate(2001, "GSL_ERROR in %s: %s\n", where, ksn_last_error());
-    if (rc == KSN_ENODEV) terminate(3001, "%s: no usable B200 device (%s); this library has no CPU path\n", where, ksn_last_error());
+    if (rc == KSN_ENODEV) terminate(3001, "%s: no usable B200 device: %s\n", where, ksn_last_error());
     terminate(3002, "%s: device layer failed (%d): %s\n", where, rc, ksn_last_error());
 }

@@ -1,0 +1,94 @@
+"""Index arithmetic of the opt-in float-grid kernels, restated in Python and checked against direct enumeration (CPU, no
+GPU): the kernels themselves have not run on a B200 yet (tests/test_zz_optin_gpu.py does that), but the part of them that
+is pure integer logic -- which bytes a bulk copy covers, where a thread finds its mode -- can be pinned here.
+
+* k3_scale_tma_flat_kernel (csrc/k3_scale.cu): the slab is cut into flat chunks of an even mode count; a thread derives
+  (plane, row, z) of mode e of its chunk from the chunk's first mode.
+* k1_tile_kernel<float, ..> (csrc/k1_powerspec.cu): a tile of an odd float row starts 8 bytes off the 16-byte granule of
+  cp.async.bulk; it is copied from one mode earlier and to an even mode count, and lane l reads its chunk `sh` modes into
+  the stage."""
+import pytest
+
+K3_EPT = 9
+
+
+def k3_flat_chunk(L, threads):
+    """k3_launch: whole row pairs (~16-18 KB of them) where a pair fits one CTA, else the largest even piece."""
+    capf, pair = threads * K3_EPT, 2 * L
+    if pair <= capf:
+        return pair * max(1, min(capf // pair, 18432 // (pair * 8)))
+    return capf & ~1
+
+
+@pytest.mark.parametrize("n", [4, 6, 8, 16, 30, 64, 126, 128, 254])
+@pytest.mark.parametrize("nplanes", [1, 2, 3])
+def test_k3_flat_chunks_cover_the_slab_and_find_every_mode(n, nplanes):
+    L, plane0 = n // 2 + 1, 5
+    total = nplanes * n * L
+    if total % 2:
+        pytest.skip("odd mode total: the host keeps the plain kernel")
+    chunk = k3_flat_chunk(L, 256)
+    assert chunk % 2 == 0 and chunk <= 256 * K3_EPT
+    nct = (total + chunk - 1) // chunk
+    seen = 0
+    for b in range(nct):
+        e0 = b * chunk
+        nel = min(chunk, total - e0)
+        assert e0 % 2 == 0 and nel % 2 == 0                       # 16-byte aligned start, whole 16-byte granules
+        r0 = e0 // L
+        zb = e0 - r0 * L
+        pl0 = r0 // n
+        j0 = r0 - pl0 * n
+        for e in range(nel):                                      # the kernel's per-mode code
+            z, j, gi = zb + e, j0, plane0 + pl0
+            if z >= L:
+                z -= L
+                j += 1
+                if z >= L:
+                    q = z // L
+                    z -= q * L
+                    j += q
+            if j >= n:
+                q = j // n
+                j -= q * n
+                gi += q
+            g = e0 + e
+            row = g // L
+            assert (gi - plane0, j, z) == (row // n, row % n, g % L)
+            seen += 1
+    assert seen == total
+
+
+def test_k3_flat_chunk_sizes_at_the_named_grids():
+    assert k3_flat_chunk(1025, 256) == 2050          # PMGRID 2048 float: two whole rows, 16400 B (the double kernel's block)
+    assert k3_flat_chunk(2049, 256) == 2304          # PMGRID 4096 float: pieces that ignore row boundaries
+    assert k3_flat_chunk(513, 256) == 2052           # PMGRID 1024 float: four rows
+
+
+@pytest.mark.parametrize("n,C", [(4, 1), (8, 1), (16, 1), (64, 5), (64, 9), (96, 5), (128, 9), (256, 13), (256, 17), (126, 5), (2048, 33)])
+def test_k1_float_tile_copies_are_aligned_in_bounds_and_indexed_right(n, C):
+    L = n // 2 + 1
+    TE = 32 * C
+    T = (L + TE - 1) // TE
+    stage_elems = (((TE + 8) * 8 + 127) // 128 * 128) // 8       # k1_tile_smem with 8 bytes per mode
+    for nplanes in (1, 2):
+        nrows = nplanes * n
+        total = nrows * L
+        assert total % 2 == 0                                    # (even PMGRID; the host keeps the scan kernel otherwise)
+        rows = range(nrows) if n <= 256 else list(range(0, 9)) + list(range(nrows - 9, nrows))
+        for r in rows:
+            for t in range(T):
+                z0 = t * TE
+                ln = min(TE, L - z0)
+                g0 = r * L + z0
+                sh = g0 & 1
+                nel = (ln + sh + 1) & ~1
+                src = g0 - sh
+                assert src % 2 == 0 and src >= 0 and src + nel <= total and nel <= stage_elems
+                for lane in (0, 1, 15, 16, 31):
+                    for e in (0, C - 1):
+                        z = z0 + lane * C + e
+                        idx = sh + lane * C + e                   # where the lane reads
+                        assert idx < stage_elems
+                        if z < L:
+                            assert idx < nel and src + idx == r * L + z

@@ -122,6 +122,26 @@ __device__ __forceinline__ double k3_factor(int k2i, const K3Seg *__restrict__ s
     return fma(ab.y, lg, ab.x);
 }
 
+// The same factor for a FLOAT grid when KSN_K3_F32_TMA=2: the product is narrowed to float (2^-24), so the series may stop
+// at u^4 -- truncation u^5/5 <= 7e-9 of ln(1+u), which itself enters as the small correction B ln(k^2/K^2) to A ~ 1 --
+// and the factor costs 5 FP64 instructions less per mode (the float kernel has half the bytes per mode to hide them
+// behind).  Differs from k3_factor by far less than the float rounding of the result; opt-in.
+__device__ __forceinline__ double k3_factor_short(int k2i, const K3Seg *__restrict__ seg, const unsigned short *__restrict__ cellv, const K3Params &prm)
+{
+    const double k2 = (double) k2i;
+    int cell = (int) ((fast_log2((float) k2i) - prm.cell_lo) * prm.cell_scale);
+    cell = max(0, min(cell, prm.cells - 1));
+    int s = __ldg(cellv + cell);
+    s += (k2 >= __ldg(&seg[s + 1].K2));
+    const double2 ki = __ldg((const double2 *) &seg[s].K2);
+    const double2 ab = __ldg((const double2 *) &seg[s].A);
+    const double uu = fmax(fma(k2, ki.y, -1.0), 0.0);
+    double lg;
+    if (uu < 0.03125) lg = uu * (1.0 + uu * (-0.5 + uu * (1.0 / 3 + uu * (-0.25))));
+    else lg = log1p(uu);
+    return fma(ab.y, lg, ab.x);
+}
+
 // Sweep: SHORT-LIVED CTAs, one per block of `rows_per_cta` consecutive rows (one row of N/2+1 modes for large grids):
 // every thread issues all its loads up front, the CTA's accesses form one contiguous range, and the hardware block
 // scheduler balances the SMs.  Measured on this B200 (tools/bw_probe.cu) this pattern sustains 6.9 TB/s for an
@@ -289,7 +309,7 @@ k3_scale_tma_kernel(C2<real> *__restrict__ grid, int nrows, int rows_per_cta, in
 // once per thread.
 constexpr int K3_FLAT_THREADS = 256;
 
-template <typename real, int THREADS>
+template <typename real, int THREADS, bool SHORT = false>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 k3_scale_tma_flat_kernel(C2<real> *__restrict__ grid, long long total, int chunk, int N, long long plane0,
                          const double *__restrict__ tab, const K3Params prm, const K3Greens gr)
@@ -332,7 +352,7 @@ k3_scale_tma_flat_kernel(C2<real> *__restrict__ grid, long long total, int chunk
             const int ki = gi <= N / 2 ? (int) gi : (int) (gi - N);
             const int kj = j <= N / 2 ? j : j - N;
             const int k2i = ki * ki + kj * kj + z * z;
-            if (k2i > 0) smth[k] = k3_factor<real>(k2i, seg, cellv, prm);     // F(0,0,0) keeps factor 1 ...
+            if (k2i > 0) smth[k] = SHORT ? k3_factor_short(k2i, seg, cellv, prm) : k3_factor<real>(k2i, seg, cellv, prm);     // F(0,0,0) keeps factor 1 ...
             if (gr.on) smth[k] = k2i > 0 ? smth[k] * k3_greens(gr, k2i, k3_greens_row(gr, ki, kj), z) : 0.0;   // ... or is zeroed
         }
     }
@@ -503,7 +523,7 @@ int k3_launch(void *dgrid, int real_bytes, int dims, long long plane0_global, lo
             const long long nct = (total + chunk - 1) / chunk;
             if (nct <= 0x7fffffffLL) {
                 const size_t smem = (size_t) chunk * 8 + 128;
-                auto kern = k3_scale_tma_flat_kernel<float, K3_FLAT_THREADS>;
+                auto kern = atoi(f32tma) >= 2 ? k3_scale_tma_flat_kernel<float, K3_FLAT_THREADS, true> : k3_scale_tma_flat_kernel<float, K3_FLAT_THREADS, false>;
                 KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
                 KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 58));
                 kern<<<(unsigned) nct, K3_FLAT_THREADS, smem, c.stream>>>((C2<float> *) dgrid, total, chunk, dims, plane0_global, c.d_k3tab, g_k3prm, gr);

@@ -281,3 +281,24 @@ def test_mpi_build_picks_its_collective_on_two_gpus(gpu, comm, tmp_path):
     assert res[1][:2] == res[2][:2]
     np.testing.assert_allclose(res[2][2], res[1][2], rtol=1e-10)
     np.testing.assert_allclose(res[2][3], res[1][3], rtol=1e-10)
+
+
+@pytest.mark.parametrize("n,start,nslab", [(64, 0, 64), (256, 0, 256), (2048, 1000, 4)])
+def test_k3_float_short_series_factor_stays_within_one_float_rounding(gpu, n, start, nslab):
+    """KSN_K3_F32_TMA=2: ln(1+u) stops at u^4 for the narrow bins (truncation <= 7e-9 of a small correction term) -- the
+    factor then differs from the full one by far less than the float rounding of the product, so results agree with the
+    default float kernel to one float ulp, and mostly bit for bit."""
+    from kspace_neutrinos_b200 import capi
+    box = refs.BOX
+    rng = np.random.default_rng(n + 17)
+    g = rng.standard_normal((nslab, n, n // 2 + 1, 2)).astype(np.float32)
+    logkk, ratio, norm = _table(n, box, nk=min(40, max(3, n // 2)))
+    outs = []
+    for knob in (None, "2"):
+        with _env(KSN_K3_F32_TMA=knob):
+            d = refs.DeviceBuffer(gpu, g)
+            capi.check(gpu.ksn_scale_modes(d.ptr, 4, n, start, nslab, box, refs.dptr(logkk), refs.dptr(ratio), len(logkk), norm))
+            outs.append(d.download(g))
+            d.free()
+    np.testing.assert_allclose(outs[1], outs[0], rtol=1.3e-7, atol=0)
+    assert np.mean(outs[1] == outs[0]) > 0.99

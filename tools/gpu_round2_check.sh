@@ -55,3 +55,4 @@ done | tee -a $O/r2_small_grids.txt
 # 3g. the whole step on a float grid (Gadget-2's default build) at 2048^3: default float kernels / the opt-in bulk-copy ones
 timeout 200 python tools/step_bench.py 2048 4 10 2>&1 | tail -n 1 | cut -c1-400 | tee $O/r2_step_f32_default.txt
 KSN_K3_F32_TMA=1 KSN_K1_F32_TILE=1 timeout 200 python tools/step_bench.py 2048 4 10 2>&1 | tail -n 1 | cut -c1-400 | tee $O/r2_step_f32_optin.txt
+KSN_K3_F32_TMA=2 KSN_K1_F32_TILE=1 timeout 200 python tools/step_bench.py 2048 4 10 2>&1 | tail -n 1 | cut -c1-400 | tee $O/r2_step_f32_optin_short.txt

@@ -44,12 +44,21 @@ def parse_args():
     ap.add_argument("--no-greens", action="store_true", help="skip the fused Green's-function side measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-planes", type=int, default=0, help="planes per rank in the CPU sample (0 = auto)")
-    return ap.parse_args()
+    # the other BASELINE.json configs (parity-test cases, measured beside the headline): e.g. --pmgrid 4096 --mnu 0.2,0.1,0.3
+    # --no-hybrid for configs[4]; the CPU arm is fixed to the headline's neutrino set-up, so use --no-cpu-baseline with them
+    ap.add_argument("--mnu", default="0.1,0.1,0.1", help="the three neutrino masses in eV")
+    ap.add_argument("--no-hybrid", action="store_true", help="hybrid neutrinos off")
+    args = ap.parse_args()
+    args.mnu = tuple(float(x) for x in args.mnu.split(","))
+    if len(args.mnu) != 3:
+        ap.error("--mnu takes three masses")
+    return args
 
 
-def workload_config(n, gpus, extra=None):
-    cfg = {"workload": f"PMGRID={n}^3 double, x-slab sharded over {gpus} GPU(s), 3x0.1 eV, hybrid neutrinos on "
-                       f"(Vcrit=500, NuPartTime=0.333), 99-row delta_tot history (a=0.98+)",
+def workload_config(n, gpus, extra=None, mnu=(0.1, 0.1, 0.1), hybrid=True):
+    masses = "3x0.1 eV" if tuple(mnu) == (0.1, 0.1, 0.1) else "MNu = " + "/".join(f"{m:g}" for m in mnu) + " eV"
+    cfg = {"workload": f"PMGRID={n}^3 double, x-slab sharded over {gpus} GPU(s), {masses}, hybrid neutrinos "
+                       f"{'on (Vcrit=500, NuPartTime=0.333)' if hybrid else 'off'}, 99-row delta_tot history (a=0.98+)",
            "pmgrid": n, "stored_modes": n * n * (n // 2 + 1), "nrbins": n // 2,
            "parallelism": f"slab{gpus}", "l2": "grid (>= 8.6 GB per GPU) far exceeds the 126 MB L2; no flush needed"}
     if extra:
@@ -224,7 +233,7 @@ def ours(args):
     n = args.pmgrid
     slab = host.slab_partition(n, world)[rank]
     modes_total = n * n * (n // 2 + 1)
-    cosmo = host.Cosmology(transfer_file=TRANSFER, mnu=(0.1, 0.1, 0.1), hybrid_neutrinos_on=1)
+    cosmo = host.Cosmology(transfer_file=TRANSFER, mnu=args.mnu, hybrid_neutrinos_on=0 if args.no_hybrid else 1)
     sim = host.KspaceNeutrinos(cosmo, n, rank=rank)
     grid = host.DeviceGrid(n, slab)
     grid.fill_synthetic()
@@ -398,7 +407,7 @@ def ours(args):
                 "k2_kernel": f"speculation width {L.ksn_k2_spec_width() or 'by regime (hybrid, one species: 3)'}, slowest bin {L.ksn_last_k2_max_trips()} passes through the integrand"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(n, world, {"collective": comm_backend}), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "data": "synthetic", "config": workload_config(n, world, {"collective": comm_backend}, args.mnu, not args.no_hybrid), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "wall_ms_per_step": wall_ms / args.steps}
     if greens is not None:
         line["greens_fusion"] = greens

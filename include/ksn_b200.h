@@ -165,6 +165,8 @@ int ksn_k1_tile_plan(int dims, int nrbins, size_t smem_budget, int sms, int *war
 int ksn_k1_tile_plan_ex(int dims, int nrbins, size_t smem_budget, int sms, int real_bytes, int *warps, int *chunk, int *stages, int *tiles_per_row, int *hot_lo);
 /* which K1 kernel (and tile configuration) the most recent power-spectrum sweep launched */
 const char *ksn_last_k1_kernel(void);
+/* which K3 kernel the most recent scaling pass launched (template instance, rows per CTA / pieces per row) */
+const char *ksn_last_k3_kernel(void);
 /* integrand evaluations of the most recent ksn_delta_nu_integrate call (fslength table included) */
 unsigned long long ksn_last_k2_evals(void);
 /* largest number of 61-point rule applications any single k bin needed in that call (the kernel's critical path) */

@@ -1254,7 +1254,7 @@ extern "C" int ksn_powerspectrum_sums(const void *grid, int real_bytes, int dims
 {
     int rc = ensure_init();
     if (rc) return rc;
-    if ((!grid && nslab > 0) || (real_bytes != 4 && real_bytes != 8) || dims < 2 || (dims & 1) || nrbins < 2 || nslab < 0 ||
+    if ((!grid && nslab > 0) || (real_bytes != 4 && real_bytes != 8) || dims < 2 || nrbins < 2 || nslab < 0 ||
         startslab < 0 || startslab + nslab > dims || !thresholds || !invwin || !power_sum || !keff_sum || !count || !total_mass2)
         return set_error(KSN_EINVAL, "ksn_powerspectrum_sums: bad arguments (dims=%d nrbins=%d slab=[%lld,+%lld))", dims, nrbins, startslab, nslab);
     if ((double) dims * dims * 0.75 > 2.0e9) return set_error(KSN_EINVAL, "dims=%d: k^2 does not fit 31 bits", dims);

@@ -20,6 +20,7 @@
 #include "ksn_internal.cuh"
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 namespace ksn {
@@ -436,6 +437,7 @@ int k3_upload_table(int dims, double boxsize, const double *logkk, const double 
 }
 
 static K3Greens g_k3greens = { 0, 0.0, nullptr, nullptr };
+static char g_k3_last[160] = "none";
 
 // Switch the fused Green's function on (invwin: host table iw[0..N/2], as K1 takes it) or off (invwin == nullptr).
 static int k3_set_greens(int dims, const double *invwin, double asmth2)
@@ -501,6 +503,7 @@ int k3_launch(void *dgrid, int real_bytes, int dims, long long plane0_global, lo
             KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
             KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 58));
             kern<<<nct, K3_TMA_THREADS, smem, c.stream>>>((C2<double> *) dgrid, (long long) nrows * L, rpc * L, dims, plane0_global, c.d_k3tab, g_k3prm, gr);
+            snprintf(g_k3_last, sizeof g_k3_last, "k3_scale_tma_flat_kernel<double> (%d modes per CTA%s)", rpc * L, gr.on ? ", Green's function fused" : "");
             c.launches++;
             KSN_CUDA(cudaGetLastError());
             return KSN_OK;
@@ -508,6 +511,8 @@ int k3_launch(void *dgrid, int real_bytes, int dims, long long plane0_global, lo
         const int rcl = segs > 1 ? go(k3_scale_tma_kernel<double, true, true>)
                       : rpc == 1 ? go(k3_scale_tma_kernel<double, true, false>) : go(k3_scale_tma_kernel<double, false, false>);
         if (rcl) return rcl;
+        snprintf(g_k3_last, sizeof g_k3_last, "k3_scale_tma_kernel<double, %s> (%d row%s per CTA, %d piece%s per row%s)", segs > 1 ? "true, true" : rpc == 1 ? "true, false" : "false, false",
+                 rpc, rpc > 1 ? "s" : "", segs, segs > 1 ? "s" : "", gr.on ? ", Green's function fused" : "");
         c.launches++;
         KSN_CUDA(cudaGetLastError());
         return KSN_OK;
@@ -527,6 +532,7 @@ int k3_launch(void *dgrid, int real_bytes, int dims, long long plane0_global, lo
                 KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
                 KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 58));
                 kern<<<(unsigned) nct, K3_FLAT_THREADS, smem, c.stream>>>((C2<float> *) dgrid, total, chunk, dims, plane0_global, c.d_k3tab, g_k3prm, gr);
+                snprintf(g_k3_last, sizeof g_k3_last, "k3_scale_tma_flat_kernel<float> (%d modes per CTA%s)", chunk, gr.on ? ", Green's function fused" : "");
                 c.launches++;
                 KSN_CUDA(cudaGetLastError());
                 return KSN_OK;
@@ -540,6 +546,7 @@ int k3_launch(void *dgrid, int real_bytes, int dims, long long plane0_global, lo
         k3_scale_kernel<double, U><<<ctas, K3_THREADS, 0, c.stream>>>((C2<double> *) dgrid, nrows, rows_per_cta, dims, plane0_global, c.d_k3tab, g_k3prm, gr);
     else
         k3_scale_kernel<float, U><<<ctas, K3_THREADS, 0, c.stream>>>((C2<float> *) dgrid, nrows, rows_per_cta, dims, plane0_global, c.d_k3tab, g_k3prm, gr);
+    snprintf(g_k3_last, sizeof g_k3_last, "k3_scale_kernel<%s> (plain loads, %d row%s per CTA%s)", real_bytes == 8 ? "double" : "float", rows_per_cta, rows_per_cta > 1 ? "s" : "", gr.on ? ", Green's function fused" : "");
     c.launches++;
     KSN_CUDA(cudaGetLastError());
     return KSN_OK;
@@ -608,6 +615,8 @@ int k1_sums(const void *dgrid, const void *hgrid, int real_bytes, int dims, int 
 
 using namespace ksn;
 
+extern "C" const char *ksn_last_k3_kernel(void) { return g_k3_last; }
+
 static int check_table(const double *logkk, const double *ratio, int nbins, double norm)
 {
     if (!logkk || !ratio || nbins < 2 || nbins > 65535) return set_error(KSN_EINVAL, "K3: bad table (nbins=%d)", nbins);
@@ -623,7 +632,7 @@ static int scale_modes_impl(void *grid, int real_bytes, int dims, long long star
 {
     int rc = ensure_init();
     if (rc) return rc;
-    if ((!grid && nslab > 0) || (real_bytes != 4 && real_bytes != 8) || dims < 2 || (dims & 1) || nslab < 0 || startslab < 0 ||
+    if ((!grid && nslab > 0) || (real_bytes != 4 && real_bytes != 8) || dims < 2 || nslab < 0 || startslab < 0 ||
         startslab + nslab > dims || !(boxsize > 0))
         return set_error(KSN_EINVAL, "ksn_scale_modes: bad arguments");
     rc = check_table(logkk, ratio, nbins, norm);
@@ -668,7 +677,7 @@ static int step_staged_impl(void *hgrid, int real_bytes, int dims, int nrbins, l
 {
     int rc = ensure_init();
     if (rc) return rc;
-    if ((!hgrid && nslab > 0) || !between || !thresholds || !invwin || (real_bytes != 4 && real_bytes != 8) || dims < 2 || (dims & 1) ||
+    if ((!hgrid && nslab > 0) || !between || !thresholds || !invwin || (real_bytes != 4 && real_bytes != 8) || dims < 2 ||
         nrbins < 2 || nslab < 0 || startslab < 0 || startslab + nslab > dims || !(boxsize > 0))
         return set_error(KSN_EINVAL, "ksn_step_staged: bad arguments");
     Ctx &c = ctx();

@@ -67,7 +67,7 @@ static void box_layout(MPI_Comm comm, int rank, int size, int *local_rank, int *
  *   nccl  ncclAllReduce on a communicator bootstrapped with MPI_Bcast of the unique id;
  *   mpi   the sums go to the host and through MPI_Allreduce, as the reference does.
  * A host that has already bound a backend itself (ksn_comm_*) is left alone. */
-static void bind_comm(MPI_Comm comm)
+void ksn_bind_comm(MPI_Comm comm)
 {
     int rank, size;
     the_comm = comm;
@@ -121,12 +121,12 @@ static void bind_comm(MPI_Comm comm)
     message(0, "kspace-neutrinos: bin sums are reduced with MPI_Allreduce on the host (%d ranks)\n", size);
 }
 #else
-static void bind_comm(MPI_Comm comm) { (void) comm; }
+void ksn_bind_comm(MPI_Comm comm) { (void) comm; }
 #endif
 
 void InitOmegaNu(const double HubbleParam, const double tcmb0, MPI_Comm MYMPI_COMM_WORLD)
 {
-    bind_comm(MYMPI_COMM_WORLD);
+    ksn_bind_comm(MYMPI_COMM_WORLD);
 #ifdef KSN_HAVE_MPI
     MPI_Bcast(&kspace_params, sizeof(kspace_params), MPI_BYTE, 0, MYMPI_COMM_WORLD);
 #endif
@@ -135,7 +135,7 @@ void InitOmegaNu(const double HubbleParam, const double tcmb0, MPI_Comm MYMPI_CO
 
 void allocate_kspace_memory(const int nk_in, const int ThisTask, const double BoxSize, const double UnitTime_in_s, const double UnitLength_in_cm, const double Omega0, char *snapdir, const double TimeMax, MPI_Comm MYMPI_COMM_WORLD)
 {
-    bind_comm(MYMPI_COMM_WORLD);
+    ksn_bind_comm(MYMPI_COMM_WORLD);
     /* vcrit is in km/s, so the speed of light goes in km/s as well */
     if (kspace_params.hybrid_neutrinos_on)
         init_hybrid_nu(&omeganu_table.hybnu, kspace_params.MNu, kspace_params.vcrit, LIGHTCGS / 1e5, kspace_params.nu_crit_time, omeganu_table.kBtnu);

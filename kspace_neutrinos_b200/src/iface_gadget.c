@@ -86,13 +86,13 @@ static void add_nu_power_any(int real_bytes, const double Time, const double Box
 
 void add_nu_power_to_rhogrid_f64(const double Time, const double BoxSize, void *grid, const int pmgrid, int slabstart_y, int nslab_y, MPI_Comm comm)
 {
-    (void) comm;
+    ksn_bind_comm(comm);
     add_nu_power_any(8, Time, BoxSize, grid, pmgrid, slabstart_y, nslab_y, -1.0);
 }
 
 void add_nu_power_to_rhogrid_f32(const double Time, const double BoxSize, void *grid, const int pmgrid, int slabstart_y, int nslab_y, MPI_Comm comm)
 {
-    (void) comm;
+    ksn_bind_comm(comm);
     add_nu_power_any(4, Time, BoxSize, grid, pmgrid, slabstart_y, nslab_y, -1.0);
 }
 
@@ -101,15 +101,15 @@ void add_nu_power_to_rhogrid_f32(const double Time, const double BoxSize, void *
  * (pm_periodic.c, the loop after the hook of gadget-2/0002 patch:116-125).  asmth2 = (2 pi Asmth / BoxSize)^2, as there. */
 void add_nu_power_and_greens_to_rhogrid_f64(const double Time, const double BoxSize, void *grid, const int pmgrid, int slabstart_y, int nslab_y, const double asmth2, MPI_Comm comm)
 {
-    (void) comm;
     if (!(asmth2 >= 0)) terminate(1, "add_nu_power_and_greens_to_rhogrid: asmth2 = %g\n", asmth2);
+    ksn_bind_comm(comm);
     add_nu_power_any(8, Time, BoxSize, grid, pmgrid, slabstart_y, nslab_y, asmth2);
 }
 
 void add_nu_power_and_greens_to_rhogrid_f32(const double Time, const double BoxSize, void *grid, const int pmgrid, int slabstart_y, int nslab_y, const double asmth2, MPI_Comm comm)
 {
-    (void) comm;
     if (!(asmth2 >= 0)) terminate(1, "add_nu_power_and_greens_to_rhogrid: asmth2 = %g\n", asmth2);
+    ksn_bind_comm(comm);
     add_nu_power_any(4, Time, BoxSize, grid, pmgrid, slabstart_y, nslab_y, asmth2);
 }
 

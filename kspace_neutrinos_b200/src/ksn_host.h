@@ -26,6 +26,13 @@ int ksn_bin_tables(int dims, int nrbins, const unsigned int **thresholds, const 
 void ksn_ensure_background(double a_lo, double a_hi);
 void ksn_invalidate_background(void);
 
+/* The collective for the bin sums on the communicator a reference-named entry was handed (-DKSN_HAVE_MPI: the first call
+ * with more than one rank picks the backend collectively, later calls return at once; without MPI the handle is an int and
+ * the host binds a backend through ksn_comm_* itself).  Every entry that ends in the reference's MPI_Allreduce calls
+ * (powerspectrum.c:91-95) calls it, so that a host which never goes through InitOmegaNu -- gadget-2 patch 0004 with
+ * KSPACE_NEUTRINOS_2 off: pmforce_periodic -> compute_total_power_spectrum -- still gets global sums. */
+void ksn_bind_comm(MPI_Comm comm);
+
 /* glue used by both interface files */
 _delta_pow compute_neutrino_power_internal(const double Time, double *keff, double *delta_cdm_curr, double *delta_nu_curr, const int nk_nonzero);
 int ksn_finish_powerspectrum(int nrbins, double total_mass2, double *power, long long *count, double *keffs);

@@ -106,13 +106,13 @@ static int total_powerspectrum_any(int real_bytes, const int dims, void *outfiel
 
 int total_powerspectrum_f64(const int dims, void *outfield, const int nrbins, const int startslab, const int nslab, double *power, long long int *count, double *keffs, const MPI_Comm comm)
 {
-    (void) comm;
+    ksn_bind_comm(comm);
     return total_powerspectrum_any(8, dims, outfield, nrbins, startslab, nslab, power, count, keffs);
 }
 
 int total_powerspectrum_f32(const int dims, void *outfield, const int nrbins, const int startslab, const int nslab, double *power, long long int *count, double *keffs, const MPI_Comm comm)
 {
-    (void) comm;
+    ksn_bind_comm(comm);
     return total_powerspectrum_any(4, dims, outfield, nrbins, startslab, nslab, power, count, keffs);
 }
 

@@ -60,6 +60,9 @@ double orc_dnudcdm(const double *logkk, const double *ratio, int nbins, double n
 void orc_scale_modes(void *grid, int is_double, int dims, long long startslab, long long nslab, double box,
                      const double *logkk, const double *ratio, int nbins, double norm);
 
+/* ---- the Green's-function multiply that follows the hook in GADGET-2's pmforce_periodic (gadget2_greens.c) ---- */
+void orc_gadget2_greens(void *grid, int is_double, int PMGRID, long long slabstart_y, long long nslab_y, double asmth2);
+
 /* ---- K2 + state machine: delta_tot_table.c ---- */
 typedef struct orc_dtot {
     int nk, nk_allocated, namax, ia, init_done;

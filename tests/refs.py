@@ -196,6 +196,13 @@ def greens_numpy(grid, startslab, asmth2):
     return out
 
 
+def greens_gadget2(grid, startslab, asmth2):
+    """The C restatement of GADGET-2.0.7's Green's-function loop (oracle/gadget2_greens.c) on a copy of `grid`."""
+    out = np.ascontiguousarray(grid).copy()
+    orc().orc_gadget2_greens(out.ctypes.data_as(C.c_void_p), 1 if grid.dtype == np.float64 else 0, grid.shape[1], startslab, grid.shape[0], asmth2)
+    return out
+
+
 # ----------------------------------------------------------------------------- integrator fixtures
 def load_golden_state():
     """The arrays delta_tot_table_test.c:setup_delta_pow (:367-452) builds from testdata/:
@@ -312,6 +319,7 @@ def orc():
         "orc_total_powerspectrum": (I, [I, V, I, I, LL, LL, dp, llp, dp]),
         "orc_dnudcdm": (D, [dp, dp, I, D, D]),
         "orc_scale_modes": (None, [V, I, I, LL, LL, D, dp, dp, I, D]),
+        "orc_gadget2_greens": (None, [V, I, I, LL, LL, D]),
         "orc_dtot_alloc": (None, [tp, I, D, D, D, cp, D, D]),
         "orc_dtot_free": (None, [tp]),
         "orc_dtot_read": (I, [tp, C.c_char_p]),

@@ -1,0 +1,93 @@
+"""Parity AT THE BENCHMARK'S GRID WIDTHS against the reference's own sources.  The kernel instantiations bench.py times
+(K1 k1_tile_kernel<double,17,0> with two tiles per row and K3 k3_scale_tma_kernel<double,true,false> at PMGRID 2048; the
+bin-window K1 and the row-piece K3 <true,true> at 4096; the several-rows-per-CTA K3 <false,false> at 1024) are selected by the
+grid WIDTH, not by the number of planes -- so a few planes of a full-width grid exercise exactly them, and the reference
+(oracle/_ref/ref_slabs = powerspectrum.c + interface_gadget.c + ... compiled unmodified) does the same planes in seconds.
+
+Two plane ranges per case, as two ranks: [0, p) (holds F(0,0,0), the total mass) and a range across the Nyquist plane
+(negative k_x, the highest bins), so that total_mass2 != 0 and the all-reduce is part of the comparison
+(powerspectrum.c:45-47,91-95).  Same bytes on both sides: the device's synthetic grid (the one bench.py uses) is copied
+out and handed to the reference.  Asserted: mode counts exactly; P(k), keff, delta_nu after every step and the corrected
+grid to 1e-10 relative (BASELINE.json north_star, double grid)."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SLABS = os.path.join(ROOT, "oracle", "_ref", "ref_slabs")
+TRANSFER = os.path.join(ROOT, "tests", "golden", "ics_transfer_99.dat")
+pytestmark = pytest.mark.gpu
+
+
+def read_out(path):
+    raw = open(path, "rb").read()
+    n, nret, nk, ia, T = np.frombuffer(raw[:20], dtype=np.int32)
+    v = np.frombuffer(raw[20:], dtype=np.float64)
+    P, K, Cn = v[:nret], v[nret:2 * nret], v[2 * nret:3 * nret]
+    p = 3 * nret
+    dnus = []
+    for _ in range(T):
+        m = int(v[p]); dnus.append(v[p + 1:p + 1 + m]); p += 1 + m
+    assert p == v.size
+    return dict(n=int(n), nret=int(nret), nk=int(nk), ia=int(ia), P=P, K=K, C=Cn, dnu=dnus)
+
+
+def run_case(tmp_path, n, slabs, masses, hybrid, times, world_port):
+    if not os.path.exists(REF_SLABS):
+        pytest.skip("oracle/_ref/ref_slabs not built (needs /root/reference at build time)")
+    inp, out_p, out_r = str(tmp_path / "in.bin"), str(tmp_path / "prod.bin"), str(tmp_path / "ref.bin")
+    tail = [str(len(slabs))] + [str(x) for s in slabs for x in s] + [str(len(times))] + [repr(t) for t in times]
+    head = [str(n), str(int(hybrid))] + [repr(m) for m in masses]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={len(slabs)}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(world_port),
+                        os.path.join(ROOT, "tests", "fullsize_worker.py"), *head, inp, out_p, *tail],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and r.stdout.count(" ok") == len(slabs), r.stdout[-2000:] + r.stderr[-3000:]
+    r = subprocess.run([REF_SLABS, *head, TRANSFER, inp, out_r, *tail], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-2000:]
+    ref = read_out(out_r)
+    names = json.load(open(out_p + ".json"))
+    for which in (out_p + ".first", out_p):          # three-sum kernel (first sweep), tile kernel + cached geometry
+        got = read_out(which)
+        assert got["nret"] == ref["nret"], which
+        assert np.array_equal(got["C"], ref["C"]), which                              # mode counts: bit-exact
+        np.testing.assert_allclose(got["P"], ref["P"], rtol=1e-10, atol=0, err_msg=which)
+        np.testing.assert_allclose(got["K"], ref["K"], rtol=1e-10, atol=0, err_msg=which)
+    assert (got["nk"], got["ia"]) == (ref["nk"], ref["ia"])
+    for t, (a, b) in enumerate(zip(got["dnu"], ref["dnu"])):
+        np.testing.assert_allclose(a, b, rtol=1e-10, atol=0, err_msg=f"delta_nu after step {t}")
+    g_ref = np.fromfile(out_r + ".grid")
+    g_got = np.fromfile(out_p + ".grid")
+    g_in = np.fromfile(inp)
+    assert g_ref.size == g_got.size == g_in.size
+    assert not np.array_equal(g_ref, g_in)                                            # the steps did change the grid
+    np.testing.assert_allclose(g_got, g_ref, rtol=1e-10, atol=0)
+    return names
+
+
+def test_pmgrid_2048_bench_shape(tmp_path):
+    """BASELINE configs[3] (the headline): 3 x 0.1 eV, hybrid on; the last step is past NuPartTime = 0.333."""
+    names = run_case(tmp_path, 2048, [(0, 3), (1022, 5)], (0.1, 0.1, 0.1), True, (0.01, 0.02, 0.34), 29811)
+    assert "k1_bin_kernel" in names["k1_first"]
+    assert "k1_tile_kernel (8 warps x 17 modes per lane, 2 stages, 2 tiles per row)" in names["k1_cached"], names
+    assert names["k1_step"] == names["k1_cached"]
+    assert "k3_scale_tma_kernel<double, true, false>" in names["k3"], names
+
+
+def test_pmgrid_4096_bin_window_and_row_pieces(tmp_path):
+    """BASELINE configs[4]: non-degenerate masses, no hybrid; K1 with the bin window, K3 with rows cut into pieces."""
+    names = run_case(tmp_path, 4096, [(0, 2), (2046, 3)], (0.2, 0.1, 0.3), False, (0.01, 0.02, 0.035), 29812)
+    assert "k1_tile_kernel" in names["k1_cached"] and "in shared memory" in names["k1_cached"], names
+    assert "k3_scale_tma_kernel<double, true, true>" in names["k3"], names
+
+
+def test_pmgrid_1024_rows_sharing_a_cta(tmp_path):
+    """BASELINE configs[2]: 0.3 eV total, no hybrid; K3 with two rows per CTA."""
+    names = run_case(tmp_path, 1024, [(0, 4), (509, 7), (1020, 4)], (0.1, 0.1, 0.1), False, (0.01, 0.02, 0.05, 0.0505), 29813)
+    assert "k1_tile_kernel" in names["k1_cached"], names
+    assert "k3_scale_tma_kernel<double, false, false>" in names["k3"], names

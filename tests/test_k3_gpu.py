@@ -163,3 +163,33 @@ def test_long_rows_split_between_ctas_at_pmgrid_4096(gpu, start, greens):
     if greens:
         want = refs.greens_numpy(want, start, asmth2)
     np.testing.assert_allclose(split, want, rtol=1e-10, atol=0)
+
+
+@pytest.mark.parametrize("n,start,nslab,dtype,tol", [(64, 0, 64, np.float64, 1e-10), (64, 7, 30, np.float32, 1e-5), (33, 0, 33, np.float64, 1e-10),
+                                                     (1024, 510, 4, np.float64, 1e-10), (2048, 0, 2, np.float64, 1e-10),
+                                                     (2048, 1023, 3, np.float64, 1e-10), (4096, 2047, 2, np.float64, 1e-10)])
+def test_fused_greens_function_against_the_gadget2_loop(gpu, n, start, nslab, dtype, tol):
+    """The fused pass against the C restatement of GADGET-2.0.7's own loop (oracle/gadget2_greens.c: pm_periodic.c,
+    pmforce_periodic, 'multiply with Green's function for the potential') applied after the oracle's restatement of the
+    reference's scaling loop (interface_gadget.c:163-188) -- at small grids and on planes of the full-width grids, so that
+    every K3 instantiation (rows sharing a CTA, one row per CTA, row pieces) meets it with the Green's function on."""
+    from kspace_neutrinos_b200 import capi
+    box = refs.BOX
+    asmth2 = (2 * np.pi * 1.25 / n) ** 2
+    rng = np.random.default_rng(5 * n + start)
+    g = rng.standard_normal((nslab, n, n // 2 + 1, 2)).astype(dtype)
+    logkk, ratio, norm = _table(n, box, nk=min(40, max(3, n // 2)))
+    want = np.ascontiguousarray(g).copy()
+    refs.orc().orc_scale_modes(want.ctypes.data_as(C.c_void_p), 1 if dtype == np.float64 else 0, n, start, nslab, box,
+                               refs.dptr(logkk), refs.dptr(ratio), len(logkk), norm)
+    want = refs.greens_gadget2(want, start, asmth2)
+    d = refs.DeviceBuffer(gpu, g)
+    capi.check(gpu.ksn_scale_modes_greens(d.ptr, g.dtype.itemsize, n, start, nslab, box, refs.dptr(logkk), refs.dptr(ratio), len(logkk), norm, _invwin(gpu, n), asmth2))
+    got = d.download(g)
+    d.free()
+    assert b"Green's function fused" in gpu.ksn_last_k3_kernel()
+    if n >= 1152 and n <= 2302:
+        assert b"<double, true, false>" in gpu.ksn_last_k3_kernel()
+    if start == 0:
+        assert got[0, 0, 0, 0] == 0 and got[0, 0, 0, 1] == 0
+    np.testing.assert_allclose(got, want, rtol=tol, atol=0)

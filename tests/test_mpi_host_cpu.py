@@ -66,3 +66,30 @@ def test_slab_split_pm_steps_over_mini_mpi(tmp_path):
         np.testing.assert_allclose(res[ranks][2], res[1][2], rtol=1e-12)
         np.testing.assert_allclose(res[ranks][3], res[1][3], rtol=1e-12)
     assert not np.array_equal(res[1][3][2:], np.zeros_like(res[1][3][2:]))
+
+
+def test_communicator_passed_to_total_powerspectrum_is_bound_without_InitOmegaNu(tmp_path):
+    """The KSPACE_NEUTRINOS_2-off hook (gadget-2 patch 0004) calls compute_total_power_spectrum(..., comm) and nothing else:
+    the collective must be bound from that argument (powerspectrum.c:91-95 reduces on the communicator it is handed)."""
+    import numpy as np
+    exe = str(tmp_path / "mpi_total_power")
+    srcs = sorted(glob.glob(os.path.join(PKG, "src", "*.c")))
+    orc = [os.path.join(ROOT, "oracle", f) for f in ("ksn_oracle.c", "mini_gsl.c", "mini_mpi.c")]
+    cmd = ["gcc", "-O2", "-g", "-Wall", "-Werror=implicit-function-declaration", "-DKSN_HAVE_MPI", "-DDOUBLEPRECISION_FFTW",
+           "-I", os.path.join(ROOT, "oracle", "shim"), "-I", os.path.join(ROOT, "oracle"), "-I", os.path.join(ROOT, "include"),
+           "-I", os.path.join(PKG, "src"),
+           os.path.join(ROOT, "tests", "mpi_total_power.c"), os.path.join(ROOT, "tests", "device_standin.c"), *srcs, *orc,
+           "-lm", "-lpthread", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = {}
+    for ranks in (1, 2, 3):
+        out = str(tmp_path / f"tp{ranks}.bin")
+        r = subprocess.run([exe, str(ranks), out], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0 and "MPI TOTAL POWER OK" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
+        res[ranks] = np.fromfile(out)
+    nb = (res[1].size - 1) // 3
+    for ranks in (2, 3):
+        assert res[ranks][0] == res[1][0]
+        assert np.array_equal(res[ranks][1 + 2 * nb:], res[1][1 + 2 * nb:])            # counts
+        np.testing.assert_allclose(res[ranks][1:1 + 2 * nb], res[1][1:1 + 2 * nb], rtol=1e-12)

@@ -39,10 +39,14 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pmgrid", type=int, default=int(os.environ.get("KSN_BENCH_PMGRID", "2048")))
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-greens", action="store_true", help="skip the fused Green's-function side measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-check", action="store_true", help="skip the end-of-run parity check against the CPU oracle (outside the timed region)")
+    ap.add_argument("--ref-budget-s", type=float, default=float(os.environ.get("KSN_REF_BUDGET_S", "420")),
+                    help="--impl reference: wall-clock budget for the warm-up + timed steps; the full slab is timed when it fits "
+                         "host memory and this budget, else fewer planes per rank (reported)")
     ap.add_argument("--cpu-planes", type=int, default=0, help="planes per rank in the CPU sample (0 = auto)")
     # the other BASELINE.json configs (parity-test cases, measured beside the headline): e.g. --pmgrid 4096 --mnu 0.2,0.1,0.3
     # --no-hybrid for configs[4]; the CPU arm is fixed to the headline's neutrino set-up, so use --no-cpu-baseline with them
@@ -60,17 +64,17 @@ def workload_config(n, gpus, extra=None, mnu=(0.1, 0.1, 0.1), hybrid=True):
     cfg = {"workload": f"PMGRID={n}^3 double, x-slab sharded over {gpus} GPU(s), {masses}, hybrid neutrinos "
                        f"{'on (Vcrit=500, NuPartTime=0.333)' if hybrid else 'off'}, 99-row delta_tot history (a=0.98+)",
            "pmgrid": n, "stored_modes": n * n * (n // 2 + 1), "nrbins": n // 2,
-           "parallelism": f"slab{gpus}", "l2": "grid (>= 8.6 GB per GPU) far exceeds the 126 MB L2; no flush needed"}
+           "parallelism": f"slab{gpus}", "l2": f"grid ({16 * n * n * (n // 2 + 1) / gpus / 1e9:.3g} GB per GPU) " + ("far exceeds" if 16 * n * n * (n // 2 + 1) / gpus > 1.26e9 else "vs") + " the 126 MB L2; no flush between steps"}
     if extra:
         cfg.update(extra)
     return cfg
 
 
 # ----------------------------------------------------------------------------- reference / CPU arm
-def run_ref_bench(n, planes, ranks, steps, hybrid=1, timeout=1500):
+def run_ref_bench(n, planes, ranks, steps, hybrid=1, timeout=3000, warmup=1, budget_s=0.0, mnu=(0.1, 0.1, 0.1)):
     """Time the reference's CPU path (oracle/_ref/ref_bench: reference sources + shims, forked ranks)."""
-    out = subprocess.run([REF_BENCH, str(n), str(planes), str(ranks), str(steps), str(hybrid), TRANSFER],
-                         capture_output=True, text=True, timeout=timeout)
+    out = subprocess.run([REF_BENCH, str(n), str(planes), str(ranks), str(steps), str(hybrid), TRANSFER, str(warmup), repr(float(budget_s))] +
+                         [repr(float(m)) for m in mnu], capture_output=True, text=True, timeout=timeout)
     if out.returncode != 0:
         raise RuntimeError("ref_bench failed: " + out.stderr[-500:])
     return json.loads(out.stdout.strip().splitlines()[-1])
@@ -120,33 +124,56 @@ def run_port_bench(n, planes, ranks, steps):
     return {"N": n, "P": planes, "R": ranks, "steps": [{"total": t, "k1": None, "integral": None, "k3": None} for t in per_step]}
 
 
-def cpu_throughput(n, steps, planes=0):
-    """modes/s of the CPU path on all host cores, from a bounded sample (P planes per rank)."""
+def mem_available_bytes():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    return 0
+
+
+def cpu_throughput(n, steps, planes=0, warmup=1, budget_s=0.0, full_slab=False, mnu=(0.1, 0.1, 0.1), hybrid=True):
+    """modes/s of the CPU path on all host cores.  full_slab: every rank takes its whole slab of the PMGRID^3 grid when the
+    grid fits host memory (and stays below 2^31 elements per rank, the reference's `int` indices) -- nothing extrapolated;
+    ref_bench itself cuts the planes per rank after the first warm-up step if warmup+steps would not fit budget_s.
+    Otherwise a bounded sample (P planes per rank, ~6 s of CPU work per step), grid passes scaled to the full slab."""
     ranks = os.cpu_count() or 1
     while n % ranks:
         ranks -= 1
+    whole = n // ranks
+    plane_elems = n * (n // 2 + 1)
     if planes <= 0:
-        # ~0.2 us per mode per core for the two grid passes (measured 0.1-0.25) -> aim at ~6 s of CPU work per step:
-        # long enough that the extrapolation to the full slab is not dominated by start-up noise
-        per_plane = n * (n // 2 + 1) * 0.2e-6
-        planes = max(1, min(n // ranks, int(6.0 / per_plane)))
+        grid_bytes = 16 * plane_elems * n
+        if full_slab and whole * plane_elems < 2 ** 31 and mem_available_bytes() > 1.15 * grid_bytes + (8 << 30):
+            planes = whole
+        else:
+            # ~0.2 us per mode per core for the two grid passes (measured 0.1-0.25) -> aim at ~6 s of CPU work per step:
+            # long enough that the extrapolation to the full slab is not dominated by start-up noise
+            planes = max(1, min(whole, int(6.0 / (plane_elems * 0.2e-6))))
     if os.path.exists(REF_BENCH):
-        kind, r = "reference", run_ref_bench(n, planes, ranks, steps)
+        kind, r = "reference", run_ref_bench(n, planes, ranks, steps, hybrid=1 if hybrid else 0, warmup=warmup, budget_s=budget_s, mnu=mnu)
     else:
         kind, r = "port", run_port_bench(n, planes, ranks, steps)
-    scale = (n / ranks) / planes
-    full = []
+    full, used = [], set()
     for s in r["steps"]:
+        p_s = s.get("planes", planes)
+        used.add(p_s)
+        scale = whole / p_s
         if s.get("integral") is not None:
-            full.append((s["k1"] + s["k3"]) * scale + s["integral"])
+            full.append(s["total"] if p_s == whole else (s["k1"] + s["k3"]) * scale + s["integral"])
         else:
             full.append(s["total"] * scale)        # port: integral not separable; scaled with the grid (pessimistic for the CPU only by the integral share)
     t = statistics.median(full)
     modes = n * n * (n // 2 + 1)
-    sample = (f"{kind} CPU path, {ranks} forked ranks x {planes} planes of the {n}^3 grid per step "
-              f"(grid passes scaled by {scale:.1f} to the full slab = extrapolated; integral timed in full, "
-              f"nk={r.get('nk')}, Na={r.get('Na')}), {len(full)} step(s)")
-    return modes / t, t, {"kind": kind, "cores": ranks, "sample": sample, "raw": r}
+    extrapolated = used != {whole}
+    how = (f"whole slabs ({whole} planes per rank = the full {n}^3 grid, {16 * plane_elems * n / 1e9:.1f} GB): nothing extrapolated" if not extrapolated else
+           f"{sorted(used)} planes per rank of {whole} (grid passes scaled to the full slab = extrapolated; integral timed in full)")
+    sample = (f"{kind} CPU path, {ranks} forked ranks, {how}; nk={r.get('nk')}, Na={r.get('Na')}, {len(full)} timed step(s) after "
+              f"{r.get('warmup', 1)} warm-up; grid = the GPU arm's counter-based synthetic field")
+    return modes / t, t, {"kind": kind, "cores": ranks, "sample": sample, "raw": r, "extrapolated": extrapolated, "warmup": r.get("warmup", 1)}
 
 
 def reference_arm(args):
@@ -155,10 +182,13 @@ def reference_arm(args):
         return
     n = args.pmgrid
     t0 = time.time()
-    val, t_step, info = cpu_throughput(n, max(1, args.steps), args.cpu_planes)
+    val, t_step, info = cpu_throughput(n, max(1, args.steps), args.cpu_planes, warmup=max(0, args.warmup), budget_s=args.ref_budget_s,
+                                       full_slab=True, mnu=args.mnu, hybrid=not args.no_hybrid)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": 1, "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(n, args.gpus),
+            "warmup": info["warmup"], "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(n, args.gpus, None, args.mnu, not args.no_hybrid),
+            "collective": "MPI_Allreduce over the forked ranks (mini-MPI shim: shared memory)",
+            "extrapolated": info["extrapolated"],
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.time() - t0}
@@ -243,7 +273,7 @@ def ours(args):
     a = 0.98
     # < 0.009: the row is integrated every step but not kept -> steady state; and never past a = 1 (TimeMax), however
     # many steps the caller asks for
-    n_calls = max(3, args.warmup) + args.steps + (0 if args.no_e2e else args.e2e_steps + 1) + 2
+    n_calls = max(3, args.warmup) + args.steps + (0 if args.no_e2e else args.e2e_steps + 1) + 4
     da = min(0.001, (0.9995 - a) / n_calls)
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -279,6 +309,8 @@ def ours(args):
     step_ms = dev_ms / args.steps
     value = modes_total / (step_ms * 1e-3)
     launches = int(tm.launches)
+    k3_name = L.ksn_last_k3_kernel().decode()           # the instantiation the timed steps launched
+    k1_name = L.ksn_last_k1_kernel().decode()
 
     # ---- what fusing the PM Green's function into K3 saves (one launch each, N=1 only; not part of `value`)
     greens = None
@@ -373,6 +405,21 @@ def ours(args):
         if pin is not None:
             pin.free()
 
+    # ---- parity check (outside every timed region): one more PM step whose K1 / K2 / K3 results are re-derived by the CPU
+    # oracle from the same inputs (tests/bench_check.py); every rank takes the step, rank 0 compares
+    check = None
+    if not args.no_check:
+        a += da
+        if rank == 0:
+            try:
+                from tests import bench_check
+                check = bench_check.check_step(L, sim, grid, slab, n, a, args.mnu, not args.no_hybrid, world)
+            except Exception as exc:  # noqa: BLE001 - report, never lose the measured line
+                check = {"ok": False, "error": repr(exc)}
+        else:
+            sim.add_nu_power_to_rhogrid(a, grid.ptr, slab)
+        barrier()
+
     if rank != 0:
         return
     peaks = {}
@@ -394,10 +441,10 @@ def ours(args):
             traffic = traffic * local_modes / modes_total   # a launch on this rank's slab
     except (OSError, ValueError):
         pass
-    roofline = {"bound": "hbm", "kernel": "k3_scale_tma_kernel<double> (read-modify-write, 32 B per stored mode)",
+    roofline = {"bound": "hbm", "kernel": k3_name + " (read-modify-write, 32 B per stored mode)",
                 "achieved": 32.0 * local_modes / (k3_launch_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                 "frac": 32.0 * local_modes / (k3_launch_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
-                "k1": {"kernel": L.ksn_last_k1_kernel().decode() + " (read-only, 16 B per stored mode)",
+                "k1": {"kernel": k1_name + " (read-only, 16 B per stored mode)",
                        "achieved": 16.0 * local_modes / (k1_launch_ms * 1e-3) / 1e9,
                        "frac": 16.0 * local_modes / (k1_launch_ms * 1e-3) / 1e9 / peak},
                 "step": {"achieved": 48.0 * local_modes / (step_ms * 1e-3) / 1e9,
@@ -407,13 +454,15 @@ def ours(args):
                 "k2_kernel": f"speculation width {L.ksn_k2_spec_width() or 'by regime (hybrid, one species: 3)'}, slowest bin {L.ksn_last_k2_max_trips()} passes through the integrand"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(n, world, {"collective": comm_backend}, args.mnu, not args.no_hybrid), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "data": "synthetic", "config": workload_config(n, world, None, args.mnu, not args.no_hybrid), "collective": comm_backend, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "wall_ms_per_step": wall_ms / args.steps}
+    if check is not None:
+        line["parity_check"] = check
     if greens is not None:
         line["greens_fusion"] = greens
     if world == 1 and not args.no_cpu_baseline:
         try:
-            v, t_step, info = cpu_throughput(n, 1, args.cpu_planes)
+            v, t_step, info = cpu_throughput(n, 1, args.cpu_planes, mnu=args.mnu, hybrid=not args.no_hybrid)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"],
                                     "s_per_step": t_step}
         except Exception as exc:  # noqa: BLE001 - report, never fail the GPU number on the CPU leg

@@ -167,6 +167,10 @@ int ksn_k1_tile_plan_ex(int dims, int nrbins, size_t smem_budget, int sms, int r
 const char *ksn_last_k1_kernel(void);
 /* which K3 kernel the most recent scaling pass launched (template instance, rows per CTA / pieces per row) */
 const char *ksn_last_k3_kernel(void);
+/* the _delta_pow table (and norm, box size) the most recent scaling pass used: pointers into a host copy owned by the
+ * library, valid until the next pass.  For checkers: a pass can then be compared with the CPU restatement of
+ * interface_gadget.c:163-188 on exactly the table it applied. */
+int ksn_last_k3_table(const double **logkk, const double **ratio, int *nbins, double *norm, double *boxsize);
 /* integrand evaluations of the most recent ksn_delta_nu_integrate call (fslength table included) */
 unsigned long long ksn_last_k2_evals(void);
 /* largest number of 61-point rule applications any single k bin needed in that call (the kernel's critical path) */

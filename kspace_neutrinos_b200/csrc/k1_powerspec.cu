@@ -440,18 +440,11 @@ __device__ __forceinline__ double queue_get(unsigned addr)
 // rarely used ones below in a global-memory array of its own (`cold`, read and written through L1 by this warp only, in
 // the same fixed order), which makes room for eight warps again.
 //
-// real = float (opt-in, KSN_K1_F32_TILE=1: written after this round's GPU minutes were spent, not yet run on a B200): a
-// float row is (N/2+1)*8 bytes, so every other row -- and with it every tile of that row -- starts 8 bytes off the
+// real = float: a float row is (N/2+1)*8 bytes, so every other row -- and with it every tile of that row -- starts 8 bytes off the
 // 16-byte granule of a bulk copy.  Such a tile is copied from one mode earlier (`sh` = 1) and to an even mode count; the
 // lanes read their chunks `sh` modes into the stage, and the one or two foreign modes at the ends are either never read
 // or walked with weight 0 like everything past a row's end.  |F|^2 is formed in float as the reference's float build does
 // (powerspectrum.c:68 with fftw_real = float), the window stays the separable double one (float-grid tolerance 1e-5).
-// WIN == 2 (opt-in, KSN_K1_WIN=3: written after this round's GPU minutes were spent, not yet run on a B200): the same layout
-// as WIN == 1, but the choice between the two homes of a bin is made once per TILE instead of once per update.  A tile whose
-// first mode already lies in bin hot_lo or above (k^2 grows along z, so then all of it does) walks with shared-memory-only
-// bin accesses -- LDS/STS, no generic-address loads and no per-update branches, the instruction stream of the kernel
-// without a window; the few cold tiles (rows within ~60 grid units of the axis) take the general walk with the
-// two-homed accesses.  Same bins, same update order: bit-identical sums to WIN == 1.
 template <typename real, int CT, int WIN>
 __global__ void __launch_bounds__((CT == 5 || CT == 9 ? K1T_MAXW : 8) * 32, 1)
 k1_tile_kernel(const Cplx<real> *__restrict__ grid, int nrows, int N, int nrbins, long long plane0, float binscale,
@@ -524,18 +517,10 @@ k1_tile_kernel(const Cplx<real> *__restrict__ grid, int nrows, int N, int nrbins
     // tile k is issued together with the set-up arithmetic of tile k+1, so that the two latency chains overlap.
     int p_fbin = 0x7fffffff;               // previous tile's first-run bin / sum / row factor (none yet)
     double p_facc = 0.0, p_wxy = 0.0;
-    auto binp_hot = [&](int idx) -> double * { return mybins + (idx - hot_lo); };     // WIN == 2, hot tiles only
     auto merge_first_runs = [&]() {
         double v1[1] = { p_facc };
         const unsigned tails = segmented_sum<1>(p_fbin, v1, lane, le_mask);
-        if (((tails >> lane) & 1u) && p_fbin != 0x7fffffff) {
-            if constexpr (WIN == 2) {                   // typed accesses under a branch instead of a generic pointer
-                if (p_fbin >= hot_lo) { double *bp = mybins + (p_fbin - hot_lo); *bp = fma(v1[0], p_wxy, *bp); }
-                else { double *bp = mycold + p_fbin; *bp = fma(v1[0], p_wxy, *bp); }
-            } else {
-                double *bp = binp(p_fbin); *bp = fma(v1[0], p_wxy, *bp);
-            }
-        }
+        if (((tails >> lane) & 1u) && p_fbin != 0x7fffffff) { double *bp = binp(p_fbin); *bp = fma(v1[0], p_wxy, *bp); }
         __syncwarp();
     };
     double wreg[CT > 0 ? CT : 1];
@@ -641,41 +626,13 @@ k1_tile_kernel(const Cplx<real> *__restrict__ grid, int nrows, int N, int nrbins
                 if (i <= closed) *bp_of(fbin + i) = fma(g[i - 1], wxy, m[i - 1]);
             facc = queue_get(q0);
         };
-        // GENERAL tile (the low-k corner, where bins are narrower than a step in k^2): finished runs go straight to the bins
-        auto general_walk = [&](auto bp_of) {
-            facc = 0.0;
-            auto step = [&](const Cplx<real> v, double w) {
-                double pp;
-                if constexpr (sizeof(real) == 8) pp = fma(v.im, v.im, v.re * v.re); else pp = (double) fmaf(v.im, v.im, v.re * v.re);
-                if (k2 >= nxt) {
-                    if (b == fbin) facc = acc; else { double *bp = bp_of(b); *bp = fma(acc, wxy, *bp); }
-                    acc = 0.0;
-                    do { b++; nxt = thr_s[b + 1]; } while (k2 >= nxt);
-                }
-                acc = fma(pp, w, acc);
-                k2 += dz;
-                dz += 2u;
-            };
-            step(chunk[0], __ldg(wz) * worigin);
-#pragma unroll 1
-            for (int e = 1; e < C; e++) step(chunk[e], __ldg(wz + e));
-            if (b == fbin) facc = acc; else { double *bp = bp_of(b); *bp = fma(acc, wxy, *bp); }
-            __syncwarp();
-            if (lane == 0 && ri < nrows) issue(ri, ti, s);
-        };
-        if constexpr (WIN == 2) {
-            if ((unsigned) c + (unsigned) z0 * (unsigned) z0 < thr_s[hot_lo]) general_walk(binp);     // cold tile: some bins live in the global array
-            else if (single && spread <= 3) fast_walk(std::integral_constant<int, 4>(), binp_hot);
-            else if (single && spread <= K1T_QRUNS - 1) fast_walk(std::integral_constant<int, K1T_QRUNS>(), binp_hot);
-            else general_walk(binp_hot);
-        } else {
+        {
             if (single && spread <= 3) {
                 fast_walk(std::integral_constant<int, 4>(), binp);
             } else if (single && spread <= K1T_QRUNS - 1) {
                 fast_walk(std::integral_constant<int, K1T_QRUNS>(), binp);
             } else {
-                // (the general walk once more, in line: as a call of the lambda above it compiles to the same instructions
-                // in another register allocation, and these instantiations are the ones measured on the B200)
+                // GENERAL tile (the low-k corner, where bins are narrower than a step in k^2): finished runs go straight to the bins
                 facc = 0.0;
                 auto step = [&](const Cplx<real> v, double w) {
                     double pp;
@@ -747,11 +704,9 @@ static bool k1_tile_config(int L, int nrbins, size_t budget, int ctas, K1TileCfg
     int fw = 0, fc = 0, fs = 0;
     const char *env = getenv("KSN_K1_TILE");
     if (env && sscanf(env, "%d,%d,%d", &fw, &fc, &fs) != 3) fw = 0;
-    // bin window: "0" off, "1" where all the bins do not fit for eight warps, "2" (tests) always, with a quarter of the bins;
-    // "3" / "4": as "1" / "2" with the kernel that chooses a bin's home per tile (k1_tile_kernel<.., 2>, opt-in)
+    // bin window: "0" off, "1" where all the bins do not fit for eight warps, "2" (tests) always, with a quarter of the bins
     const char *wenv = getenv("KSN_K1_WIN");
-    const int wval = wenv ? atoi(wenv) : KSN_K1_WIN_DEFAULT;
-    const int window = wval == 3 ? 1 : wval == 4 ? 2 : wval;                  // 3 / 4: as 1 / 2, other kernel (k1_launch_t)
+    const int window = wenv ? atoi(wenv) : KSN_K1_WIN_DEFAULT;
     for (int C = 1; C <= 65; C += 4)
         for (int W = 4; W <= k1_tile_max_warps(C); W++)
             for (int S = 1; S <= 4; S++) {
@@ -776,6 +731,10 @@ static bool k1_tile_config(int L, int nrbins, size_t budget, int ctas, K1TileCfg
                 if (T > 1 && C < 5) continue;                             // tiny tiles only for tiny rows
                 const double eff = (double) L / ((double) T * TE);        // lane slots that carry a mode
                 double score = W * (C / (C + 10.0)) * eff * (compile_time ? 1.0 : 0.88) * (1.0 + 0.01 * S) * (hot_lo ? 0.99 : 1.0);
+                // float rows: half the bytes per mode for the same instructions -- the walk is bound by issue slots, not by
+                // per-warp latency, so warps beyond eight buy nothing and the per-tile bookkeeping is what counts (measured
+                // at 2048^3: 8 warps x 33 modes, a whole row per tile, 5.57 TB/s; 15 x 9: 4.10; 8 x 17: 4.52; 12 x 9: 3.76)
+                if (esz == 8) score = std::min(W, 8) * (C / (C + 10.0)) * eff * (compile_time ? 1.0 : 0.88) * (1.0 + 0.01 * S) * (hot_lo ? 0.99 : 1.0) - 0.001 * W;
                 if (((long long) ctas * W) % T) score *= 0.97;            // the warp's tile-of-row changes every tile: weights reloaded
                 if (score > best_score) {
                     best_score = score;
@@ -943,10 +902,7 @@ static int k1_launch_t(const void *dgrid, int dims, int nrbins, long long plane0
     constexpr int NV = FULL ? 3 : 1;
     if (nplanes * dims > 0x7fffffffLL) return set_error(KSN_EINVAL, "K1: %lld rows in one slab", nplanes * dims);
     const int nrows = (int) (nplanes * dims);
-    // experiment knob: KSN_K1_CFG = "<max warps><unroll>" in {164, 204, 242, 244, 162}
-    const char *cfg = FULL ? nullptr : getenv("KSN_K1_CFG");
-    const int cfgv = cfg ? atoi(cfg) : 164;
-    int nwarps = FULL ? K1_MAX_WARPS : cfgv / 10;
+    int nwarps = K1_MAX_WARPS;
     while (nwarps > 1 && k1_smem_bytes(dims, nrbins, nwarps, NV) > c.smem_optin) nwarps--;
     const size_t smem = k1_smem_bytes(dims, nrbins, nwarps, NV);
     if (smem > c.smem_optin)
@@ -965,10 +921,9 @@ static int k1_launch_t(const void *dgrid, int dims, int nrbins, long long plane0
         return KSN_OK;
     };
     K1TileCfg tc;
-    // float rows through the tile kernel: opt-in until it has been through the GPU parity suite (see the kernel); it needs
-    // an even number of modes in the slab (the last bulk copy is rounded up to a mode pair)
-    const char *f32tile = getenv("KSN_K1_F32_TILE");
-    const bool tile_ok = sizeof(real) == 8 || (f32tile && atoi(f32tile) > 0 && ((long long) nrows * (dims / 2 + 1)) % 2 == 0);
+    // float rows through the tile kernel need an even number of modes in the slab (the last bulk copy is rounded up to a
+    // mode pair); the scan-based kernel takes the rest
+    const bool tile_ok = sizeof(real) == 8 || ((long long) nrows * (dims / 2 + 1)) % 2 == 0;
     if (!FULL && tile_ok && !getenv("KSN_K1_PAIR") && !getenv("KSN_K1_NOPAIR") && ((uintptr_t) dgrid & 15) == 0 &&
         k1_tile_config(dims / 2 + 1, nrbins, c.smem_optin, c.num_sms, &tc, (int) (2 * sizeof(real)))) {
         int log2N = -1;
@@ -984,9 +939,6 @@ static int k1_launch_t(const void *dgrid, int dims, int nrbins, long long plane0
                                                          g_k1_k2_single, log2N, tc.hot_lo, c.d_cold);
             return KSN_OK;
         };
-        // KSN_K1_WIN=3: the bin window with the home of a bin chosen per tile (k1_tile_kernel<.., 2>; opt-in, see the kernel)
-        const char *wenv3 = getenv("KSN_K1_WIN");
-        const bool tile_choice = wenv3 && (atoi(wenv3) == 3 || atoi(wenv3) == 4);       // 4: with the forced window of the tests
         int rct;
         switch (tc.hot_lo ? -tc.C : tc.C) {
         case 5: rct = go(k1_tile_kernel<real, 5, 0>); break;
@@ -997,17 +949,17 @@ static int k1_launch_t(const void *dgrid, int dims, int nrbins, long long plane0
             if constexpr (sizeof(real) == 4) rct = go(k1_tile_kernel<real, 33, 0>);
             else rct = go(k1_tile_kernel<real, 0, 0>);
             break;
-        case -9: rct = tile_choice ? go(k1_tile_kernel<real, 9, 2>) : go(k1_tile_kernel<real, 9, 1>); break;
-        case -13: rct = tile_choice ? go(k1_tile_kernel<real, 13, 2>) : go(k1_tile_kernel<real, 13, 1>); break;
-        case -17: rct = tile_choice ? go(k1_tile_kernel<real, 17, 2>) : go(k1_tile_kernel<real, 17, 1>); break;
+        case -9: rct = go(k1_tile_kernel<real, 9, 1>); break;
+        case -13: rct = go(k1_tile_kernel<real, 13, 1>); break;
+        case -17: rct = go(k1_tile_kernel<real, 17, 1>); break;
         default: rct = go(k1_tile_kernel<real, 0, 0>); break;
         }
         if (rct) return rct;
         c.launches++;
         KSN_CUDA(cudaGetLastError());
         if (tc.hot_lo)
-            snprintf(g_k1_last, sizeof g_k1_last, "k1_tile_kernel%s (%d warps x %d modes per lane, %d stages, %d tiles per row, bins >= %d of %d in shared memory%s)",
-                     sizeof(real) == 4 ? "<float>" : "", tc.W, tc.C, tc.S, tc.T, tc.hot_lo, nrbins, tile_choice ? ", home chosen per tile" : "");
+            snprintf(g_k1_last, sizeof g_k1_last, "k1_tile_kernel%s (%d warps x %d modes per lane, %d stages, %d tiles per row, bins >= %d of %d in shared memory)",
+                     sizeof(real) == 4 ? "<float>" : "", tc.W, tc.C, tc.S, tc.T, tc.hot_lo, nrbins);
         else
             snprintf(g_k1_last, sizeof g_k1_last, "k1_tile_kernel%s (%d warps x %d modes per lane, %d stages, %d tiles per row)",
                      sizeof(real) == 4 ? "<float>" : "", tc.W, tc.C, tc.S, tc.T);
@@ -1017,10 +969,6 @@ static int k1_launch_t(const void *dgrid, int dims, int nrbins, long long plane0
     }
     snprintf(g_k1_last, sizeof g_k1_last, "%s<%s>", FULL || getenv("KSN_K1_NOPAIR") ? "k1_bin_kernel" : "k1_pair_kernel", sizeof(real) == 8 ? "double" : "float");
     if (FULL || getenv("KSN_K1_NOPAIR")) rc = launch(k1_bin_kernel<real, FULL>);
-    else if (cfgv == 204) rc = launch(k1_pair_kernel<real, 20, 4>);
-    else if (cfgv == 242) rc = launch(k1_pair_kernel<real, 24, 2>);
-    else if (cfgv == 244) rc = launch(k1_pair_kernel<real, 24, 4>);
-    else if (cfgv == 162) rc = launch(k1_pair_kernel<real, 16, 2>);
     else rc = launch(k1_pair_kernel<real, 16, 4>);
     if (rc) return rc;
     *ctas_out = ctas;
@@ -1067,8 +1015,6 @@ int k1_finish(int real_bytes, int dims, int nrbins, bool full, int ctas, int str
 
 // The tables depend on (dims, nrbins) only, and a PM run passes the same ones every step: remember what sits in
 // c.d_thr / c.d_iw (by content hash, not by host address) and skip the three uploads and the stream sync they cost.
-// Opt-in (KSN_K1_TABLE_CACHE=1) until it has been through the GPU parity suite: it was written after this round's
-// GPU minutes were spent.
 struct K1TabKey { bool valid; int dims, nrbins; unsigned long long h_thr, h_iw; const void *d_thr, *d_iw; };
 static K1TabKey g_k1_tab = { false, 0, 0, 0, 0, nullptr, nullptr };
 void k1_tables_invalidate() { g_k1_tab.valid = false; }
@@ -1112,7 +1058,7 @@ static int k1_upload_tables(int dims, int nrbins, const unsigned int *thresholds
     const unsigned long long h_thr = hash_words(thresholds, (size_t) nrbins * sizeof(unsigned));
     const unsigned long long h_iw = hash_words(invwin, (size_t) L * sizeof(double));
     if (g_k1_tab.valid && g_k1_tab.dims == dims && g_k1_tab.nrbins == nrbins && g_k1_tab.h_thr == h_thr && g_k1_tab.h_iw == h_iw &&
-        g_k1_tab.d_thr == c.d_thr && g_k1_tab.d_iw == c.d_iw && getenv("KSN_K1_TABLE_CACHE"))
+        g_k1_tab.d_thr == c.d_thr && g_k1_tab.d_iw == c.d_iw)
         return KSN_OK;
     g_k1_tab.valid = false;
     {
@@ -1187,7 +1133,9 @@ int k1_sums(const void *dgrid, const void *hgrid, int real_bytes, int dims, int 
     int rc = k1_upload_tables(dims, nrbins, thresholds, invwin);
     if (rc) return rc;
     const bool cache_ok = !getenv("KSN_NO_GEOM_CACHE");
-    const bool have_geom = cache_ok && c.geom.valid && c.geom.dims == dims && c.geom.nrbins == nrbins &&
+    // keff and count sums depend on the thresholds' CONTENT too (a C-ABI caller may pass other bin edges for the same shape)
+    const unsigned long long h_thr = g_k1_tab.h_thr;
+    const bool have_geom = cache_ok && c.geom.valid && c.geom.dims == dims && c.geom.nrbins == nrbins && c.geom.h_thr == h_thr &&
                            c.geom.startslab == startslab && c.geom.nslab == nslab && c.geom.epoch == c.comm_epoch;
     const bool full = !have_geom;
     int ctas = 0, stride = 0;
@@ -1232,7 +1180,7 @@ int k1_sums(const void *dgrid, const void *hgrid, int real_bytes, int dims, int 
             c.geom.count[b] = (long long) llrint(c.h_red[2 * nrbins + 1 + b]);   // exact: < 2^53
         }
         c.geom.valid = true; c.geom.dims = dims; c.geom.nrbins = nrbins;
-        c.geom.startslab = startslab; c.geom.nslab = nslab; c.geom.epoch = c.comm_epoch;
+        c.geom.startslab = startslab; c.geom.nslab = nslab; c.geom.epoch = c.comm_epoch; c.geom.h_thr = h_thr;
     }
     memcpy(power_sum, c.h_red, sizeof(double) * nrbins);
     *total_mass2 = c.h_red[nrbins];

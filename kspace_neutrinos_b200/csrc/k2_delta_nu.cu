@@ -812,197 +812,6 @@ k2_delta_nu_spec_kernel(const __grid_constant__ K2Dev p)
     }
 }
 
-// ---------------------------------------------------------------- one k bin spread over a CLUSTER of M CTAs
-// (opt-in, KSN_K2_CLUSTER=2|3|4: written after this round's GPU minutes were spent, not yet run on a B200.)
-// With hybrid neutrinos K2's time is the critical path of its deepest bins, and inside k2_delta_nu_spec_kernel<M> a pass
-// through the integrand is slowed by the 4 M warps of one CTA sharing one SM's FP64 pipe (a pass costs 12.5 us at M = 3
-// against 5.8 us for the 4 warps of the sequential kernel, profiles/r1_k2_widths.txt).  Here the M groups of a pass are M
-// CTAs of a thread-block cluster, one SM each: CTA c integrates the two halves of slot sel[c]; the interval list lives in
-// the shared memory of CTA 0, the others read their interval from it and write their results into it through
-// distributed shared memory; CTA 0's warp 0 replays QAG's loop (ksn_qag_spec.h) exactly as the one-CTA kernel does.
-// Same arithmetic, same reduction tree, same decisions: bit-identical output.  Two cluster barriers per pass.
-template <int M, class F>
-__device__ void qk61_cluster(const F &f, SpecShared<M> *S0, double (*red)[4], int rank, bool whole)
-{
-    const int tid = threadIdx.x, g = tid >> 6, n = tid & 63, warp = tid >> 5;     // g: which half
-    const bool gactive = whole ? (rank == 0 && g == 0) : rank < S0->nsel;
-    int slot = 0;
-    double a = 0.0, b = 0.0;
-    if (gactive) {
-        slot = whole ? 0 : S0->sel[rank];
-        const double a_i = S0->L.a[slot], b_i = S0->L.b[slot];
-        if (whole) {
-            a = a_i; b = b_i;
-        } else {
-            const double mid = 0.5 * (a_i + b_i);
-            a = g ? mid : a_i;
-            b = g ? b_i : mid;
-        }
-    }
-    const double center = 0.5 * (a + b), half_length = 0.5 * (b - a);
-    const bool active = gactive && n < 61;
-    const int j = n <= 30 ? n : 60 - n;
-    double fv = 0.0, wk = 0.0, wgs = 0.0;
-    if (active) {
-        const double absc = half_length * c_xgk[j];
-        fv = f(n <= 30 ? center - absc : center + absc);
-        wk = c_wgk[j];
-        wgs = (j & 1) ? c_wg[j >> 1] : 0.0;
-    }
-    const double sk = warp_sum(wk * fv), sg = warp_sum(wgs * fv), sa = warp_sum(wk * fabs(fv));
-    if ((tid & 31) == 0) { red[warp][0] = sk; red[warp][1] = sg; red[warp][2] = sa; }
-    __syncthreads();
-    const double kron = red[2 * g][0] + red[2 * g + 1][0];
-    const double gaus = red[2 * g][1] + red[2 * g + 1][1];
-    const double rabs = red[2 * g][2] + red[2 * g + 1][2];
-    const double mean = kron * 0.5;
-    const double sc = warp_sum(active ? wk * fabs(fv - mean) : 0.0);
-    if ((tid & 31) == 0) red[warp][3] = sc;
-    __syncthreads();
-    if (gactive && n == 0) {
-        const double rasc = red[2 * g][3] + red[2 * g + 1][3];
-        QkOut o;
-        o.result = kron * half_length;
-        o.resabs = rabs * fabs(half_length);
-        o.resasc = rasc * fabs(half_length);
-        o.abserr = rescale_error_d((kron - gaus) * half_length, o.resabs, o.resasc);
-        if (whole) {
-            S0->q0[0] = o.result; S0->q0[1] = o.abserr; S0->q0[2] = o.resabs; S0->q0[3] = o.resasc;
-        } else {                                        // into the leader's list (distributed shared memory)
-            S0->L.cr[2 * slot + g] = o.result;
-            S0->L.ce[2 * slot + g] = o.abserr;
-            S0->L.cf[2 * slot + g] = o.resasc != o.abserr;
-        }
-    }
-    __syncthreads();
-}
-
-// gsl_integration_qag (key 6) by a cluster of M CTAs of 128 threads; every thread of every CTA returns the same values.
-// S: this CTA's copy (only the leader's, rank 0, is used), S0: the leader's as seen from here.
-template <int M, class F>
-__device__ int qag61_cluster(const F &f, double a, double b, double epsabs, double epsrel, int limit,
-                             SpecShared<M> &S, SpecShared<M> *S0, double (*red)[4], int rank, cg::cluster_group &cluster,
-                             double *result, double *abserr, unsigned *passes, unsigned *rules, unsigned *trips)
-{
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool replayer = rank == 0 && warp == 0;
-    if (rank == 0 && tid == 0) { S.L.a[0] = a; S.L.b[0] = b; S.nsel = 0; S.done = 0; }
-    cluster.sync();
-    qk61_cluster<M>(f, S0, red, rank, true);
-    QagSpecState s;                       // lives in lane 0 of warp 0 of the leader
-    unsigned nrules = 1, ntrips = 1;
-    int size = 1;
-    if (replayer && lane == 0) {
-        int st = QAGS_OK;
-        if (qags_begin(s, S.L, a, b, epsabs, epsrel, limit, S.q0[0], S.q0[1], S.q0[2], S.q0[3], &st)) {
-            S.result = S.q0[0]; S.abserr = S.q0[1]; S.status = st; S.passes = 1; S.rules = 1; S.trips = 1; S.done = 1;
-        } else {
-            S.L.cached[0] = 1; S.sel[0] = 0; S.nsel = 1;
-        }
-    }
-    for (;;) {
-        cluster.sync();                   // the leader's selection (or verdict) is visible in the whole cluster
-        if (*(volatile int *) &S0->done) break;
-        qk61_cluster<M>(f, S0, red, rank, false);
-        cluster.sync();                   // every CTA's results have landed in the leader's list
-        if (!replayer) continue;
-        nrules += 2 * S.nsel;
-        ntrips++;
-        // replay QAG's loop over the cached halves (as qag61_spec)
-        for (;;) {
-            const int i = warp_argmax_err(S.L.e, nullptr, 0.0, size, lane);
-            int act = 1;                  // 0: one trip made, go on; 1: slot i must be integrated first; 2: finished
-            double floor_ = 0.0;
-            if (lane == 0) {
-                if (S.L.cached[i]) act = qags_apply(s, S.L, i) ? 0 : 2;
-                else floor_ = qags_spec_threshold(s);
-            }
-            act = __shfl_sync(0xffffffffu, act, 0);
-            __syncwarp();
-            if (act != 1) size++;
-            if (act == 0) continue;
-            if (act == 2) {
-                if (lane == 0) {
-                    double res, err;
-                    S.status = qags_finish(s, S.L, &res, &err);
-                    S.result = res; S.abserr = err; S.passes = s.passes; S.rules = nrules; S.trips = ntrips; S.done = 1;
-                }
-                break;
-            }
-            floor_ = __shfl_sync(0xffffffffu, floor_, 0);
-            if (lane == 0) { S.L.cached[i] = 1; S.sel[0] = i; }
-            int ns = 1;
-            for (; ns < M; ns++) {
-                __syncwarp();
-                const int jn = warp_argmax_err(S.L.e, S.L.cached, floor_, size, lane);
-                if (jn < 0) break;
-                if (lane == 0) { S.L.cached[jn] = 1; S.sel[ns] = jn; }
-            }
-            if (lane == 0) S.nsel = ns;
-            break;
-        }
-    }
-    *result = S0->result;
-    *abserr = S0->abserr;
-    if (passes) *passes = S0->passes;
-    if (rules) *rules = S0->rules;
-    if (trips) *trips = S0->trips;
-    return S0->status;
-}
-
-template <int M>
-__global__ void __cluster_dims__(M, 1, 1) __launch_bounds__(K2_THREADS, 4)
-k2_delta_nu_cluster_kernel(const __grid_constant__ K2Dev p)
-{
-    cg::cluster_group cluster = cg::this_cluster();
-    const int rank = (int) cluster.block_rank();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ SpecShared<M> S;
-    __shared__ double red[4][4];
-    __shared__ double jt_s[JT_DOUBLES];
-    SpecShared<M> *S0 = cluster.map_shared_rank(&S, 0);
-    double *sx = (double *) smem_raw, *sy = sx + p.Na, *sc = sy + p.Na, *sb = sc + p.Na, *sd = sb + p.Na;
-    const int nclusters = (int) (gridDim.x / M), cid = (int) (blockIdx.x / M);
-    const int ik = p.k_first + (nclusters - 1 - cid);                    // deepest (highest-k) bins are scheduled first
-    const int sp = blockIdx.y;
-    jfrac_table_init(jt_s, p.qc[sp], p.nufrac_low0);
-    for (int i = threadIdx.x; i < p.Na; i += blockDim.x) {
-        sx[i] = p.scalefact[i];
-        sy[i] = p.delta_tot[(size_t) ik * p.namax + i];
-    }
-    __syncthreads();
-    const double k = p.wavenum[ik], mnubykT = p.mnubykT[sp];
-    const double fsl_A0a = p.fslengths[0];
-    const double specJ0 = specialJ_fit_d(k * fsl_A0a / (mnubykT > 0 ? mnubykT : 1));
-    double dnu = specJ0 * p.delta_nu_init[ik] * (1. + p.deriv_prefac * fsl_A0a);
-    int st = Q_OK;
-    unsigned passes = 0, rules = 0, trips = 0;
-    if (p.integrate[sp]) {                     // (uniform over the cluster: same species)
-        if (p.Na > 2) {                        // every CTA of the cluster builds its own copy of the bin's spline
-            for (int i = threadIdx.x; i < p.Na - 2; i += blockDim.x) sc[i + 1] = spline_rhs(sx, sy, i);
-            __syncthreads();
-            if (threadIdx.x == 0) spline_solve_seq(p.Na, p.dt_alpha, p.dt_gamma, sc);
-            __syncthreads();
-            for (int i = threadIdx.x; i < p.Na - 1; i += blockDim.x) cspline_segment(sx, sy, sc, i, sb[i], sd[i]);
-            __syncthreads();
-        }
-        DeltaNuIntegrand f;
-        f.P = &p; f.sx = sx; f.sy = sy; f.sc = sc; f.sb = sb; f.sd = sd;
-        f.k = k; f.mnubykT = mnubykT; f.qc = p.qc[sp]; f.jt = jt_s;
-        f.fs_x0 = p.loga0;
-        f.fs_inv_dx = (p.Nfs - 1.) / (p.loga - p.loga0);
-        double res, err;
-        st = qag61_cluster<M>(f, p.loga0, p.loga, 0.0, p.relerr[sp], QAG_LIMIT, S, S0, red, rank, cluster, &res, &err, &passes, &rules, &trips);
-        dnu += p.delta_nu_prefac * res;
-    }
-    if (rank == 0 && threadIdx.x == 0) {
-        p.out[(size_t) sp * p.nk + ik] = dnu;
-        p.status[(size_t) sp * p.nk + ik] = st | ((int) passes << 8) | ((int) trips << 20);
-        if (p.evals && rules) atomicAdd(p.evals, 61ull * rules);
-    }
-    cluster.sync();                            // the leader's shared memory outlives every read of it
-}
-
 static BgPatch g_bg_patch[BG_MAX_PATCH];
 static int g_bg_npatch = 0, g_bg_flagged = 0;
 
@@ -1223,16 +1032,7 @@ extern "C" int ksn_delta_nu_integrate(const ksn_delta_nu_args *A, double *out, u
         k2_prep_splines_kernel<<<2, 256, 0, c.stream>>>(d_fsscales, d_fslengths, Nfs, d_fsc, d_fsb, d_fsd, d_sa, d_sg, d_in, Na, d_dta, d_dtg);
         c.launches++;
     }
-    // bins of this launch: all of them, or (experiment: KSN_K2_SHARD="r,R") the r-th of R contiguous shares
-    int k_first = 0, k_count = nk;
-    {
-        int r = 0, R = 0;
-        const char *env = getenv("KSN_K2_SHARD");
-        if (env && sscanf(env, "%d,%d", &r, &R) == 2 && R > 0 && r >= 0 && r < R) {
-            k_first = (int) ((long long) nk * r / R);
-            k_count = (int) ((long long) nk * (r + 1) / R) - k_first;
-        }
-    }
+    const int k_first = 0, k_count = nk;
     K2Dev p;
     p.nk = nk; p.Na = Na; p.namax = A->namax; p.Nfs = Nfs; p.k_first = k_first;
     p.loga0 = loga0; p.loga = loga; p.light = A->light; p.delta_nu_prefac = A->delta_nu_prefac;
@@ -1250,24 +1050,10 @@ extern "C" int ksn_delta_nu_integrate(const ksn_delta_nu_args *A, double *out, u
         const size_t smem = 5 * (size_t) Na * sizeof(double);
         int width = k2_spec_width();
         if (width == 0) width = k2_spec_auto(ns, p.qc);
-        // opt-in (see k2_delta_nu_cluster_kernel): one k bin per cluster of M CTAs
-        const char *cenv = getenv("KSN_K2_CLUSTER");
-        const int cl = cenv ? atoi(cenv) : 0;
-        if (cl >= 2 && cl <= 4 && (long long) k_count * cl <= 0x7fffffffLL) {
-            const dim3 cgrid((unsigned) (k_count * cl), ns);
-            if (cl == 2) k2_delta_nu_cluster_kernel<2><<<cgrid, K2_THREADS, smem, c.stream>>>(p);
-            else if (cl == 3) k2_delta_nu_cluster_kernel<3><<<cgrid, K2_THREADS, smem, c.stream>>>(p);
-            else k2_delta_nu_cluster_kernel<4><<<cgrid, K2_THREADS, smem, c.stream>>>(p);
-            width = -cl;
-        }
         switch (width) {
-        case -2: case -3: case -4: break;       // launched above
         case 2: k2_delta_nu_spec_kernel<2, 3><<<grid, 2 * K2_THREADS, smem, c.stream>>>(p); break;
         case 3: k2_delta_nu_spec_kernel<3, 2><<<grid, 3 * K2_THREADS, smem, c.stream>>>(p); break;
-        case 4:
-            if (getenv("KSN_K2_SPEC4_ONE_PER_SM")) k2_delta_nu_spec_kernel<4, 1><<<grid, 4 * K2_THREADS, smem, c.stream>>>(p);
-            else k2_delta_nu_spec_kernel<4, 2><<<grid, 4 * K2_THREADS, smem, c.stream>>>(p);
-            break;
+        case 4: k2_delta_nu_spec_kernel<4, 2><<<grid, 4 * K2_THREADS, smem, c.stream>>>(p); break;
         default: k2_delta_nu_kernel<<<grid, K2_THREADS, smem, c.stream>>>(p); break;
         }
     }

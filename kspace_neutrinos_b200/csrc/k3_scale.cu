@@ -22,6 +22,8 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
+#include <type_traits>
 
 namespace ksn {
 
@@ -62,6 +64,8 @@ __device__ __forceinline__ float fast_log2(float x)
 
 // per-knot record
 struct __align__(16) K3Seg { double K2, inv, A, B; };
+// the same in float, for float grids whose table is smooth enough (see k3_upload_table): delta = A - 1 = norm * ratio
+struct __align__(16) K3SegF { float inv, A1, B, pad; };
 
 // Optional second factor: the periodic PM Green's function with CIC deconvolution that a Gadget-style PM step applies
 // to the same grid right after the neutrino correction (Gadget-2 pm_periodic.c, the loop that follows the hook of
@@ -75,7 +79,8 @@ struct K3Greens {
 };
 
 // exp(-k2 a) = exp(-(kx^2+ky^2) a) * exp(-kz^2 a): a per-row scalar (with the x-y window) times a per-z table, so that a
-// mode costs one table read, two multiplies and a reciprocal of the integer k2 (float seed + two Newton steps, < 1e-15).
+// mode costs one table read, two multiplies and a reciprocal of the integer k2 (correctly rounded float seed, relative
+// error 2^-24, + one Newton step: 2^-48 = 3.6e-15; FP64 issue is what the fused pass is short of).
 __device__ __forceinline__ double k3_greens_row(const K3Greens &gr, int ki, int kj)
 {
     const double a = __ldg(gr.iw + (ki < 0 ? -ki : ki)), b = __ldg(gr.iw + (kj < 0 ? -kj : kj));
@@ -88,7 +93,6 @@ __device__ __forceinline__ double k3_greens(const K3Greens &gr, int k2i, double 
     const double k2 = (double) k2i;
     double r = (double) __frcp_rn((float) k2i);
     r = r * fma(-k2, r, 2.0);
-    r = r * fma(-k2, r, 2.0);
     return rowfac * __ldg(gr.gz + z) * r;
 }
 
@@ -97,63 +101,96 @@ struct K3Params {
     int cells;        // lookup cells in log2(k2); the host sizes them so that no cell holds two knots
     float cell_lo;    // log2(K2_0)
     float cell_scale; // cells per unit log2
+    int off_kthr;     // table offsets in units of 4 bytes from the table base: integer knot thresholds, float records
+    int off_segf;
+    int multi;        // a cell may hold several knots (knots closer than the finest cells): loop in the segment search
 };
+
+// How the factor 1 + norm*interp is evaluated (chosen per table by the host, k3_upload_table):
+//   FM_D9   double, ln(1+u) as a series to u^9 (truncation < 1e-16 for u < 2^-5): any table
+//   FM_D5   double, series to u^5: tables whose narrow segments satisfy |B| u_max^6 / 6 <= 1e-14 -- four FP64
+//           instructions less per mode, the same factor to 1e-14
+//   FM_F32  FLOAT grids only: delta = factor - 1 entirely in float and x*factor as fmaf(x, delta, x), for tables with
+//           |B| <= 1/64 and |norm*ratio| <= 1/32, where the float evaluation of delta is off by < 2^-28 of the factor
+//           (1/16 of a float ulp of the product) -- no FP64 instruction left in the float pass
+enum { FM_D9 = 0, FM_D5 = 1, FM_F32 = 2 };
 
 // The lookup tables live in GLOBAL memory and are read through L1 (__ldg): they are identical for every CTA, a few
 // tens of KB, and the streaming grid accesses bypass L1 (L1::no_allocate), so after the first CTAs of a launch every
 // lookup is an L1 hit -- without the per-CTA staging cost that would forbid short-lived CTAs.
-template <typename real>
-__device__ __forceinline__ double k3_factor(int k2i, const K3Seg *__restrict__ seg, const unsigned short *__restrict__ cellv, const K3Params &prm)
+// Segment of k2: a cell lookup in log2(k2) (one MUFU) gives the last knot at or below the cell's lower edge; the cell
+// holds at most one more knot (host guarantee), found by one INTEGER compare -- k2 >= K2_{s+1} <=> k2 >= ceil(K2_{s+1})
+// for integer k2.
+__device__ __forceinline__ int k3_segment(int k2i, const unsigned short *__restrict__ cellv, const unsigned *__restrict__ kthr, const K3Params &prm)
 {
-    const double k2 = (double) k2i;
     int cell = (int) ((fast_log2((float) k2i) - prm.cell_lo) * prm.cell_scale);
     cell = max(0, min(cell, prm.cells - 1));
-    int s = __ldg(cellv + cell);                                // last knot at or below the cell's lower edge
-    s += (k2 >= __ldg(&seg[s + 1].K2));                         // at most one knot inside a cell (host guarantee)
+    int s = __ldg(cellv + cell);
+    s += ((unsigned) k2i >= __ldg(kthr + s + 1));
+    if (prm.multi) while ((unsigned) k2i >= __ldg(kthr + s + 1)) s++;        // (kthr ends in 0xffffffff: terminates)
+    return s;
+}
+
+template <int FM>
+__device__ __forceinline__ double k3_factor(int k2i, const double *__restrict__ tab, const K3Params &prm)
+{
+    const K3Seg *seg = (const K3Seg *) tab;
+    const unsigned short *cellv = (const unsigned short *) (seg + prm.n + 1);
+    const unsigned *kthr = (const unsigned *) tab + prm.off_kthr;
+    const int s = k3_segment(k2i, cellv, kthr, prm);
     const double2 ki = __ldg((const double2 *) &seg[s].K2);    // {K2, 1/K2}
     const double2 ab = __ldg((const double2 *) &seg[s].A);     // {A, B}
-    const double uu = fmax(fma(k2, ki.y, -1.0), 0.0);           // below the first knot: clamp (delta_pow.c:24-31)
+    const double uu = fmax(fma((double) k2i, ki.y, -1.0), 0.0); // below the first knot: clamp (delta_pow.c:24-31)
     double lg;
     if (uu < 0.03125) {
-        // log1p(u), u < 2^-5: alternating series to u^9, truncation < 1e-16
-        lg = uu * (1.0 + uu * (-0.5 + uu * (1.0 / 3 + uu * (-0.25 + uu * (0.2 + uu * (-1.0 / 6 + uu * (1.0 / 7 + uu * (-0.125 + uu * (1.0 / 9)))))))));
+        // log1p(u), u < 2^-5: alternating series
+        if (FM == FM_D5) lg = uu * (1.0 + uu * (-0.5 + uu * (1.0 / 3 + uu * (-0.25 + uu * 0.2))));
+        else lg = uu * (1.0 + uu * (-0.5 + uu * (1.0 / 3 + uu * (-0.25 + uu * (0.2 + uu * (-1.0 / 6 + uu * (1.0 / 7 + uu * (-0.125 + uu * (1.0 / 9)))))))));
     } else {
         lg = log1p(uu);
     }
     return fma(ab.y, lg, ab.x);
 }
 
-// The same factor for a FLOAT grid when KSN_K3_F32_TMA=2: the product is narrowed to float (2^-24), so the series may stop
-// at u^4 -- truncation u^5/5 <= 7e-9 of ln(1+u), which itself enters as the small correction B ln(k^2/K^2) to A ~ 1 --
-// and the factor costs 5 FP64 instructions less per mode (the float kernel has half the bytes per mode to hide them
-// behind).  Differs from k3_factor by far less than the float rounding of the result; opt-in.
-__device__ __forceinline__ double k3_factor_short(int k2i, const K3Seg *__restrict__ seg, const unsigned short *__restrict__ cellv, const K3Params &prm)
+// FM_F32: factor - 1 in float
+__device__ __forceinline__ float k3_delta_f32(int k2i, const double *__restrict__ tab, const K3Params &prm)
 {
-    const double k2 = (double) k2i;
-    int cell = (int) ((fast_log2((float) k2i) - prm.cell_lo) * prm.cell_scale);
-    cell = max(0, min(cell, prm.cells - 1));
-    int s = __ldg(cellv + cell);
-    s += (k2 >= __ldg(&seg[s + 1].K2));
-    const double2 ki = __ldg((const double2 *) &seg[s].K2);
-    const double2 ab = __ldg((const double2 *) &seg[s].A);
-    const double uu = fmax(fma(k2, ki.y, -1.0), 0.0);
-    double lg;
-    if (uu < 0.03125) lg = uu * (1.0 + uu * (-0.5 + uu * (1.0 / 3 + uu * (-0.25))));
-    else lg = log1p(uu);
-    return fma(ab.y, lg, ab.x);
+    const K3Seg *seg = (const K3Seg *) tab;
+    const unsigned short *cellv = (const unsigned short *) (seg + prm.n + 1);
+    const unsigned *kthr = (const unsigned *) tab + prm.off_kthr;
+    const K3SegF *segf = (const K3SegF *) ((const unsigned *) tab + prm.off_segf);
+    const int s = k3_segment(k2i, cellv, kthr, prm);
+    const float4 r = __ldg((const float4 *) (segf + s));       // {1/K2, A - 1, B, -}
+    const float uu = fmaxf(fmaf((float) k2i, r.x, -1.0f), 0.0f);  // k2 < 2^24 is exact in float
+    float lg;
+    if (uu < 0.03125f) lg = uu * (1.0f + uu * (-0.5f + uu * (1.0f / 3 + uu * (-0.25f + uu * 0.2f))));
+    else lg = log1pf(uu);
+    return fmaf(r.z, lg, r.y);
+}
+
+// one mode times its factor, in the grid's precision rules: fftw_real *= double (interface_gadget.c:185-186)
+template <typename real> __device__ __forceinline__ void k3_apply(C2<real> &v, double smth)
+{
+    v.re = (real) ((double) v.re * smth);
+    v.im = (real) ((double) v.im * smth);
+}
+__device__ __forceinline__ void k3_apply_delta(C2<float> &v, float d)
+{
+    v.re = fmaf(v.re, d, v.re);
+    v.im = fmaf(v.im, d, v.im);
 }
 
 // Sweep: SHORT-LIVED CTAs, one per block of `rows_per_cta` consecutive rows (one row of N/2+1 modes for large grids):
 // every thread issues all its loads up front, the CTA's accesses form one contiguous range, and the hardware block
 // scheduler balances the SMs.  Measured on this B200 (tools/bw_probe.cu) this pattern sustains 6.9 TB/s for an
-// in-place scale against 6.1 TB/s for a persistent loop.
-template <typename real, int U>
+// in-place scale against 6.1 TB/s for a persistent loop.  Plain loads and stores: the fall-back for slabs the bulk-copy
+// kernels below cannot take (a base pointer off the 16-byte granule, an odd mode total of a float slab) and the
+// comparison kernel of the tests (KSN_K3_NOTMA).
+template <typename real, int U, int FM>
 __global__ void __launch_bounds__(K3_THREADS)
 k3_scale_kernel(C2<real> *__restrict__ grid, int nrows, int rows_per_cta, int N, long long plane0,
                 const double *__restrict__ tab, const K3Params prm, const K3Greens gr)
 {
-    const K3Seg *seg = (const K3Seg *) tab;
-    const unsigned short *cellv = (const unsigned short *) (seg + prm.n + 1);
     const int L = N / 2 + 1;
     const int row0 = blockIdx.x * rows_per_cta;
     const int nr = min(rows_per_cta, nrows - row0);
@@ -179,169 +216,143 @@ k3_scale_kernel(C2<real> *__restrict__ grid, int nrows, int rows_per_cta, int N,
             const int kj = j <= N / 2 ? j : j - N;
             const int k2i = ki * ki + kj * kj + z * z;
             if (k2i == 0 && !gr.on) continue;                    // F(0,0,0) is skipped (interface_gadget.c:174)
-            double smth = k2i > 0 ? k3_factor<real>(k2i, seg, cellv, prm) : 0.0;
-            if (gr.on && k2i > 0) smth *= k3_greens(gr, k2i, k3_greens_row(gr, ki, kj), z);   // the mean is zeroed
-            C2<real> o;
-            o.re = (real) ((double) v[u].re * smth);
-            o.im = (real) ((double) v[u].im * smth);
+            C2<real> o = v[u];
+            if constexpr (FM == FM_F32) {
+                k3_apply_delta(o, k3_delta_f32(k2i, tab, prm));          // (never launched with the Green's function on)
+            } else {
+                double smth = k2i > 0 ? k3_factor<FM>(k2i, tab, prm) : 0.0;
+                if (gr.on && k2i > 0) smth *= k3_greens(gr, k2i, k3_greens_row(gr, ki, kj), z);   // the mean is zeroed
+                k3_apply<real>(o, smth);
+            }
             st_cs(base + e, o);
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// TMA variant (default for double/float grids): the CTA's block of rows is brought into shared memory by ONE bulk
-// asynchronous copy (cp.async.bulk, completion on an mbarrier) issued before anything else; while it is in flight every
-// thread computes the scale factors of its modes (they depend on geometry only), then scales in shared memory and one
-// bulk store writes the block back.  In-flight bytes are bounded by shared memory (~32 KB per CTA, 5-6 CTAs per SM),
-// not by registers.
+// Bulk-copy kernels (default): the CTA's piece of the grid is brought into shared memory by ONE bulk asynchronous copy
+// (cp.async.bulk, completion on an mbarrier) issued before anything else; while it is in flight every thread computes
+// the scale factors of its modes (they depend on geometry only), then scales in shared memory and one bulk store
+// writes the piece back.  In-flight bytes are bounded by shared memory (~16 KB per CTA, 7-8 CTAs per SM), not by
+// registers.
 constexpr int K3_EPT = 9;                  // modes per thread
 constexpr int K3_TMA_THREADS = 128;        // <= 1152 modes (one 2048^3 row) per CTA: many small CTAs keep L1 for the tables
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
 
-template <typename real, bool ONE_ROW, bool SPLIT>
+// the three phases shared by the bulk-copy kernels
+__device__ __forceinline__ void k3_bulk_load(void *buf, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(buf)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void k3_bulk_wait(unsigned long long *bar)
+{
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void k3_bulk_store(void *dst, const void *buf, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(buf)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the read
+}
+
+// One grid ROW per CTA (PMGRID 1152 ... 2302), or -- SPLIT -- one piece of a row that does not fit one CTA's 1152 modes
+// (PMGRID = 4096: two pieces of 1025 and 1024 modes): everything but z is CTA-uniform.
+template <bool SPLIT, int FM>
 __global__ void __launch_bounds__(K3_TMA_THREADS, 8)
-k3_scale_tma_kernel(C2<real> *__restrict__ grid, int nrows, int rows_per_cta, int N, long long plane0,
+k3_scale_row_kernel(C2<double> *__restrict__ grid, int N, long long plane0,
                     const double *__restrict__ tab, const K3Params prm, const K3Greens gr, int segs, int seg_len)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
-    C2<real> *buf = (C2<real> *) smem_raw;
-    const K3Seg *seg = (const K3Seg *) tab;
-    const unsigned short *cellv = (const unsigned short *) (seg + prm.n + 1);
+    C2<double> *buf = (C2<double> *) smem_raw;
     const int L = N / 2 + 1;
-    // ONE_ROW: the CTA owns segment (blockIdx % segs) of row (blockIdx / segs) -- the whole row when segs == 1, a piece of
-    // seg_len modes when a row does not fit one CTA (PMGRID = 4096: two pieces of 1025 and 1024 modes).  Otherwise a
-    // block of rows_per_cta whole rows.
     int row0, nel, z0 = 0;
-    if (ONE_ROW && SPLIT) {
+    if (SPLIT) {
         row0 = (int) (blockIdx.x / (unsigned) segs);
         z0 = (int) (blockIdx.x - (unsigned) row0 * (unsigned) segs) * seg_len;
         nel = min(seg_len, L - z0);
-    } else if (ONE_ROW) {
+    } else {
         row0 = blockIdx.x;
         nel = L;
-    } else {
-        row0 = blockIdx.x * rows_per_cta;
-        nel = min(rows_per_cta, nrows - row0) * L;
     }
-    const unsigned bytes = (unsigned) nel * (unsigned) sizeof(C2<real>);
-    C2<real> *base = grid + (size_t) row0 * L + z0;
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(buf)), "l"(base), "r"(bytes), "r"(smem_u32(&bar)) : "memory");
-    }
+    const unsigned bytes = (unsigned) nel * (unsigned) sizeof(C2<double>);
+    C2<double> *base = grid + (size_t) row0 * L + z0;
+    if (threadIdx.x == 0) k3_bulk_load(buf, base, bytes, &bar);
     // factors while the copy is in flight
-    auto row_k = [&](int r, int &ki, int &kj) {
-        const int pl = r / N, j = r - pl * N;
-        const long long gi = plane0 + pl;
-        ki = gi <= N / 2 ? (int) gi : (int) (gi - N);
-        kj = j <= N / 2 ? j : j - N;
-    };
-    auto row_c = [&](int r) {                // kx^2 + ky^2 of grid row r
-        int ki, kj;
-        row_k(r, ki, kj);
-        return ki * ki + kj * kj;
-    };
-    const int c0 = row_c(row0);              // CTA-uniform: the only row when ONE_ROW
-    double w0 = 1.0;                         // -exp(-(kx^2+ky^2) asmth2) (iwx iwy)^4 of that row, for the Green's function
-    if (gr.on && ONE_ROW) { int ki, kj; row_k(row0, ki, kj); w0 = k3_greens_row(gr, ki, kj); }
+    const int pl = row0 / N, j = row0 - pl * N;
+    const long long gi = plane0 + pl;
+    const int ki = gi <= N / 2 ? (int) gi : (int) (gi - N);
+    const int kj = j <= N / 2 ? j : j - N;
+    const int c0 = ki * ki + kj * kj;
+    const double w0 = gr.on ? k3_greens_row(gr, ki, kj) : 1.0;   // -exp(-(kx^2+ky^2) asmth2) (iwx iwy)^4 of this row
     double smth[K3_EPT];
 #pragma unroll
     for (int k = 0; k < K3_EPT; k++) {
         const int e = threadIdx.x + K3_TMA_THREADS * k;
         smth[k] = 1.0;
         if (e < nel) {
-            int k2i, z = z0 + e;
-            double wxy4 = w0;
-            if (ONE_ROW) {
-                k2i = c0 + z * z;
-            } else {
-                const int rl = e / L;
-                z = e - rl * L;
-                int ki, kj;
-                row_k(row0 + rl, ki, kj);
-                k2i = ki * ki + kj * kj + z * z;
-                if (gr.on) wxy4 = k3_greens_row(gr, ki, kj);
-            }
-            if (k2i > 0) smth[k] = k3_factor<real>(k2i, seg, cellv, prm);     // F(0,0,0) keeps factor 1 ...
-            if (gr.on) smth[k] = k2i > 0 ? smth[k] * k3_greens(gr, k2i, wxy4, z) : 0.0;   // ... or is zeroed with the potential
+            const int z = z0 + e, k2i = c0 + z * z;
+            if (k2i > 0) smth[k] = k3_factor<FM>(k2i, tab, prm);                            // F(0,0,0) keeps factor 1 ...
+            if (gr.on) smth[k] = k2i > 0 ? smth[k] * k3_greens(gr, k2i, w0, z) : 0.0;       // ... or is zeroed with the potential
         }
     }
     __syncthreads();                       // the barrier was initialised before anyone polls it
-    {
-        unsigned done = 0;
-        while (!done)
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"(smem_u32(&bar)) : "memory");
-    }
+    k3_bulk_wait(&bar);
 #pragma unroll
     for (int k = 0; k < K3_EPT; k++) {
         const int e = threadIdx.x + K3_TMA_THREADS * k;
         if (e < nel) {
-            C2<real> v = buf[e];
-            v.re = (real) ((double) v.re * smth[k]);
-            v.im = (real) ((double) v.im * smth[k]);
+            C2<double> v = buf[e];
+            k3_apply<double>(v, smth[k]);
             buf[e] = v;
         }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the bulk store
     __syncthreads();
-    if (threadIdx.x == 0) {
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(base), "r"(smem_u32(buf)), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the read
-    }
+    if (threadIdx.x == 0) k3_bulk_store(base, buf, bytes);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Float grids (opt-in, KSN_K3_F32_TMA=1: written after this round's GPU minutes were spent, not yet run on a B200).
-// A float row is (N/2+1)*8 bytes -- 8200 at PMGRID = 2048 -- so every other row starts 8 bytes off the 16-byte granule
-// bulk copies need.  The slab is therefore cut into FLAT chunks of an even number of modes (two whole rows where they
-// fit one CTA: 2050 modes = 16400 B at 2048, the double kernel's block size), ignoring row boundaries; a thread finds
-// row and z of its modes from the chunk's first mode.  Same three phases as above: bulk copy in, factors while it is in
-// flight, scale in shared memory, bulk store.  256 threads x 9 modes.
-// The same kernel serves double grids whose rows are short enough for several to share a CTA (PMGRID <= 1150, opt-in
-// KSN_K3_FLAT=1, 128 threads): k3_scale_tma_kernel<double, false, false> divides by the row length for every mode, this one
-// once per thread.
+// FLAT chunks: the slab cut into pieces of an even number of modes, ignoring row boundaries; a thread finds row and z of
+// its modes from the chunk's first mode (one division per thread, none per mode).  Serves
+//  * double grids whose rows are short enough for several to share a CTA (PMGRID <= 1150: whole rows per chunk,
+//    128 threads; 6.6 TB/s at 1024^3 against 5.3 for a kernel that divides per mode), and
+//  * float grids (256 threads): a float row is (N/2+1)*8 bytes -- 8200 at PMGRID = 2048 -- so every other row starts
+//    8 bytes off the 16-byte granule bulk copies need; chunks of an even mode count (two whole rows, 16400 B, at 2048) do not.
 constexpr int K3_FLAT_THREADS = 256;
 
-template <typename real, int THREADS, bool SHORT = false>
+template <typename real, int THREADS, int FM>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
-k3_scale_tma_flat_kernel(C2<real> *__restrict__ grid, long long total, int chunk, int N, long long plane0,
-                         const double *__restrict__ tab, const K3Params prm, const K3Greens gr)
+k3_scale_flat_kernel(C2<real> *__restrict__ grid, long long total, int chunk, int N, long long plane0,
+                     const double *__restrict__ tab, const K3Params prm, const K3Greens gr)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
     C2<real> *buf = (C2<real> *) smem_raw;
-    const K3Seg *seg = (const K3Seg *) tab;
-    const unsigned short *cellv = (const unsigned short *) (seg + prm.n + 1);
     const int L = N / 2 + 1;
     const long long e0 = (long long) blockIdx.x * chunk;           // first mode of this CTA's chunk (slab-relative, even)
     const int nel = (int) min((long long) chunk, total - e0);      // even: chunk and total are
     const unsigned bytes = (unsigned) nel * (unsigned) sizeof(C2<real>);
     C2<real> *base = grid + e0;
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(buf)), "l"(base), "r"(bytes), "r"(smem_u32(&bar)) : "memory");
-    }
+    if (threadIdx.x == 0) k3_bulk_load(buf, base, bytes, &bar);
     // (plane, row-in-plane, z) of the chunk's first mode
     const long long r0 = e0 / L;
     const int zb = (int) (e0 - r0 * L);
     const long long pl0 = r0 / N;
     const int j0 = (int) (r0 - pl0 * N);
-    double smth[K3_EPT];
+    using fac_t = typename std::conditional<FM == FM_F32, float, double>::type;
+    fac_t smth[K3_EPT];
 #pragma unroll
     for (int k = 0; k < K3_EPT; k++) {
         const int e = threadIdx.x + THREADS * k;
-        smth[k] = 1.0;
+        smth[k] = FM == FM_F32 ? (fac_t) 0 : (fac_t) 1;            // FM_F32 holds factor - 1
         if (e < nel) {
             int z = zb + e, j = j0;
             long long gi = plane0 + pl0;
@@ -353,42 +364,52 @@ k3_scale_tma_flat_kernel(C2<real> *__restrict__ grid, long long total, int chunk
             const int ki = gi <= N / 2 ? (int) gi : (int) (gi - N);
             const int kj = j <= N / 2 ? j : j - N;
             const int k2i = ki * ki + kj * kj + z * z;
-            if (k2i > 0) smth[k] = SHORT ? k3_factor_short(k2i, seg, cellv, prm) : k3_factor<real>(k2i, seg, cellv, prm);     // F(0,0,0) keeps factor 1 ...
-            if (gr.on) smth[k] = k2i > 0 ? smth[k] * k3_greens(gr, k2i, k3_greens_row(gr, ki, kj), z) : 0.0;   // ... or is zeroed
+            if constexpr (FM == FM_F32) {
+                if (k2i > 0) smth[k] = k3_delta_f32(k2i, tab, prm);       // (never launched with the Green's function on)
+            } else {
+                if (k2i > 0) smth[k] = k3_factor<FM>(k2i, tab, prm);                                         // F(0,0,0) keeps factor 1 ...
+                if (gr.on) smth[k] = k2i > 0 ? smth[k] * k3_greens(gr, k2i, k3_greens_row(gr, ki, kj), z) : 0.0;   // ... or is zeroed
+            }
         }
     }
     __syncthreads();                       // the barrier was initialised before anyone polls it
-    {
-        unsigned done = 0;
-        while (!done)
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"(smem_u32(&bar)) : "memory");
-    }
+    k3_bulk_wait(&bar);
 #pragma unroll
     for (int k = 0; k < K3_EPT; k++) {
         const int e = threadIdx.x + THREADS * k;
         if (e < nel) {
             C2<real> v = buf[e];
-            v.re = (real) ((double) v.re * smth[k]);               // interface_gadget.c:185-186: fftw_real *= double
-            v.im = (real) ((double) v.im * smth[k]);
+            if constexpr (FM == FM_F32) k3_apply_delta(v, smth[k]); else k3_apply<real>(v, smth[k]);
             buf[e] = v;
         }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the bulk store
     __syncthreads();
-    if (threadIdx.x == 0) {
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(base), "r"(smem_u32(buf)), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the read
-    }
+    if (threadIdx.x == 0) k3_bulk_store(base, buf, bytes);
 }
 
-static size_t k3_tab_doubles(int n, int cells) { return (size_t) 4 * (n + 1) + ((size_t) cells * sizeof(unsigned short) + 7) / 8; }
+// host copy of the table of the most recent scaling pass (ksn_last_k3_table: bench.py and the tests check a pass against
+// the CPU restatement with exactly the table the pass used)
+static struct { double *logkk, *ratio; int nbins, cap; double norm, boxsize; } g_k3_tab_copy = { nullptr, nullptr, 0, 0, 0.0, 0.0 };
+
+// table layout (4-byte words from the base): K3Seg[n+1] | u16 cell[cells] | u32 kthr[n+2] | pad to 16 B | K3SegF[n+1]
+static size_t k3_tab_words(int n, int cells, int *off_kthr, int *off_segf)
+{
+    size_t w = (size_t) 8 * (n + 1) + (size_t) cells / 2;
+    if (off_kthr) *off_kthr = (int) w;
+    w += (size_t) n + 2;
+    w = (w + 3) & ~(size_t) 3;
+    if (off_segf) *off_segf = (int) w;
+    return w + (size_t) 4 * (n + 1);
+}
+static size_t k3_tab_doubles(int n, int cells) { return (k3_tab_words(n, cells, nullptr, nullptr) + 1) / 2; }
 static K3Params g_k3prm;
+static int g_k3_fm_double = FM_D9;         // series length the double passes may use with the current table
+static bool g_k3_f32_ok = false;           // the current table qualifies for the all-float pass over float grids
+static bool g_k3_multi = false;            // some lookup cell holds more than one knot: the segment search loops
 
 int k3_upload_table(int dims, double boxsize, const double *logkk, const double *ratio, int nbins, double norm)
 {
-    (void) dims;
     Ctx &c = ctx();
     const size_t nd_max = k3_tab_doubles(nbins, K3_MAX_CELLS);
     int rc = ensure_device_buffer((void **) &c.d_k3tab, &c.k3tab_cap, nd_max * sizeof(double));
@@ -410,11 +431,12 @@ int k3_upload_table(int dims, double boxsize, const double *logkk, const double 
     }
     seg[nbins].K2 = INFINITY; seg[nbins].inv = 0; seg[nbins].A = seg[nbins - 1].A; seg[nbins].B = 0;
     const double lo = log2(seg[0].K2), hi = log2(seg[nbins - 1].K2);
-    // cells narrow enough that (with the float-rounding guard) no cell sees two knots
+    // cells narrow enough that (with the float-rounding guard) no cell sees two knots; where the knots are closer than the
+    // finest cells (keff values are data-dependent means: nothing forbids it, and gsl_interp has no such limit) the
+    // segment search steps over the extra knots in a loop instead
     int cells = 1024;
     while (cells < K3_MAX_CELLS && (hi - lo) / cells * 1.05 >= min_gap) cells *= 2;
-    if ((hi - lo) / cells * 1.05 >= min_gap)
-        return set_error(KSN_EINVAL, "K3: table knots closer than %g in log2(k^2) are not supported", (hi - lo) / K3_MAX_CELLS * 1.05);
+    g_k3_multi = (hi - lo) / cells * 1.05 >= min_gap;
     const double scale = cells / (hi - lo);
     unsigned short *cell = (unsigned short *) (seg + nbins + 1);
     // cell[k] = last knot at or below the lower edge of cell k, minus a guard (0.02 cell) for the float log2 on the
@@ -428,10 +450,47 @@ int k3_upload_table(int dims, double boxsize, const double *logkk, const double 
         }
         for (; k < cells; k++) cell[k] = (unsigned short) (nbins - 1);
     }
+    if (g_k3_tab_copy.cap < nbins) {
+        free(g_k3_tab_copy.logkk); free(g_k3_tab_copy.ratio);
+        g_k3_tab_copy.logkk = (double *) malloc(sizeof(double) * nbins);
+        g_k3_tab_copy.ratio = (double *) malloc(sizeof(double) * nbins);
+        g_k3_tab_copy.cap = (g_k3_tab_copy.logkk && g_k3_tab_copy.ratio) ? nbins : 0;
+    }
+    g_k3_tab_copy.nbins = 0;
+    if (g_k3_tab_copy.cap >= nbins) {
+        memcpy(g_k3_tab_copy.logkk, logkk, sizeof(double) * nbins);
+        memcpy(g_k3_tab_copy.ratio, ratio, sizeof(double) * nbins);
+        g_k3_tab_copy.nbins = nbins; g_k3_tab_copy.norm = norm; g_k3_tab_copy.boxsize = boxsize;
+    }
+    int off_kthr, off_segf;
+    k3_tab_words(nbins, cells, &off_kthr, &off_segf);
+    unsigned *kthr = (unsigned *) c.h_k3tab + off_kthr;
+    K3SegF *segf = (K3SegF *) ((unsigned *) c.h_k3tab + off_segf);
+    // integer knot thresholds: for integer k2,  k2 >= K2_i  <=>  k2 >= ceil(K2_i)
+    for (int i = 0; i < nbins; i++) kthr[i] = seg[i].K2 >= 4294967295.0 ? 0xffffffffu : (unsigned) ceil(seg[i].K2);
+    kthr[nbins] = kthr[nbins + 1] = 0xffffffffu;
+    // how much arithmetic the table needs.  Narrow segments (u = k2/K2_i - 1 < 2^-5 over the whole segment) use a series
+    // for ln(1+u): to u^5 where |B| u_max^6 / 6 <= 1e-14 on every one of them (four orders below the 1e-10 bar), else to u^9.  The all-float pass over a
+    // float grid: error of delta = factor - 1 about 2^-23 (|B| (1 + 3 u) + |delta|), wanted below 2^-28.
+    double worst_d5 = 0, worst_f32 = 0;
+    for (int i = 0; i < nbins; i++) {
+        const double umax = i + 1 < nbins ? seg[i + 1].K2 * seg[i].inv - 1.0 : 0.0;
+        const double ab = fabs(seg[i].B);
+        if (umax < 0.03125) worst_d5 = fmax(worst_d5, ab * pow(umax, 6) / 6.0);
+        else worst_d5 = fmax(worst_d5, ab * pow(0.03125, 6) / 6.0);        // the part of a wide segment below the log1p switch
+        worst_f32 = fmax(worst_f32, ab * (1.0 + 3.0 * fmin(umax, 1.0)) + fabs(seg[i].A - 1.0) + ab * log1p(fmin(umax, 1e30)));
+        segf[i].inv = (float) seg[i].inv; segf[i].A1 = (float) (norm * ratio[i]); segf[i].B = (float) seg[i].B; segf[i].pad = 0;
+    }
+    segf[nbins] = segf[nbins - 1]; segf[nbins].B = 0; segf[nbins].inv = 0;
+    g_k3_fm_double = worst_d5 <= 1e-14 ? FM_D5 : FM_D9;
+    g_k3_f32_ok = worst_f32 <= 1.0 / 32 && 3.0 * (double) dims * dims / 4 < 16777216.0 && seg[0].K2 > 1e-30;
     g_k3prm.n = nbins;
     g_k3prm.cells = cells;
     g_k3prm.cell_lo = (float) lo;
     g_k3prm.cell_scale = (float) scale;
+    g_k3prm.off_kthr = off_kthr;
+    g_k3prm.off_segf = off_segf;
+    g_k3prm.multi = g_k3_multi ? 1 : 0;
     KSN_CUDA(cudaMemcpyAsync(c.d_k3tab, c.h_k3tab, k3_tab_doubles(nbins, cells) * sizeof(double), cudaMemcpyHostToDevice, c.stream));
     return KSN_OK;
 }
@@ -479,77 +538,100 @@ int k3_launch(void *dgrid, int real_bytes, int dims, long long plane0_global, lo
     if (nrows == 0) return KSN_OK;
     constexpr int U = 4;
     const int L = dims / 2 + 1;
-    const int cap = K3_TMA_THREADS * K3_EPT;                    // modes one CTA holds
+    const long long total = (long long) nrows * L;
+    const int cap = K3_TMA_THREADS * K3_EPT;                    // modes one 128-thread CTA holds
     const int segs = (L + cap - 1) / cap;                       // pieces per row when a row is longer than that (PMGRID > 2302)
-    const bool split_ok = segs == 1 || (!getenv("KSN_K3_NOSPLIT") && (long long) nrows * segs <= 0x7fffffffLL);
-    if (real_bytes == 8 && !getenv("KSN_K3_NOTMA") && split_ok) {   // bulk copies need 16-byte granules: double grids
-        // ~16 KB of grid per CTA: one row at PMGRID=2048 (7 CTAs per SM inside a 132 KB carve-out), half a row at 4096
-        const size_t row_bytes = (size_t) L * 2 * real_bytes;
-        int rpc = segs > 1 ? 1 : cap / L;
-        while (rpc > 1 && rpc * row_bytes > 18432) rpc--;
-        const int seg_len = (L + segs - 1) / segs;
-        const size_t smem = (segs > 1 ? (size_t) seg_len * 2 * real_bytes : rpc * row_bytes) + 128;
-        const int nct = segs > 1 ? nrows * segs : (nrows + rpc - 1) / rpc;
-        auto go = [&](auto kern) -> int {
-            KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-            KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 58));   // ~132 of 228 KB: L1 keeps the tables
-            kern<<<nct, K3_TMA_THREADS, smem, c.stream>>>((C2<double> *) dgrid, nrows, rpc, dims, plane0_global, c.d_k3tab, g_k3prm, gr, segs, seg_len);
-            return KSN_OK;
-        };
-        const char *flat = getenv("KSN_K3_FLAT");
-        if (segs == 1 && rpc > 1 && flat && atoi(flat) > 0 && ((uintptr_t) dgrid & 15) == 0) {
-            // several short rows per CTA: the flat-chunk kernel (opt-in until GPU-verified), same bytes per CTA
-            auto kern = k3_scale_tma_flat_kernel<double, K3_TMA_THREADS>;
-            KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-            KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 58));
-            kern<<<nct, K3_TMA_THREADS, smem, c.stream>>>((C2<double> *) dgrid, (long long) nrows * L, rpc * L, dims, plane0_global, c.d_k3tab, g_k3prm, gr);
-            snprintf(g_k3_last, sizeof g_k3_last, "k3_scale_tma_flat_kernel<double> (%d modes per CTA%s)", rpc * L, gr.on ? ", Green's function fused" : "");
-            c.launches++;
-            KSN_CUDA(cudaGetLastError());
-            return KSN_OK;
-        }
-        const int rcl = segs > 1 ? go(k3_scale_tma_kernel<double, true, true>)
-                      : rpc == 1 ? go(k3_scale_tma_kernel<double, true, false>) : go(k3_scale_tma_kernel<double, false, false>);
-        if (rcl) return rcl;
-        snprintf(g_k3_last, sizeof g_k3_last, "k3_scale_tma_kernel<double, %s> (%d row%s per CTA, %d piece%s per row%s)", segs > 1 ? "true, true" : rpc == 1 ? "true, false" : "false, false",
-                 rpc, rpc > 1 ? "s" : "", segs, segs > 1 ? "s" : "", gr.on ? ", Green's function fused" : "");
+    // KSN_K3_EXACT=1 (tests): always the 9-term double factor, whatever the table would allow
+    const bool exact = getenv("KSN_K3_EXACT") != nullptr;
+    // (the all-float factor only without the Green's function, whose range is not that of "1 + small")
+    const int fm = exact ? FM_D9 : (real_bytes == 4 && g_k3_f32_ok && !gr.on) ? FM_F32 : g_k3_fm_double;
+    static const char *const fm_name[] = { "series to u^9", "series to u^5", "factor in float" };
+    const char *gname = gr.on ? ", Green's function fused" : "";
+    const bool aligned = ((uintptr_t) dgrid & 15) == 0;
+    const bool bulk = !getenv("KSN_K3_NOTMA") && aligned;       // bulk copies need 16-byte granules
+    auto shared_cfg = [&](auto kern, size_t smem) -> int {
+        KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 58));   // ~132 of 228 KB: L1 keeps the tables
+        return KSN_OK;
+    };
+    auto done = [&]() -> int {
         c.launches++;
         KSN_CUDA(cudaGetLastError());
         return KSN_OK;
-    }
-    {
-        // float grids through bulk copies: opt-in until it has been through the GPU parity suite (see the kernel)
-        const long long total = (long long) nrows * L;
-        const char *f32tma = getenv("KSN_K3_F32_TMA");
-        if (real_bytes == 4 && f32tma && atoi(f32tma) > 0 && total % 2 == 0 && ((uintptr_t) dgrid & 15) == 0) {
-            const int capf = K3_FLAT_THREADS * K3_EPT, pair = 2 * L;
-            // whole row pairs (~16-18 KB of them) where a pair fits one CTA, else the largest even piece
-            const int chunk = pair <= capf ? pair * max(1, min(capf / pair, (int) (18432 / ((size_t) pair * 8)))) : (capf & ~1);
+    };
+    if (real_bytes == 8 && bulk && (segs == 1 || (!getenv("KSN_K3_NOSPLIT") && (long long) nrows * segs <= 0x7fffffffLL))) {
+        // ~16 KB of grid per CTA: one row at PMGRID = 2048 (7 CTAs per SM inside a 132 KB carve-out), half a row at 4096,
+        // several whole rows (as one flat chunk) where they are shorter
+        const size_t row_bytes = (size_t) L * 16;
+        int rpc = segs > 1 ? 1 : cap / L;
+        while (rpc > 1 && rpc * row_bytes > 18432) rpc--;
+        if (segs == 1 && rpc > 1) {
+            const int chunk = rpc * L;
+            const size_t smem = (size_t) chunk * 16 + 128;
             const long long nct = (total + chunk - 1) / chunk;
-            if (nct <= 0x7fffffffLL) {
-                const size_t smem = (size_t) chunk * 8 + 128;
-                auto kern = atoi(f32tma) >= 2 ? k3_scale_tma_flat_kernel<float, K3_FLAT_THREADS, true> : k3_scale_tma_flat_kernel<float, K3_FLAT_THREADS, false>;
-                KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-                KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 58));
-                kern<<<(unsigned) nct, K3_FLAT_THREADS, smem, c.stream>>>((C2<float> *) dgrid, total, chunk, dims, plane0_global, c.d_k3tab, g_k3prm, gr);
-                snprintf(g_k3_last, sizeof g_k3_last, "k3_scale_tma_flat_kernel<float> (%d modes per CTA%s)", chunk, gr.on ? ", Green's function fused" : "");
-                c.launches++;
-                KSN_CUDA(cudaGetLastError());
+            auto go = [&](auto kern) -> int {
+                int rc = shared_cfg(kern, smem);
+                if (rc) return rc;
+                kern<<<(unsigned) nct, K3_TMA_THREADS, smem, c.stream>>>((C2<double> *) dgrid, total, chunk, dims, plane0_global, c.d_k3tab, g_k3prm, gr);
                 return KSN_OK;
-            }
+            };
+            const int rc = fm == FM_D5 ? go(k3_scale_flat_kernel<double, K3_TMA_THREADS, FM_D5>) : go(k3_scale_flat_kernel<double, K3_TMA_THREADS, FM_D9>);
+            if (rc) return rc;
+            snprintf(g_k3_last, sizeof g_k3_last, "k3_scale_flat_kernel<double> (%d rows = %d modes per CTA, %s%s)", rpc, chunk, fm_name[fm], gname);
+            return done();
+        }
+        const int seg_len = (L + segs - 1) / segs;
+        const size_t smem = (size_t) (segs > 1 ? seg_len : L) * 16 + 128;
+        const int nct = nrows * segs;
+        auto go = [&](auto kern) -> int {
+            int rc = shared_cfg(kern, smem);
+            if (rc) return rc;
+            kern<<<nct, K3_TMA_THREADS, smem, c.stream>>>((C2<double> *) dgrid, dims, plane0_global, c.d_k3tab, g_k3prm, gr, segs, seg_len);
+            return KSN_OK;
+        };
+        const int rc = segs > 1 ? (fm == FM_D5 ? go(k3_scale_row_kernel<true, FM_D5>) : go(k3_scale_row_kernel<true, FM_D9>))
+                                : (fm == FM_D5 ? go(k3_scale_row_kernel<false, FM_D5>) : go(k3_scale_row_kernel<false, FM_D9>));
+        if (rc) return rc;
+        snprintf(g_k3_last, sizeof g_k3_last, "k3_scale_row_kernel<%s> (one row per CTA, %d piece%s per row, %s%s)", segs > 1 ? "split" : "whole",
+                 segs, segs > 1 ? "s" : "", fm_name[fm], gname);
+        return done();
+    }
+    if (real_bytes == 4 && bulk && total % 2 == 0) {
+        const int capf = K3_FLAT_THREADS * K3_EPT, pair = 2 * L;
+        // whole row pairs (~16-18 KB of them) where a pair fits one CTA, else the largest even piece
+        const int chunk = pair <= capf ? pair * max(1, min(capf / pair, (int) (18432 / ((size_t) pair * 8)))) : (capf & ~1);
+        const long long nct = (total + chunk - 1) / chunk;
+        if (nct <= 0x7fffffffLL) {
+            const size_t smem = (size_t) chunk * 8 + 128;
+            auto go = [&](auto kern) -> int {
+                int rc = shared_cfg(kern, smem);
+                if (rc) return rc;
+                kern<<<(unsigned) nct, K3_FLAT_THREADS, smem, c.stream>>>((C2<float> *) dgrid, total, chunk, dims, plane0_global, c.d_k3tab, g_k3prm, gr);
+                return KSN_OK;
+            };
+            const int rc = fm == FM_F32 ? go(k3_scale_flat_kernel<float, K3_FLAT_THREADS, FM_F32>)
+                         : fm == FM_D5 ? go(k3_scale_flat_kernel<float, K3_FLAT_THREADS, FM_D5>) : go(k3_scale_flat_kernel<float, K3_FLAT_THREADS, FM_D9>);
+            if (rc) return rc;
+            snprintf(g_k3_last, sizeof g_k3_last, "k3_scale_flat_kernel<float> (%d modes per CTA, %s%s)", chunk, fm_name[fm], gname);
+            return done();
         }
     }
-    // one CTA per ~1024 modes: a single row for large grids, several short rows otherwise
+    // plain loads and stores, one CTA per ~1024 modes: a single row for large grids, several short rows otherwise
     const int rows_per_cta = L >= K3_THREADS * U ? 1 : (K3_THREADS * U) / L;
     const int ctas = (nrows + rows_per_cta - 1) / rows_per_cta;
-    if (real_bytes == 8)
-        k3_scale_kernel<double, U><<<ctas, K3_THREADS, 0, c.stream>>>((C2<double> *) dgrid, nrows, rows_per_cta, dims, plane0_global, c.d_k3tab, g_k3prm, gr);
-    else
-        k3_scale_kernel<float, U><<<ctas, K3_THREADS, 0, c.stream>>>((C2<float> *) dgrid, nrows, rows_per_cta, dims, plane0_global, c.d_k3tab, g_k3prm, gr);
-    snprintf(g_k3_last, sizeof g_k3_last, "k3_scale_kernel<%s> (plain loads, %d row%s per CTA%s)", real_bytes == 8 ? "double" : "float", rows_per_cta, rows_per_cta > 1 ? "s" : "", gr.on ? ", Green's function fused" : "");
-    c.launches++;
-    KSN_CUDA(cudaGetLastError());
-    return KSN_OK;
+    auto go = [&](auto kern, auto *g) {
+        kern<<<ctas, K3_THREADS, 0, c.stream>>>(g, nrows, rows_per_cta, dims, plane0_global, c.d_k3tab, g_k3prm, gr);
+    };
+    if (real_bytes == 8) {
+        if (fm == FM_D5) go(k3_scale_kernel<double, U, FM_D5>, (C2<double> *) dgrid); else go(k3_scale_kernel<double, U, FM_D9>, (C2<double> *) dgrid);
+    } else {
+        if (fm == FM_F32) go(k3_scale_kernel<float, U, FM_F32>, (C2<float> *) dgrid);
+        else if (fm == FM_D5) go(k3_scale_kernel<float, U, FM_D5>, (C2<float> *) dgrid);
+        else go(k3_scale_kernel<float, U, FM_D9>, (C2<float> *) dgrid);
+    }
+    snprintf(g_k3_last, sizeof g_k3_last, "k3_scale_kernel<%s> (plain loads, %d row%s per CTA, %s%s)", real_bytes == 8 ? "double" : "float", rows_per_cta,
+             rows_per_cta > 1 ? "s" : "", fm_name[fm], gname);
+    return done();
 }
 
 // K3 over a host-resident slab, chunk by chunk, each chunk copied back to the host buffer as soon as it is scaled.
@@ -616,6 +698,17 @@ int k1_sums(const void *dgrid, const void *hgrid, int real_bytes, int dims, int 
 using namespace ksn;
 
 extern "C" const char *ksn_last_k3_kernel(void) { return g_k3_last; }
+
+extern "C" int ksn_last_k3_table(const double **logkk, const double **ratio, int *nbins, double *norm, double *boxsize)
+{
+    if (!g_k3_tab_copy.nbins) return set_error(KSN_EINVAL, "ksn_last_k3_table: no scaling pass yet");
+    if (logkk) *logkk = g_k3_tab_copy.logkk;
+    if (ratio) *ratio = g_k3_tab_copy.ratio;
+    if (nbins) *nbins = g_k3_tab_copy.nbins;
+    if (norm) *norm = g_k3_tab_copy.norm;
+    if (boxsize) *boxsize = g_k3_tab_copy.boxsize;
+    return KSN_OK;
+}
 
 static int check_table(const double *logkk, const double *ratio, int nbins, double norm)
 {

@@ -41,7 +41,7 @@ struct Ctx {
     double *d_cold = nullptr; size_t cold_cap = 0;         // per-warp bins below the bin window (k1_tile_kernel<.., true>)
     // geometry cache (global sums over all ranks)
     struct { bool valid = false; int dims = 0, nrbins = 0; long long startslab = 0, nslab = 0;
-             unsigned long long epoch = 0; double *keff = nullptr; long long *count = nullptr; size_t cap = 0; } geom;
+             unsigned long long epoch = 0, h_thr = 0; double *keff = nullptr; long long *count = nullptr; size_t cap = 0; } geom;
     // K3 workspace
     double *d_k3tab = nullptr; size_t k3tab_cap = 0; double *h_k3tab = nullptr; size_t h_k3tab_cap = 0;
     double *d_gz = nullptr; size_t gz_cap = 0;             // z factor of the fused Green's function (k3_set_greens)

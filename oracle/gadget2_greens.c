@@ -23,6 +23,7 @@
  *     }
  *     after the loop:  if (slabstart_y == 0) fft_of_rhogrid[0].re = fft_of_rhogrid[0].im = 0.0;
  */
+#define _GNU_SOURCE
 #include <math.h>
 #include <stddef.h>
 
@@ -54,4 +55,11 @@
 void orc_gadget2_greens(void *grid, int is_double, int PMGRID, long long slabstart_y, long long nslab_y, double asmth2)
 {
     if (is_double) { GREENS_LOOP(double) } else { GREENS_LOOP(float) }
+}
+
+/* the synthetic field of the benchmark, CPU restatement (synthetic_grid.h) */
+#include "synthetic_grid.h"
+void orc_fill_synthetic_grid(double *g, int N, long long startslab, long long nslab, unsigned long long seed, double slope)
+{
+    orc_fill_synthetic_slab(g, N, startslab, nslab, seed, slope);
 }

@@ -3,15 +3,24 @@
  *
  * Linked against the reference sources compiled unmodified from /root/reference plus the shims
  * (oracle/Makefile target _ref/ref_bench).  R forked ranks (mini-MPI) each own a slab that starts
- * where their slab of the full PMGRID^3 grid would start, but only P planes deep (bounded sample:
- * both grid passes are linear in the number of modes); the linear-response integral is replicated on
- * every rank exactly as in the reference and is timed in full, at a ~100-row stored history.
- * Phase boundaries come from the reference's own progress messages (ref_host.c records their time).
+ * where their slab of the full PMGRID^3 grid starts and is P planes deep: P = N/R is the whole
+ * slab (nothing extrapolated), a smaller P a bounded sample of it (both grid passes are linear in
+ * the number of modes).  The linear-response integral is replicated on every rank exactly as in
+ * the reference and is always timed in full, at a ~100-row stored history.  Phase boundaries come
+ * from the reference's own progress messages (ref_host.c records their time).
  *
- * usage: ref_bench N P R STEPS HYBRID TRANSFER_FILE
+ * The grid is the one bench.py's GPU arm fills its slabs with (ksn_fill_synthetic_grid,
+ * csrc/ksn_device.cu): the same counter-based generator keyed by (seed, global mode index), restated
+ * in oracle/synthetic_grid.h -- a Gaussian field with P(k) ~ k^slope, element (0,0,0) = N^3.  (Equal values up to the last
+ * bits of libm's log/sincos against the device's.)
+ *
+ * usage: ref_bench N P R STEPS HYBRID TRANSFER_FILE [WARMUP [BUDGET_S [m0 m1 m2]]]
+ *   WARMUP   untimed steps before the STEPS timed ones (default 1)
+ *   BUDGET_S > 0: after the first warm-up step the planes per rank are cut so that WARMUP+STEPS steps fit this many
+ *            seconds (never grown; the JSON says how many planes the timed steps used)
  * prints one JSON line on rank 0.
  */
-#define _GNU_SOURCE
+#include "synthetic_grid.h"
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -35,29 +44,31 @@ static double now(void)
     return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
 
-static unsigned long long mix(unsigned long long x)
-{
-    x += 0x9E3779B97F4A7C15ull;
-    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-    return x ^ (x >> 31);
-}
+#define SEED 20261017ull     /* host.DeviceGrid.fill_synthetic's default */
+#define SLOPE (-1.0)
 
 int main(int argc, char **argv)
 {
-    if (argc < 7) { fprintf(stderr, "usage: %s N P R STEPS HYBRID TRANSFER_FILE\n", argv[0]); return 2; }
-    const int N = atoi(argv[1]), P = atoi(argv[2]), R = atoi(argv[3]), steps = atoi(argv[4]), hybrid = atoi(argv[5]);
+    if (argc < 7) { fprintf(stderr, "usage: %s N P R STEPS HYBRID TRANSFER_FILE [WARMUP [BUDGET_S [m0 m1 m2]]]\n", argv[0]); return 2; }
+    const int N = atoi(argv[1]), R = atoi(argv[3]), steps = atoi(argv[4]), hybrid = atoi(argv[5]);
+    int P = atoi(argv[2]);
     const char *transfer = argv[6];
+    const int warmup = argc > 7 ? atoi(argv[7]) : 1;
+    const double budget = argc > 8 ? atof(argv[8]) : 0;
+    double mnu[3] = { 0.1, 0.1, 0.1 };
+    if (argc > 11) for (int i = 0; i < 3; i++) mnu[i] = atof(argv[9 + i]);
     const double UL = 3.085678e21, UT = UL / 1e5, BOX = 512000, OMEGA0 = 0.2793;
     const int L = N / 2 + 1;
-    double *times = ksn_minimpi_shared_alloc(sizeof(double) * 4 * (steps + 1));
+    const int total = warmup + steps;
+    double *times = ksn_minimpi_shared_alloc(sizeof(double) * 4 * (total + 1));
+    int *planes = ksn_minimpi_shared_alloc(sizeof(int) * (total + 1));
     const int rank = ksn_minimpi_fork(R);
     ThisTask = rank;
     ksn_ref_quiet = 2;                  /* record time stamps, print nothing */
     strncpy(kspace_params.KspaceTransferFunction, transfer, 499);
     kspace_params.TimeTransfer = 0.01;
     kspace_params.InputSpectrum_UnitLength_in_cm = UL * 1e3;
-    kspace_params.MNu[0] = kspace_params.MNu[1] = kspace_params.MNu[2] = 0.1;
+    for (int i = 0; i < 3; i++) kspace_params.MNu[i] = mnu[i];
     kspace_params.hybrid_neutrinos_on = hybrid;
     kspace_params.vcrit = 500;
     kspace_params.nu_crit_time = 0.333;
@@ -71,17 +82,9 @@ int main(int argc, char **argv)
     const size_t nel = (size_t) P * N * L;
     fftw_complex *grid = malloc(nel * sizeof(fftw_complex));
     if (!grid) { fprintf(stderr, "rank %d: cannot allocate %zu bytes\n", rank, nel * sizeof(fftw_complex)); ksn_minimpi_exit(1); return 1; }
-    for (size_t e = 0; e < nel; e++) {
-        const long long row = e / L, i = startslab + row / N;
-        const int z = (int) (e - row * L), j = (int) (row % N);
-        const double ki = i <= N / 2 ? i : i - N, kj = j <= N / 2 ? j : j - N;
-        const double k2 = ki * ki + kj * kj + (double) z * z;
-        const unsigned long long h = mix(20261017ull ^ mix((unsigned long long) ((i * N + j) * L + z)));
-        const double amp = k2 > 0 ? pow(k2, -0.25) : 0;       /* P(k) ~ 1/k */
-        grid[e].re = amp * (((h >> 11) & 0xfffff) / 524288.0 - 1.0);
-        grid[e].im = amp * (((h >> 31) & 0xfffff) / 524288.0 - 1.0);
-    }
-    if (rank == 0) { grid[0].re = (double) N * N * N; grid[0].im = 0; }
+    const double tg0 = now();
+    orc_fill_synthetic_slab((double *) grid, N, startslab, P, SEED, SLOPE);
+    const double t_gen = now() - tg0;
 
     /* first call: delta_tot_init at a = TimeTransfer (untimed) */
     add_nu_power_to_rhogrid(0.01, BOX, grid, N, (int) startslab, P, MPI_COMM_WORLD);
@@ -95,8 +98,10 @@ int main(int argc, char **argv)
         set_nu_state(sf, dt, nk, ia, MPI_COMM_WORLD);
         free(sf); free(dt);
     }
-    for (int s = 0; s <= steps; s++) {          /* s = 0 is a warm-up */
-        const double a = 0.98 + 0.001 * (s + 1);
+    /* every step advances a by less than 0.009 (the row is integrated in full but not kept: steady state), and a stays < 1 */
+    const double a0 = 0.98, da = fmin(0.001, (0.9995 - a0) / (total + 1));
+    for (int s = 0; s < total; s++) {
+        const double a = a0 + da * (s + 1);
         MPI_Barrier(MPI_COMM_WORLD);
         const double t0 = now();
         add_nu_power_to_rhogrid(a, BOX, grid, N, (int) startslab, P, MPI_COMM_WORLD);
@@ -106,13 +111,27 @@ int main(int argc, char **argv)
             times[4 * s + 1] = ksn_ref_t_mass - t0;                    /* K1 loop + all-reduce */
             times[4 * s + 2] = ksn_ref_t_nupower - ksn_ref_t_mass;     /* integral */
             times[4 * s + 3] = t1 - ksn_ref_t_nupower;                 /* scaling loop + barrier */
+            planes[s] = P;
+            /* after the first step: do the remaining ones fit the budget?  If not, fewer planes per rank from here on
+             * (decided by rank 0, read by all after the barrier below) */
+            planes[total] = P;
+            if (s == 0 && budget > 0 && (t1 - t0) * total > budget) {
+                const double grid_t = times[1] + times[3], fixed = times[2];
+                const double per_plane = grid_t / P, room = budget / total - fixed;
+                int p2 = room > 0 ? (int) (room / per_plane) : 1;
+                if (p2 < 1) p2 = 1;
+                if (p2 < P) planes[total] = p2;
+            }
         }
+        MPI_Barrier(MPI_COMM_WORLD);
+        P = planes[total];
     }
     if (rank == 0) {
-        printf("{\"N\": %d, \"P\": %d, \"R\": %d, \"nk\": %d, \"Na\": %d, \"steps\": [", N, P, R, delta_tot_table.nk, delta_tot_table.ia + 1);
-        for (int s = 1; s <= steps; s++)
-            printf("%s{\"total\": %.6f, \"k1\": %.6f, \"integral\": %.6f, \"k3\": %.6f}", s > 1 ? ", " : "",
-                   times[4 * s], times[4 * s + 1], times[4 * s + 2], times[4 * s + 3]);
+        printf("{\"N\": %d, \"P\": %d, \"P_full\": %d, \"R\": %d, \"nk\": %d, \"Na\": %d, \"warmup\": %d, \"gen_s\": %.3f, \"same_generator_as_gpu_arm\": true, \"steps\": [",
+               N, planes[total - 1], N / R, R, delta_tot_table.nk, delta_tot_table.ia + 1, warmup, t_gen);
+        for (int s = warmup; s < total; s++)
+            printf("%s{\"total\": %.6f, \"k1\": %.6f, \"integral\": %.6f, \"k3\": %.6f, \"planes\": %d}", s > warmup ? ", " : "",
+                   times[4 * s], times[4 * s + 1], times[4 * s + 2], times[4 * s + 3], planes[s]);
         printf("]}\n");
     }
     ksn_minimpi_exit(0);

@@ -320,6 +320,7 @@ def orc():
         "orc_dnudcdm": (D, [dp, dp, I, D, D]),
         "orc_scale_modes": (None, [V, I, I, LL, LL, D, dp, dp, I, D]),
         "orc_gadget2_greens": (None, [V, I, I, LL, LL, D]),
+        "orc_fill_synthetic_grid": (None, [dp, I, LL, LL, C.c_ulonglong, D]),
         "orc_dtot_alloc": (None, [tp, I, D, D, D, cp, D, D]),
         "orc_dtot_free": (None, [tp]),
         "orc_dtot_read": (I, [tp, C.c_char_p]),

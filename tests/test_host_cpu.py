@@ -224,11 +224,13 @@ def test_k1_tile_plan_for_the_named_grids(monkeypatch):
         assert L.ksn_k1_tile_plan_ex(n, n // 2, 232448, 148, 4, *[C.byref(x) for x in v]) == 1
         return tuple(x.value for x in v)
 
-    # float rows (opt-in KSN_K1_F32_TILE): stages are half as large, so more warps fit beside the bins
-    assert plan_f32(2048) == (15, 9, 2, 4, 0)
-    assert plan_f32(4096) == (8, 17, 4, 4, 1056)
-    monkeypatch.setenv("KSN_K1_TILE", "8,33,2")                # a whole 2048 float row as ONE tile (compile-time chunk of 33)
+    # float rows: issue-bound, so eight warps and the longest chunk -- a whole 2048 float row as ONE tile (compile-time
+    # chunk of 33; measured 5.57 TB/s at 2048^3 against 4.10 for 15 warps x 9 modes, profiles/r2_optin_timings.txt)
     assert plan_f32(2048) == (8, 33, 2, 1, 0)
+    assert plan_f32(1024) == (8, 17, 4, 1, 0)
+    assert plan_f32(4096) == (8, 17, 4, 4, 1056)
+    monkeypatch.setenv("KSN_K1_TILE", "15,9,2")
+    assert plan_f32(2048) == (15, 9, 2, 4, 0)
     monkeypatch.setenv("KSN_K1_TILE", "4,9,3")
     assert plan(256)[:3] == (4, 9, 3)
 

@@ -303,3 +303,20 @@ def test_bin_window_kernel_agrees_at_pmgrid_4096(gpu, monkeypatch):
         np.testing.assert_allclose(win[0][live], plain[0][live], rtol=2e-13)
         np.testing.assert_allclose(win[0][live], pair[0][live], rtol=2e-13)
         np.testing.assert_allclose(win[0][live], first[0][live], rtol=2e-13)
+
+
+@pytest.mark.parametrize("n,start,nslab", [(32, 0, 32), (2048, 1023, 2)])
+def test_synthetic_grid_equals_the_cpu_generator_of_the_reference_arm(gpu, n, start, nslab):
+    """bench.py's GPU arm fills its slabs with ksn_fill_synthetic_grid; the reference's CPU arm (oracle/ref_bench.c) with
+    the restatement in oracle/synthetic_grid.h -- the same counter-based field, equal up to the last bits of log/sincos."""
+    from kspace_neutrinos_b200 import capi
+    want = np.zeros((nslab, n, n // 2 + 1, 2))
+    refs.orc().orc_fill_synthetic_grid(refs.dptr(want), n, start, nslab, 20261017, -1.0)
+    d = refs.DeviceBuffer(gpu, want)
+    capi.check(gpu.ksn_fill_synthetic_grid(d.ptr, 8, n, start, nslab, 20261017, -1.0))
+    got = d.download(want)
+    d.free()
+    if start == 0:
+        assert got[0, 0, 0, 0] == float(n) ** 3 and got[0, 0, 0, 1] == 0
+    scale = np.hypot(want[..., 0], want[..., 1])[..., None] + 1e-300
+    assert np.max(np.abs(got - want) / scale) < 1e-13

@@ -1,8 +1,8 @@
-"""Index arithmetic of the opt-in float-grid kernels, restated in Python and checked against direct enumeration (CPU, no
-GPU): the kernels themselves have not run on a B200 yet (tests/test_zz_optin_gpu.py does that), but the part of them that
-is pure integer logic -- which bytes a bulk copy covers, where a thread finds its mode -- can be pinned here.
+"""Index arithmetic of the float-grid kernels, restated in Python and checked against direct enumeration (CPU, no GPU):
+the kernels themselves are tested on the GPU (tests/test_promoted_kernels_gpu.py); the part of them that is pure integer
+logic -- which bytes a bulk copy covers, where a thread finds its mode -- is pinned here.
 
-* k3_scale_tma_flat_kernel (csrc/k3_scale.cu): the slab is cut into flat chunks of an even mode count; a thread derives
+* k3_scale_flat_kernel (csrc/k3_scale.cu): the slab is cut into flat chunks of an even mode count; a thread derives
   (plane, row, z) of mode e of its chunk from the chunk's first mode.
 * k1_tile_kernel<float, ..> (csrc/k1_powerspec.cu): a tile of an odd float row starts 8 bytes off the 16-byte granule of
   cp.async.bulk; it is copied from one mode earlier and to an even mode count, and lane l reads its chunk `sh` modes into

@@ -1,11 +1,9 @@
-"""Opt-in kernels written after round 1's GPU minutes were spent (float grids -- K3: KSN_K3_F32_TMA=1, flat bulk-copy
-chunks; K1: KSN_K1_F32_TILE=1, the tile kernel on float rows; the K1 bin window with a bin's home chosen per tile,
-KSN_K1_WIN=3; K2 with one k bin per thread-block cluster, KSN_K2_CLUSTER=2|3|4; K3's flat-chunk kernel on double grids,
-KSN_K3_FLAT=1; the collective bootstrap of the -DKSN_HAVE_MPI host layer on two GPUs).  They have NOT run on a B200 yet, so these tests are skipped unless
-KSN_TEST_UNVERIFIED=1 (tools/gpu_round2_check.sh sets it); the default float path stays the verified one until then.
-Each test compares the opt-in kernel with the numpy restatement / the reference AND, bit for bit where the arithmetic is
-the same, with the default float kernel.  Also here, for the same reason: odd PMGRID on the device (default kernels, a
-case the GPU suite did not cover in round 1)."""
+"""Kernels that were written at the end of round 1 and verified on a B200 at the start of round 2 (profiles/r2_optin_*):
+float grids through the bulk-copy kernels (K1: the tile kernel on float rows; K3: flat chunks, with the factor in float
+where the table allows it), K3's flat-chunk kernel on double grids with short rows, odd PMGRID on the device, the
+collective bootstrap of the -DKSN_HAVE_MPI host layer on two GPUs.  Each bulk-copy kernel is compared with the numpy
+restatement / the reference AND, bit for bit where the arithmetic is the same, with the plain-load kernel that the
+library keeps as the fall-back (KSN_K1_PAIR=1, KSN_K3_NOTMA=1)."""
 import ctypes as C
 import os
 
@@ -14,8 +12,7 @@ import pytest
 
 from tests import refs
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("KSN_TEST_UNVERIFIED") != "1", reason="opt-in kernels: set KSN_TEST_UNVERIFIED=1")]
+pytestmark = pytest.mark.gpu
 
 
 def _table(n, box, nk=40, seed=0):
@@ -48,19 +45,21 @@ class _env:
 @pytest.mark.parametrize("n,start,nslab", [(4, 0, 4), (6, 0, 6), (64, 0, 64), (64, 5, 17), (126, 120, 6), (256, 0, 256), (2048, 1000, 6), (4096, 3000, 2)])
 def test_k3_float_bulk_copy_kernel_equals_the_plain_float_kernel(gpu, n, start, nslab):
     """Same factor arithmetic, same narrowing to float: the two kernels must agree bit for bit; and with numpy to the
-    float-grid tolerance."""
+    float-grid tolerance.  (This table is far too steep for the all-float factor: both kernels evaluate it in double.)"""
     from kspace_neutrinos_b200 import capi
     box = refs.BOX
     rng = np.random.default_rng(n + start)
     g = rng.standard_normal((nslab, n, n // 2 + 1, 2)).astype(np.float32)
     logkk, ratio, norm = _table(n, box, nk=min(40, max(3, n // 2)))
     outs = []
-    for knob in (None, "1"):
-        with _env(KSN_K3_F32_TMA=knob):
+    for knob in ("1", None):
+        with _env(KSN_K3_NOTMA=knob):
             d = refs.DeviceBuffer(gpu, g)
             capi.check(gpu.ksn_scale_modes(d.ptr, 4, n, start, nslab, box, refs.dptr(logkk), refs.dptr(ratio), len(logkk), norm))
             outs.append(d.download(g))
             d.free()
+            assert (b"plain loads" if knob else b"k3_scale_flat_kernel<float>") in gpu.ksn_last_k3_kernel(), gpu.ksn_last_k3_kernel()
+            assert b"factor in float" not in gpu.ksn_last_k3_kernel()
     np.testing.assert_array_equal(outs[1], outs[0])
     if n <= 256:
         np.testing.assert_allclose(outs[1], refs.k3_numpy(g, start, box, logkk, ratio, norm), rtol=1e-5, atol=0)
@@ -76,8 +75,8 @@ def test_k3_float_bulk_copy_kernel_with_the_greens_function(gpu):
     iw = capi.c_double_p()
     assert gpu.ksn_bin_tables(n, n // 2, C.byref(thr), C.byref(iw)) == 0
     outs = []
-    for knob in (None, "1"):
-        with _env(KSN_K3_F32_TMA=knob):
+    for knob in ("1", None):
+        with _env(KSN_K3_NOTMA=knob):
             d = refs.DeviceBuffer(gpu, g)
             capi.check(gpu.ksn_scale_modes_greens(d.ptr, 4, n, 0, n, box, refs.dptr(logkk), refs.dptr(ratio), len(logkk), norm, iw, asmth2))
             outs.append(d.download(g))
@@ -88,21 +87,20 @@ def test_k3_float_bulk_copy_kernel_with_the_greens_function(gpu):
 
 @pytest.mark.parametrize("n,nrbins", [(8, 4), (64, 32), (96, 48), (128, 64), (256, 128)])
 def test_k1_float_tile_kernel_matches_the_pair_kernel_and_the_reference(gpu, n, nrbins):
-    """K1 on float rows through the tile kernel: counts bit-exact, power within the north star's float-grid tolerance of
-    the reference's float build, and within 3e-6 of the default float kernel (the tile kernel does not reproduce the
-    reference's float roundings of the window product, the pair kernel does)."""
+    """K1 on float rows through the tile kernel (default): counts bit-exact, power within the north star's float-grid
+    tolerance of the reference's float build, and within 3e-6 of the scan-based float kernel (the tile kernel does not
+    reproduce the reference's float roundings of the window product, the pair kernel does)."""
     g = refs.random_grid(n, seed=n + 1, dtype=np.float32)
     res = {}
-    for knob in (None, "1"):
-        with _env(KSN_K1_F32_TILE=knob):
+    for knob in ("1", None):
+        with _env(KSN_K1_PAIR=knob):
             d = refs.DeviceBuffer(gpu, g)
             refs.total_powerspectrum(gpu, g, nrbins, fn="total_powerspectrum_f32", pointer=d.ptr)      # first sweep: geometry
             res[knob] = refs.total_powerspectrum(gpu, g, nrbins, fn="total_powerspectrum_f32", pointer=d.ptr)
             name = gpu.ksn_last_k1_kernel()
             d.free()
-            if knob:
-                assert b"k1_tile_kernel" in name and b"float" in name, name
-    (n0, p0, c0, k0), (n1, p1, c1, k1) = res[None], res["1"]
+            assert (b"k1_pair_kernel<float>" in name) if knob else (b"k1_tile_kernel<float>" in name), name
+    (n0, p0, c0, k0), (n1, p1, c1, k1) = res["1"], res[None]
     assert n0 == n1 and np.array_equal(c0[:n0], c1[:n1])
     np.testing.assert_array_equal(k1[:n1], k0[:n0])
     np.testing.assert_allclose(p1[:n1], p0[:n0], rtol=3e-6)
@@ -122,8 +120,8 @@ def test_k1_float_tile_kernel_on_odd_slab_offsets_and_thin_slabs(gpu):
         sub = rng.standard_normal((nslab, n, n // 2 + 1, 2)).astype(np.float32)
         nrbins = n // 2
         out = {}
-        for knob in (None, "1"):
-            with _env(KSN_K1_F32_TILE=knob):
+        for knob in ("1", None):
+            with _env(KSN_K1_PAIR=knob):
                 class G:                                    # _sums slices g[start:start+nslab] and reads g.shape[1], g.dtype
                     shape = (start + nslab, n, n // 2 + 1, 2)
                     dtype = sub.dtype
@@ -133,13 +131,13 @@ def test_k1_float_tile_kernel_on_odd_slab_offsets_and_thin_slabs(gpu):
                 _sums(gpu, G(), nrbins, start, nslab)       # first call per geometry
                 out[knob] = _sums(gpu, G(), nrbins, start, nslab)
         assert np.array_equal(out[None][2], out["1"][2])
-        np.testing.assert_allclose(out["1"][0], out[None][0], rtol=3e-6)
+        np.testing.assert_allclose(out[None][0], out["1"][0], rtol=3e-6)
 
 
 @pytest.mark.parametrize("n,nrbins", [(5, 4), (9, 8), (15, 7), (33, 16)])
 def test_odd_pmgrid_double_matches_the_reference(gpu, n, nrbins):
     """Odd PMGRID (legal, if unusual: the reference then counts the z = dims/2 column once, powerspectrum.c:70-78).  The
-    CPU side is pinned in tests/test_host_cpu.py; this is the device side, not yet run on a B200 -- hence in this file."""
+    CPU side is pinned in tests/test_host_cpu.py; this is the device side."""
     ref = refs.ref_lib(True)
     if ref is None:
         pytest.skip("oracle/_ref not built")
@@ -159,68 +157,11 @@ def test_odd_pmgrid_double_matches_the_reference(gpu, n, nrbins):
     np.testing.assert_allclose(got, refs.k3_numpy(g, 0, refs.BOX, logkk, ratio, norm), rtol=1e-10, atol=0)
 
 
-@pytest.mark.parametrize("n,start,nslab", [(256, 0, 256), (256, 100, 7), (512, 0, 40), (4096, 0, 6), (4096, 2040, 12)])
-def test_k1_bin_window_with_the_home_chosen_per_tile_is_bit_identical(gpu, n, start, nslab):
-    """KSN_K1_WIN=3 / 4 (k1_tile_kernel<.., 2>): same bins, same update order as the window kernel that chooses per update
-    (KSN_K1_WIN=1 / 2, verified in round 1) -- the sums must be bit-identical.  Small grids force a quarter-size window
-    (values 2 / 4); slabs at 4096 include the one with the k_x = k_y = 0 axis, whose rows reach the cold bins."""
-    from kspace_neutrinos_b200 import capi
-    from tests.test_k1_gpu import _sums
-    nrbins = n // 2
-    ptr = C.c_void_p()
-    capi.check(gpu.ksn_device_malloc(C.byref(ptr), nslab * n * (n // 2 + 1) * 16))
-    capi.check(gpu.ksn_fill_synthetic_grid(ptr, 8, n, start, nslab, 13, -1.0))
-    shape = np.empty((nslab, n, 1, 1))
-    _sums(gpu, shape, nrbins, start, nslab, pointer=ptr)                 # geometry
-    per_update, per_tile = ("2", "4") if n < 4096 else ("1", "3")
-    with _env(KSN_K1_WIN=per_update):
-        a = _sums(gpu, shape, nrbins, start, nslab, pointer=ptr)
-        assert b"in shared memory" in gpu.ksn_last_k1_kernel() and b"per tile" not in gpu.ksn_last_k1_kernel()
-    with _env(KSN_K1_WIN=per_tile):
-        b = _sums(gpu, shape, nrbins, start, nslab, pointer=ptr)
-        assert b"home chosen per tile" in gpu.ksn_last_k1_kernel(), gpu.ksn_last_k1_kernel()
-        b2 = _sums(gpu, shape, nrbins, start, nslab, pointer=ptr)
-    gpu.ksn_device_free(ptr)
-    np.testing.assert_array_equal(b[0], a[0])
-    np.testing.assert_array_equal(b2[0], b[0])
-    assert np.array_equal(a[2], b[2]) and a[3] == b[3]
-
-
-@pytest.mark.parametrize("hybrid", [True, False])
-@pytest.mark.parametrize("masses", [(0.1, 0.1, 0.1), (0.2, 0.1, 0.3)])
-def test_k2_one_bin_per_cluster_is_bit_identical(gpu, masses, hybrid):
-    """k2_delta_nu_cluster_kernel<M> (KSN_K2_CLUSTER=2|3|4): the M groups of a speculative pass are the M CTAs of a
-    thread-block cluster, the interval list sits in CTA 0's shared memory.  Same arithmetic and the same replay as the
-    one-CTA kernels, so delta_nu, the rule count and the table row count must equal the sequential kernel's bit for bit."""
-    from tests.test_k2_gpu import _benchmark_state
-    om = refs.make_omnu(gpu, masses)
-    if hybrid:
-        gpu.init_hybrid_nu(C.byref(om.hybnu), (C.c_double * 3)(*masses), 500.0, 2.99792458e10 / 1e5, 0.333, om.kBtnu)
-    refs.set_background(gpu, om)
-    runs = {}
-    for cl in (0, 2, 3, 4):
-        with _env(KSN_K2_SPEC="1", KSN_K2_CLUSTER=str(cl) if cl else None):
-            d, kk, dcdm, tr = _benchmark_state(gpu, om)
-            outs = []
-            for a in (0.981, 0.982, 0.9915):
-                g = np.zeros(len(kk))
-                gpu.get_delta_nu_update(C.byref(d), a, len(kk), refs.dptr(kk), refs.dptr(dcdm), refs.dptr(g), C.byref(tr))
-                outs.append((g.copy(), gpu.ksn_last_k2_max_passes(), gpu.ksn_last_k2_max_trips(), d.ia))
-            runs[cl] = outs
-    if hybrid:
-        assert max(p for _, p, _, _ in runs[0]) > 60
-    for cl in (2, 3, 4):
-        for (g1, p1, t1, ia1), (gm, pm, tm, iam) in zip(runs[0], runs[cl]):
-            assert ia1 == iam and p1 == pm, (cl, p1, pm)
-            assert np.array_equal(g1, gm), (cl, float(np.max(np.abs(gm / g1 - 1))))
-            assert tm <= t1                       # fewer passes through the integrand than sequential bisections
-
-
 @pytest.mark.parametrize("n,start,nslab,greens", [(4, 0, 4, False), (64, 0, 64, False), (64, 7, 9, True), (96, 0, 96, False), (256, 0, 256, True),
                                                    (1024, 500, 8, False), (1024, 0, 3, True)])
 def test_k3_flat_chunk_kernel_on_double_grids_with_short_rows_is_bit_identical(gpu, n, start, nslab, greens):
-    """KSN_K3_FLAT=1: where several rows share a CTA (PMGRID <= 1150) the flat-chunk kernel finds row and z of a mode
-    without a division per mode.  Same factor arithmetic as k3_scale_tma_kernel<double, false, false>: bit-identical."""
+    """Where several rows share a CTA (PMGRID <= 1150) the flat-chunk kernel finds row and z of a mode without a division
+    per mode.  Same factor arithmetic as the plain-load kernel: bit-identical."""
     from kspace_neutrinos_b200 import capi
     box = refs.BOX
     rng = np.random.default_rng(3 * n + start)
@@ -231,8 +172,8 @@ def test_k3_flat_chunk_kernel_on_double_grids_with_short_rows_is_bit_identical(g
     assert gpu.ksn_bin_tables(n, n // 2, C.byref(thr), C.byref(iw)) == 0
     asmth2 = (2 * np.pi * 1.25 / n) ** 2
     outs = []
-    for knob in (None, "1"):
-        with _env(KSN_K3_FLAT=knob):
+    for knob in ("1", None):
+        with _env(KSN_K3_NOTMA=knob):
             d = refs.DeviceBuffer(gpu, g)
             if greens:
                 capi.check(gpu.ksn_scale_modes_greens(d.ptr, 8, n, start, nslab, box, refs.dptr(logkk), refs.dptr(ratio), len(logkk), norm, iw, asmth2))
@@ -240,6 +181,7 @@ def test_k3_flat_chunk_kernel_on_double_grids_with_short_rows_is_bit_identical(g
                 capi.check(gpu.ksn_scale_modes(d.ptr, 8, n, start, nslab, box, refs.dptr(logkk), refs.dptr(ratio), len(logkk), norm))
             outs.append(d.download(g))
             d.free()
+            assert (b"plain loads" if knob else b"k3_scale_flat_kernel<double>") in gpu.ksn_last_k3_kernel(), gpu.ksn_last_k3_kernel()
     np.testing.assert_array_equal(outs[1], outs[0])
     if not greens and n <= 256:
         np.testing.assert_allclose(outs[1], refs.k3_numpy(g, start, box, logkk, ratio, norm), rtol=1e-10, atol=0)
@@ -283,22 +225,97 @@ def test_mpi_build_picks_its_collective_on_two_gpus(gpu, comm, tmp_path):
     np.testing.assert_allclose(res[2][3], res[1][3], rtol=1e-10)
 
 
-@pytest.mark.parametrize("n,start,nslab", [(64, 0, 64), (256, 0, 256), (2048, 1000, 4)])
-def test_k3_float_short_series_factor_stays_within_one_float_rounding(gpu, n, start, nslab):
-    """KSN_K3_F32_TMA=2: ln(1+u) stops at u^4 for the narrow bins (truncation <= 7e-9 of a small correction term) -- the
-    factor then differs from the full one by far less than the float rounding of the product, so results agree with the
-    default float kernel to one float ulp, and mostly bit for bit."""
+def _smooth_table(n, box, nk=None, seed=1, jitter=0.002):
+    """A table like the one a PM step produces: one knot per P(k) bin (logarithmic bins, as narrow as the grid's own:
+    u_max ~ 1.5 % at PMGRID 2048), delta_nu/delta_cdm falling smoothly with k plus a per-bin jitter, small norm."""
+    rng = np.random.default_rng(seed)
+    nk = nk or n // 2
+    kmin, kmax = 2 * np.pi / box, np.sqrt(3) * (n / 2) * 2 * np.pi / box
+    logkk = np.linspace(np.log(kmin * 1.1), np.log(kmax * 0.97), nk)
+    ratio = 0.9 / (1 + (np.exp(logkk) / np.exp(logkk[nk // 3])) ** 2) * (1 + jitter * rng.standard_normal(nk))
+    return logkk, ratio, 0.0073
+
+
+@pytest.mark.parametrize("n,start,nslab", [(2048, 0, 2), (2048, 1023, 2), (4096, 2047, 1), (1024, 100, 4), (256, 0, 256)])
+def test_k3_short_series_for_smooth_tables_equals_the_full_series(gpu, n, start, nslab):
+    """k3_upload_table lets the double passes stop ln(1+u) at u^5 where |B| u_max^6 / 6 <= 1e-14 on every narrow segment
+    (four FP64 instructions less per mode; the bins of PMGRID >= 2048 are that narrow): against KSN_K3_EXACT=1 (always to
+    u^9) the corrected modes may differ by 1e-14 of their value, and against the oracle's restatement of
+    interface_gadget.c:163-188 they hold the 1e-10 bar."""
     from kspace_neutrinos_b200 import capi
     box = refs.BOX
-    rng = np.random.default_rng(n + 17)
+    rng = np.random.default_rng(n + start)
+    g = rng.standard_normal((nslab, n, n // 2 + 1, 2))
+    logkk, ratio, norm = _smooth_table(n, box)
+    outs = {}
+    for knob in ("1", None):
+        with _env(KSN_K3_EXACT=knob):
+            d = refs.DeviceBuffer(gpu, g)
+            capi.check(gpu.ksn_scale_modes(d.ptr, 8, n, start, nslab, box, refs.dptr(logkk), refs.dptr(ratio), len(logkk), norm))
+            outs[knob] = d.download(g)
+            d.free()
+            name = gpu.ksn_last_k3_kernel()
+            if knob:
+                assert b"series to u^9" in name, name
+            elif n >= 2048:
+                assert b"series to u^5" in name, name
+    np.testing.assert_allclose(outs[None], outs["1"], rtol=3e-14, atol=0)
+    want = g.copy()
+    refs.orc().orc_scale_modes(want.ctypes.data_as(C.c_void_p), 1, n, start, nslab, box, refs.dptr(logkk), refs.dptr(ratio), len(logkk), norm)
+    np.testing.assert_allclose(outs[None], want, rtol=1e-10, atol=0)
+    assert not np.array_equal(want, g)
+
+
+@pytest.mark.parametrize("n,start,nslab", [(2048, 0, 2), (2048, 1023, 4), (4096, 2047, 2), (1024, 100, 4), (256, 0, 256), (64, 0, 64)])
+def test_k3_float_grids_with_the_factor_in_float(gpu, n, start, nslab):
+    """Float grids, smooth table (|B| <= 1/64, |norm ratio| <= 1/32): the factor - 1 is evaluated in float and applied as
+    fmaf(x, delta, x) -- no FP64 instruction in the pass.  Against the double evaluation (KSN_K3_EXACT=1) the corrected
+    modes agree to one float rounding and mostly bit for bit; against the oracle (float build) to the float-grid tolerance."""
+    from kspace_neutrinos_b200 import capi
+    box = refs.BOX
+    rng = np.random.default_rng(n + 7 * start)
     g = rng.standard_normal((nslab, n, n // 2 + 1, 2)).astype(np.float32)
-    logkk, ratio, norm = _table(n, box, nk=min(40, max(3, n // 2)))
-    outs = []
-    for knob in (None, "2"):
-        with _env(KSN_K3_F32_TMA=knob):
+    logkk, ratio, norm = _smooth_table(n, box)
+    outs = {}
+    for knob in ("1", None):
+        with _env(KSN_K3_EXACT=knob):
             d = refs.DeviceBuffer(gpu, g)
             capi.check(gpu.ksn_scale_modes(d.ptr, 4, n, start, nslab, box, refs.dptr(logkk), refs.dptr(ratio), len(logkk), norm))
-            outs.append(d.download(g))
+            outs[knob] = d.download(g)
             d.free()
-    np.testing.assert_allclose(outs[1], outs[0], rtol=1.3e-7, atol=0)
-    assert np.mean(outs[1] == outs[0]) > 0.9
+            name = gpu.ksn_last_k3_kernel()
+            assert (b"factor in float" in name) == (knob is None), name
+    np.testing.assert_allclose(outs[None], outs["1"], rtol=1.3e-7, atol=0)
+    assert np.mean(outs[None] == outs["1"]) > 0.9
+    want = g.copy()
+    refs.orc().orc_scale_modes(want.ctypes.data_as(C.c_void_p), 0, n, start, nslab, box, refs.dptr(logkk), refs.dptr(ratio), len(logkk), norm)
+    np.testing.assert_allclose(outs[None], want, rtol=1e-5, atol=0)
+    # the plain-load kernel takes the same path: bit-identical
+    with _env(KSN_K3_NOTMA="1"):
+        d = refs.DeviceBuffer(gpu, g)
+        capi.check(gpu.ksn_scale_modes(d.ptr, 4, n, start, nslab, box, refs.dptr(logkk), refs.dptr(ratio), len(logkk), norm))
+        plain = d.download(g)
+        d.free()
+        assert b"plain loads" in gpu.ksn_last_k3_kernel() and b"factor in float" in gpu.ksn_last_k3_kernel()
+    np.testing.assert_array_equal(plain, outs[None])
+
+
+def test_k3_tables_with_knots_closer_than_the_finest_lookup_cells(gpu):
+    """keff values are data-dependent means; nothing keeps two of them apart, and gsl_interp has no minimum spacing
+    (delta_pow.c:19-37).  Knots closer than (range)/16384 in log2(k^2) used to be rejected; now the segment search steps
+    over them."""
+    from kspace_neutrinos_b200 import capi
+    n, box = 128, refs.BOX
+    rng = np.random.default_rng(5)
+    g = rng.standard_normal((n, n, n // 2 + 1, 2))
+    logkk, ratio, norm = _table(n, box, nk=30)
+    # three pairs of nearly coincident knots, one of them straddling an integer k^2
+    logkk = np.sort(np.concatenate([logkk, logkk[[5, 11, 20]] + np.array([1e-9, 3e-7, 1e-12])]))
+    ratio = 0.2 + 0.6 * rng.random(len(logkk))
+    d = refs.DeviceBuffer(gpu, g)
+    capi.check(gpu.ksn_scale_modes(d.ptr, 8, n, 0, n, box, refs.dptr(logkk), refs.dptr(ratio), len(logkk), norm))
+    got = d.download(g)
+    d.free()
+    want = g.copy()
+    refs.orc().orc_scale_modes(want.ctypes.data_as(C.c_void_p), 1, n, 0, n, box, refs.dptr(logkk), refs.dptr(ratio), len(logkk), norm)
+    np.testing.assert_allclose(got, want, rtol=1e-10, atol=0)

@@ -27,7 +27,7 @@ def k3():
 k1()
 for _ in range(4): k3(); k1()          # geometry cache, clocks settled
 ref = None
-for win in ("0", "1", "3"):          # off / home of a bin chosen per update / per tile (opt-in kernel)
+for win in ("0", "1"):               # bin window off / on
     os.environ["KSN_K1_WIN"] = win
     ts = []
     for _ in range(6): k3(); ts.append(k1())

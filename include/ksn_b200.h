@@ -191,8 +191,31 @@ int ksn_set_background(ksn_hubble_fn hub, void *user, double loga_lo, double log
 /* how the last table came out: cells whose 4-point interpolant missed the host function (kinks in H(a), e.g. the
  * spline/series switch of Omega_nu, omega_nu_single.c:180-199) and the refined patches that cover them */
 int ksn_background_info(int *npatch, int *flagged_cells);
+/* 1 while a table from ksn_set_background lives on the device (0 after ksn_shutdown: callers that cache "already set" must ask) */
+int ksn_background_loaded(void);
 /* device fslength (same table), for tests: light * int_{logai}^{logaf} dloga /(a^2 H) */
 int ksn_fslength_device(const double *logai, int n, double logaf, double light, double *out);
+
+/* ---- slab-decomposed FFT of the PM grid, device resident -----------------------------------------
+ * Replaces, for a GPU-resident PM code, the transform in front of the hook in Gadget-2's pmforce_periodic
+ * (gadget-2/0002 patch:116):  rfftwnd_mpi(fft_forward_plan, 1, rhogrid, workspace, FFTW_TRANSPOSED_ORDER).
+ *   real space (in):  x-slabs  rho[x - slabstart_x][y][z], rows padded to 2 (N/2+1) doubles (FFTW's in-place r2c layout)
+ *   k space (out):    y-slabs  F[y - slabstart_y][x][kz], kz = 0..N/2 complex -- the slab add_nu_power_to_rhogrid takes
+ * Slabs are FFTW2's: contiguous, as even as possible, the first ranks take the extra planes.  Unnormalised, like FFTW.
+ * 2-D r2c per x plane (cuFFT, loaded with dlopen) -> ONE kernel that transposes x <-> y while it writes every row into
+ * the k-space slab of the GPU that owns it, over NVLink peer memory (no pack / all-to-all / unpack passes) -> 1-D c2c
+ * along x.  More than one rank needs the peer-memory collective (ksn_comm_p2p_init) on the same ranks: its flag protocol
+ * fences the exchange.  Call order: ksn_fft_plan, allocate both buffers with ksn_device_malloc (sizes: ksn_fft_layout),
+ * ksn_fft_export on every rank, gather the 128-byte handles in rank order, ksn_fft_attach; then any number of
+ * ksn_fft_forward / ksn_fft_inverse (collective, in place: the input buffer is overwritten). */
+int ksn_fft_plan(int dims, int nranks, int rank);
+int ksn_fft_layout(long long *slabstart_x, long long *nslab_x, long long *slabstart_y, long long *nslab_y,
+                   size_t *real_bytes_padded, size_t *kspace_bytes);
+int ksn_fft_export(void *d_kspace, void *d_real, void *handles128);
+int ksn_fft_attach(void *d_kspace, void *d_real, const void *handles);
+int ksn_fft_forward(void *d_real, void *d_kspace);
+int ksn_fft_inverse(void *d_kspace, void *d_real);
+void ksn_fft_destroy(void);
 
 /* ---- introspection for bench.py --------------------------------------------------- */
 typedef struct ksn_timing {

@@ -125,6 +125,14 @@ PROTOTYPES = {
     "ksn_set_background": (C.c_int, [HUBBLE_FN, C.c_void_p, C.c_double, C.c_double, C.c_int]),
     "ksn_background_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ksn_fslength_device": (C.c_int, [c_double_p, C.c_int, C.c_double, C.c_double, c_double_p]),
+    "ksn_background_loaded": (C.c_int, []),
+    "ksn_fft_plan": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "ksn_fft_layout": (C.c_int, [c_longlong_p, c_longlong_p, c_longlong_p, c_longlong_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "ksn_fft_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ksn_fft_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ksn_fft_forward": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ksn_fft_inverse": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ksn_fft_destroy": (None, []),
     "ksn_timing_enable": (C.c_int, [C.c_int]),
     "ksn_timing_reset": (C.c_int, []),
     "ksn_timing_get": (C.c_int, [C.POINTER(Timing)]),

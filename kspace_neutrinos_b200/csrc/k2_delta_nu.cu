@@ -871,6 +871,8 @@ static double bg_lagrange_host(const double *g, int n, double s)
     return -u * um1 * um2 * (1.0 / 6.0) * g[i - 1] + up1 * um1 * um2 * 0.5 * g[i] - up1 * u * um2 * 0.5 * g[i + 1] + up1 * u * um1 * (1.0 / 6.0) * g[i + 2];
 }
 
+extern "C" int ksn_background_loaded(void) { return ctx().inited && ctx().d_bg != nullptr; }
+
 extern "C" int ksn_background_info(int *npatch, int *flagged_cells)
 {
     if (npatch) *npatch = g_bg_npatch;

@@ -104,6 +104,9 @@ struct K3Params {
     int off_kthr;     // table offsets in units of 4 bytes from the table base: integer knot thresholds, float records
     int off_segf;
     int multi;        // a cell may hold several knots (knots closer than the finest cells): loop in the segment search
+    unsigned k2_narrow; // from this k2 on every segment is narrow (u < 2^-5 throughout) and at or above the first knot:
+                        // a grid row with kx^2 + ky^2 >= k2_narrow needs no clamp, no log1p and no bounds on the cell index
+    float cell_off;   // -cell_lo * cell_scale
 };
 
 // How the factor 1 + norm*interp is evaluated (chosen per table by the host, k3_upload_table):
@@ -152,6 +155,27 @@ __device__ __forceinline__ double k3_factor(int k2i, const double *__restrict__ 
     return fma(ab.y, lg, ab.x);
 }
 
+// The same factor for a mode the host has vouched for (k2 >= prm.k2_narrow): no clamp below the first knot, no wide
+// segment (so no log1p), the cell index needs no bounds -- a straight line of code, so that the compiler can interleave
+// the dependent FP64 chains of a thread's nine modes.
+template <int FM>
+__device__ __forceinline__ double k3_factor_narrow(int k2i, const double *__restrict__ tab, const K3Params &prm)
+{
+    const K3Seg *seg = (const K3Seg *) tab;
+    const unsigned short *cellv = (const unsigned short *) (seg + prm.n + 1);
+    const unsigned *kthr = (const unsigned *) tab + prm.off_kthr;
+    const int cell = (int) fmaf(fast_log2((float) k2i), prm.cell_scale, prm.cell_off);
+    int s = __ldg(cellv + cell);
+    s += ((unsigned) k2i >= __ldg(kthr + s + 1));
+    const double inv = __ldg(&seg[s].inv);
+    const double2 ab = __ldg((const double2 *) &seg[s].A);     // {A, B}
+    const double uu = fma((double) k2i, inv, -1.0);
+    double lg;
+    if (FM == FM_D5) lg = uu * (1.0 + uu * (-0.5 + uu * (1.0 / 3 + uu * (-0.25 + uu * 0.2))));
+    else lg = uu * (1.0 + uu * (-0.5 + uu * (1.0 / 3 + uu * (-0.25 + uu * (0.2 + uu * (-1.0 / 6 + uu * (1.0 / 7 + uu * (-0.125 + uu * (1.0 / 9)))))))));
+    return fma(ab.y, lg, ab.x);
+}
+
 // FM_F32: factor - 1 in float
 __device__ __forceinline__ float k3_delta_f32(int k2i, const double *__restrict__ tab, const K3Params &prm)
 {
@@ -165,6 +189,21 @@ __device__ __forceinline__ float k3_delta_f32(int k2i, const double *__restrict_
     float lg;
     if (uu < 0.03125f) lg = uu * (1.0f + uu * (-0.5f + uu * (1.0f / 3 + uu * (-0.25f + uu * 0.2f))));
     else lg = log1pf(uu);
+    return fmaf(r.z, lg, r.y);
+}
+
+__device__ __forceinline__ float k3_delta_f32_narrow(int k2i, const double *__restrict__ tab, const K3Params &prm)
+{
+    const K3Seg *seg = (const K3Seg *) tab;
+    const unsigned short *cellv = (const unsigned short *) (seg + prm.n + 1);
+    const unsigned *kthr = (const unsigned *) tab + prm.off_kthr;
+    const K3SegF *segf = (const K3SegF *) ((const unsigned *) tab + prm.off_segf);
+    const int cell = (int) fmaf(fast_log2((float) k2i), prm.cell_scale, prm.cell_off);
+    int s = __ldg(cellv + cell);
+    s += ((unsigned) k2i >= __ldg(kthr + s + 1));
+    const float4 r = __ldg((const float4 *) (segf + s));
+    const float uu = fmaf((float) k2i, r.x, -1.0f);
+    const float lg = uu * (1.0f + uu * (-0.5f + uu * (1.0f / 3 + uu * (-0.25f + uu * 0.2f))));
     return fmaf(r.z, lg, r.y);
 }
 
@@ -294,14 +333,30 @@ k3_scale_row_kernel(C2<double> *__restrict__ grid, int N, long long plane0,
     const int c0 = ki * ki + kj * kj;
     const double w0 = gr.on ? k3_greens_row(gr, ki, kj) : 1.0;   // -exp(-(kx^2+ky^2) asmth2) (iwx iwy)^4 of this row
     double smth[K3_EPT];
+    if ((unsigned) c0 + (unsigned) z0 * (unsigned) z0 >= prm.k2_narrow) {
+        // every mode of this piece sits in a narrow segment at or above the first knot (all rows but the few around the
+        // k_x = k_y = 0 axis): branch-free factors, whole iterations without a bounds check
+        const int nfull = nel / K3_TMA_THREADS;
 #pragma unroll
-    for (int k = 0; k < K3_EPT; k++) {
-        const int e = threadIdx.x + K3_TMA_THREADS * k;
-        smth[k] = 1.0;
-        if (e < nel) {
-            const int z = z0 + e, k2i = c0 + z * z;
-            if (k2i > 0) smth[k] = k3_factor<FM>(k2i, tab, prm);                            // F(0,0,0) keeps factor 1 ...
-            if (gr.on) smth[k] = k2i > 0 ? smth[k] * k3_greens(gr, k2i, w0, z) : 0.0;       // ... or is zeroed with the potential
+        for (int k = 0; k < K3_EPT; k++) {
+            const int e = threadIdx.x + K3_TMA_THREADS * k;
+            smth[k] = 1.0;
+            if (k < nfull || e < nel) {
+                const int z = z0 + e, k2i = c0 + z * z;
+                smth[k] = k3_factor_narrow<FM>(k2i, tab, prm);
+                if (gr.on) smth[k] *= k3_greens(gr, k2i, w0, z);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < K3_EPT; k++) {
+            const int e = threadIdx.x + K3_TMA_THREADS * k;
+            smth[k] = 1.0;
+            if (e < nel) {
+                const int z = z0 + e, k2i = c0 + z * z;
+                if (k2i > 0) smth[k] = k3_factor<FM>(k2i, tab, prm);                            // F(0,0,0) keeps factor 1 ...
+                if (gr.on) smth[k] = k2i > 0 ? smth[k] * k3_greens(gr, k2i, w0, z) : 0.0;       // ... or is zeroed with the potential
+            }
         }
     }
     __syncthreads();                       // the barrier was initialised before anyone polls it
@@ -349,26 +404,60 @@ k3_scale_flat_kernel(C2<real> *__restrict__ grid, long long total, int chunk, in
     const int j0 = (int) (r0 - pl0 * N);
     using fac_t = typename std::conditional<FM == FM_F32, float, double>::type;
     fac_t smth[K3_EPT];
+    auto row_kk = [&](int rl, int &ki, int &kj) {                // wave numbers of the chunk's rl-th row
+        int j = j0 + rl;
+        long long gi = plane0 + pl0;
+        if (j >= N) { const int q = j / N; j -= q * N; gi += q; }
+        ki = gi <= N / 2 ? (int) gi : (int) (gi - N);
+        kj = j <= N / 2 ? j : j - N;
+    };
+    // does every row of this chunk lie where all segments are narrow (all but the rows around the k_x = k_y = 0 axis)?
+    bool fast = true;
+    {
+        const int rows = (zb + nel + L - 1) / L;
+        for (int rl = 0; rl < rows; rl++) {
+            int ki, kj;
+            row_kk(rl, ki, kj);
+            fast = fast && (unsigned) (ki * ki + kj * kj) >= prm.k2_narrow;
+        }
+    }
+    if (fast) {
+        const int nfull = nel / THREADS;
 #pragma unroll
-    for (int k = 0; k < K3_EPT; k++) {
-        const int e = threadIdx.x + THREADS * k;
-        smth[k] = FM == FM_F32 ? (fac_t) 0 : (fac_t) 1;            // FM_F32 holds factor - 1
-        if (e < nel) {
-            int z = zb + e, j = j0;
-            long long gi = plane0 + pl0;
-            if (z >= L) {                                          // the chunk's second row (two-row chunks end here)
-                z -= L; j++;
-                if (z >= L) { const int q = z / L; z -= q * L; j += q; }
+        for (int k = 0; k < K3_EPT; k++) {
+            const int e = threadIdx.x + THREADS * k;
+            smth[k] = FM == FM_F32 ? (fac_t) 0 : (fac_t) 1;
+            if (k < nfull || e < nel) {
+                int z = zb + e, rl = 0;
+                if (z >= L) { z -= L; rl = 1; if (z >= L) { const int q = z / L; z -= q * L; rl += q; } }
+                int ki, kj;
+                row_kk(rl, ki, kj);
+                const int k2i = ki * ki + kj * kj + z * z;
+                if constexpr (FM == FM_F32) {
+                    smth[k] = k3_delta_f32_narrow(k2i, tab, prm);
+                } else {
+                    smth[k] = k3_factor_narrow<FM>(k2i, tab, prm);
+                    if (gr.on) smth[k] *= k3_greens(gr, k2i, k3_greens_row(gr, ki, kj), z);
+                }
             }
-            if (j >= N) { const int q = j / N; j -= q * N; gi += q; }
-            const int ki = gi <= N / 2 ? (int) gi : (int) (gi - N);
-            const int kj = j <= N / 2 ? j : j - N;
-            const int k2i = ki * ki + kj * kj + z * z;
-            if constexpr (FM == FM_F32) {
-                if (k2i > 0) smth[k] = k3_delta_f32(k2i, tab, prm);       // (never launched with the Green's function on)
-            } else {
-                if (k2i > 0) smth[k] = k3_factor<FM>(k2i, tab, prm);                                         // F(0,0,0) keeps factor 1 ...
-                if (gr.on) smth[k] = k2i > 0 ? smth[k] * k3_greens(gr, k2i, k3_greens_row(gr, ki, kj), z) : 0.0;   // ... or is zeroed
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < K3_EPT; k++) {
+            const int e = threadIdx.x + THREADS * k;
+            smth[k] = FM == FM_F32 ? (fac_t) 0 : (fac_t) 1;            // FM_F32 holds factor - 1
+            if (e < nel) {
+                int z = zb + e, rl = 0;
+                if (z >= L) { z -= L; rl = 1; if (z >= L) { const int q = z / L; z -= q * L; rl += q; } }
+                int ki, kj;
+                row_kk(rl, ki, kj);
+                const int k2i = ki * ki + kj * kj + z * z;
+                if constexpr (FM == FM_F32) {
+                    if (k2i > 0) smth[k] = k3_delta_f32(k2i, tab, prm);       // (never launched with the Green's function on)
+                } else {
+                    if (k2i > 0) smth[k] = k3_factor<FM>(k2i, tab, prm);                                         // F(0,0,0) keeps factor 1 ...
+                    if (gr.on) smth[k] = k2i > 0 ? smth[k] * k3_greens(gr, k2i, k3_greens_row(gr, ki, kj), z) : 0.0;   // ... or is zeroed
+                }
             }
         }
     }
@@ -430,7 +519,10 @@ int k3_upload_table(int dims, double boxsize, const double *logkk, const double 
         if (i > 0) min_gap = fmin(min_gap, 2.0 * (logkk[i] - logkk[i - 1]) / M_LN2);   // gap in log2(k2)
     }
     seg[nbins].K2 = INFINITY; seg[nbins].inv = 0; seg[nbins].A = seg[nbins - 1].A; seg[nbins].B = 0;
-    const double lo = log2(seg[0].K2), hi = log2(seg[nbins - 1].K2);
+    // the cells run from the first knot to the largest k^2 of the grid (or the last knot, whichever is larger), so that a
+    // mode at or above the first knot needs no bound on its cell index
+    const double k2max = 3.0 * (double) (dims / 2) * (double) (dims / 2);
+    const double lo = log2(seg[0].K2), hi = fmax(log2(seg[nbins - 1].K2), log2(fmax(k2max, 2.0)) + 1e-3);
     // cells narrow enough that (with the float-rounding guard) no cell sees two knots; where the knots are closer than the
     // finest cells (keff values are data-dependent means: nothing forbids it, and gsl_interp has no such limit) the
     // segment search steps over the extra knots in a loop instead
@@ -491,6 +583,14 @@ int k3_upload_table(int dims, double boxsize, const double *logkk, const double 
     g_k3prm.off_kthr = off_kthr;
     g_k3prm.off_segf = off_segf;
     g_k3prm.multi = g_k3_multi ? 1 : 0;
+    g_k3prm.cell_off = (float) (-lo * scale);
+    {
+        // first knot from which on all segments are narrow (the last one, clamped above, has B = 0: any u will do)
+        int j = 0;
+        for (int i = 0; i + 1 < nbins; i++)
+            if (!(seg[i + 1].K2 * seg[i].inv - 1.0 < 0.03125)) j = i + 1;
+        g_k3prm.k2_narrow = g_k3_multi || getenv("KSN_K3_NOFAST") ? 0xffffffffu : kthr[j];
+    }
     KSN_CUDA(cudaMemcpyAsync(c.d_k3tab, c.h_k3tab, k3_tab_doubles(nbins, cells) * sizeof(double), cudaMemcpyHostToDevice, c.stream));
     return KSN_OK;
 }

@@ -391,6 +391,7 @@ void ksn_shutdown(void)
     if (!c.inited) return;
     cudaSetDevice(c.device);
     cudaDeviceSynchronize();
+    fft_shutdown();
     drop_comm();
     k1_tables_invalidate();
     for (auto &kv : g_registered) cudaHostUnregister((void *) kv.first);

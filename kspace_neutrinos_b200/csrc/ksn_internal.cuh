@@ -95,6 +95,7 @@ int k1_launch(const void *dgrid, int real_bytes, int dims, int nrbins, long long
               bool full, bool accumulate, int *ctas_out, int *stride_out);
 int k1_finish(int real_bytes, int dims, int nrbins, bool full, int ctas, int stride, const void *origin_elem, bool fuse_p2p);
 void k1_tables_invalidate();   // somebody else wrote c.d_iw / c.d_thr, or the context is gone
+void fft_shutdown();           // plans, work area and peer mappings of ksn_fft_* (ksn_fft.cu)
 int k3_launch(void *dgrid, int real_bytes, int dims, long long plane0_global, long long nplanes, int nknots);
 int k3_upload_table(int dims, double boxsize, const double *logkk, const double *ratio, int nbins, double norm);
 

@@ -107,6 +107,72 @@ class PinnedGrid:
             self.ptr = C.c_void_p()
 
 
+class SlabFFT:
+    """Device-resident slab FFT of the PM grid (ksn_fft_*): real space in x-slabs, rows padded to 2 (N/2+1) doubles, ->
+    k space in y-slabs, FFTW's transposed order F[y][x][kz] -- the layout of gadget-2/0002 patch:116, i.e. what
+    add_nu_power_to_rhogrid takes.  `gather`: for more than one rank, a callable that all-gathers a bytes object over the
+    ranks in rank order (e.g. torch.distributed.all_gather_object); the peer-memory collective (init_p2p_from_torch)
+    must be up on the same ranks."""
+
+    def __init__(self, pmgrid: int, rank: int = 0, world: int = 1, gather=None):
+        self.lib = capi.lib()
+        L = self.lib
+        self.pmgrid, self.rank, self.world = pmgrid, rank, world
+        capi.check(L.ksn_fft_plan(pmgrid, world, rank), "ksn_fft_plan")
+        v = [C.c_longlong() for _ in range(4)]
+        rb, kb = C.c_size_t(), C.c_size_t()
+        capi.check(L.ksn_fft_layout(*[C.byref(x) for x in v], C.byref(rb), C.byref(kb)), "ksn_fft_layout")
+        self.xslab, self.yslab = Slab(v[0].value, v[1].value), Slab(v[2].value, v[3].value)
+        self.real_bytes, self.kspace_bytes = rb.value, kb.value
+        self.real, self.kspace = C.c_void_p(), C.c_void_p()
+        capi.check(L.ksn_device_malloc(C.byref(self.real), max(self.real_bytes, 256)), "ksn_device_malloc")
+        capi.check(L.ksn_device_malloc(C.byref(self.kspace), max(self.kspace_bytes, 256)), "ksn_device_malloc")
+        handles = None
+        if world > 1:
+            if gather is None:
+                raise ValueError("SlabFFT on more than one rank needs a `gather` callable")
+            mine = (C.c_ubyte * 128)()
+            capi.check(L.ksn_fft_export(self.kspace, self.real, mine), "ksn_fft_export")
+            everyone = gather(bytes(mine))
+            handles = (C.c_ubyte * (128 * world)).from_buffer_copy(b"".join(everyone))
+        capi.check(L.ksn_fft_attach(self.kspace, self.real, handles), "ksn_fft_attach")
+
+    def upload_real(self, rho: np.ndarray) -> None:
+        """rho: this rank's x planes, [nslab_x][N][N] doubles (unpadded)."""
+        n = self.pmgrid
+        pad = np.zeros((self.xslab.count, n, 2 * (n // 2 + 1)))
+        pad[..., :n] = rho
+        if pad.nbytes:
+            capi.check(self.lib.ksn_memcpy_h2d(self.real, pad.ctypes.data_as(C.c_void_p), pad.nbytes), "ksn_memcpy_h2d")
+
+    def download_real(self) -> np.ndarray:
+        n = self.pmgrid
+        pad = np.empty((self.xslab.count, n, 2 * (n // 2 + 1)))
+        if pad.nbytes:
+            capi.check(self.lib.ksn_memcpy_d2h(pad.ctypes.data_as(C.c_void_p), self.real, pad.nbytes), "ksn_memcpy_d2h")
+        return pad[..., :n].copy()
+
+    def download_kspace(self) -> np.ndarray:
+        n = self.pmgrid
+        out = np.empty((self.yslab.count, n, n // 2 + 1, 2))
+        if out.nbytes:
+            capi.check(self.lib.ksn_memcpy_d2h(out.ctypes.data_as(C.c_void_p), self.kspace, out.nbytes), "ksn_memcpy_d2h")
+        return out
+
+    def forward(self) -> None:
+        capi.check(self.lib.ksn_fft_forward(self.real, self.kspace), "ksn_fft_forward")
+
+    def inverse(self) -> None:
+        capi.check(self.lib.ksn_fft_inverse(self.kspace, self.real), "ksn_fft_inverse")
+
+    def free(self) -> None:
+        self.lib.ksn_fft_destroy()
+        for p in (self.real, self.kspace):
+            if p:
+                self.lib.ksn_device_free(p)
+        self.real, self.kspace = C.c_void_p(), C.c_void_p()
+
+
 class KspaceNeutrinos:
     """The module-global integrator of the reference (one per process, like interface_common.c:17-26),
     driven in the host call order of SURVEY 3.1: parameters -> InitOmegaNu -> allocate_kspace_memory ->

@@ -275,7 +275,8 @@ void ksn_invalidate_background(void) { bgc.valid = 0; }
 
 void ksn_ensure_background(double a_lo, double a_hi)
 {
-    if (bgc.valid && a_lo >= bgc.a_lo && a_hi <= bgc.a_hi) {
+    /* (the device table dies with ksn_shutdown -- also when the context moves to another device: ask the device layer) */
+    if (bgc.valid && ksn_background_loaded() && a_lo >= bgc.a_lo && a_hi <= bgc.a_hi) {
         int same = 1;
         for (int i = 0; i < 3; i++) same &= hubble_function(bgc.probe_a[i]) == bgc.probe_h[i];
         if (same) return;

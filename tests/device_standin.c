@@ -96,6 +96,8 @@ int ksn_set_background(ksn_hubble_fn hub, void *user, double loga_lo, double log
     return KSN_OK;
 }
 
+int ksn_background_loaded(void) { return bg_hub != NULL; }
+
 static double inv_a2H(double loga, void *unused)                                   /* delta_tot_table.c:378-384 */
 {
     (void) unused;

@@ -402,6 +402,28 @@ def ours(args):
                        "note": "add_nu_power_to_rhogrid on pinned HOST slabs: upload, K1, K2, K3, download, every step"}
             else:
                 e2e = {"value": None, "unit": UNIT, "error": err or "the step failed on another rank"}
+        # what the host <-> device links of this box give when every rank copies at once (the ceiling of the leg above:
+        # the upload must be complete before K2 and K3 can start, so a step cannot beat upload time + download time)
+        if pin is not None and e2e and e2e.get("value"):
+            try:
+                probe = min(grid.nbytes, 4 << 30)
+                rates = []
+                for fn, dst, src in ((L.ksn_memcpy_h2d, grid.ptr, pin.ptr), (L.ksn_memcpy_d2h, pin.ptr, grid.ptr)):
+                    capi.check(fn(dst, src, probe))                    # warm
+                    barrier()
+                    tp = time.perf_counter()
+                    capi.check(fn(dst, src, probe))
+                    dt_p = torch.tensor([time.perf_counter() - tp], dtype=torch.float64, device="cuda")
+                    if world > 1:
+                        dist.all_reduce(dt_p, op=dist.ReduceOp.MAX)
+                    rates.append(probe / dt_p.item() / 1e9)
+                bound_ms = (grid.nbytes / rates[0] + grid.nbytes / rates[1]) / 1e6
+                e2e.update({"h2d_GBps_per_gpu_all_ranks_copying": rates[0], "d2h_GBps_per_gpu_all_ranks_copying": rates[1],
+                            "transfer_bound_ms_per_step": bound_ms, "frac_of_transfer_bound": bound_ms / e2e["ms_per_step"],
+                            "bound_note": "upload and download of a step cannot overlap (K2 needs the whole grid's P(k) before K3 scales the first mode): "
+                                          "ceiling = slab bytes / H2D rate + slab bytes / D2H rate, rates measured with every rank copying at once"})
+            except capi.KsnError as exc:
+                e2e["transfer_probe_error"] = str(exc)
         if pin is not None:
             pin.free()
 

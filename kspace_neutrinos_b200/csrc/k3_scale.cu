@@ -114,8 +114,8 @@ struct K3Params {
 //   FM_D5   double, series to u^5: tables whose narrow segments satisfy |B| u_max^6 / 6 <= 1e-14 -- four FP64
 //           instructions less per mode, the same factor to 1e-14
 //   FM_F32  FLOAT grids only: delta = factor - 1 entirely in float and x*factor as fmaf(x, delta, x), for tables with
-//           |B| <= 1/64 and |norm*ratio| <= 1/32, where the float evaluation of delta is off by < 2^-28 of the factor
-//           (1/16 of a float ulp of the product) -- no FP64 instruction left in the float pass
+//           |B| (1 + 3 u) + |norm*ratio| <= 1/8, where the float evaluation of delta is off by < 2^-26 of the factor
+//           (a quarter of a float ulp of the product) -- no FP64 instruction left in the float pass
 enum { FM_D9 = 0, FM_D5 = 1, FM_F32 = 2 };
 
 // The lookup tables live in GLOBAL memory and are read through L1 (__ldg): they are identical for every CTA, a few
@@ -382,6 +382,7 @@ k3_scale_row_kernel(C2<double> *__restrict__ grid, int N, long long plane0,
 //  * float grids (256 threads): a float row is (N/2+1)*8 bytes -- 8200 at PMGRID = 2048 -- so every other row starts
 //    8 bytes off the 16-byte granule bulk copies need; chunks of an even mode count (two whole rows, 16400 B, at 2048) do not.
 constexpr int K3_FLAT_THREADS = 256;
+constexpr int K3_FLAT_MAX_ROWS = 64;       // rows a chunk may touch (the launcher falls back to plain loads beyond)
 
 template <typename real, int THREADS, int FM>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
@@ -404,40 +405,40 @@ k3_scale_flat_kernel(C2<real> *__restrict__ grid, long long total, int chunk, in
     const int j0 = (int) (r0 - pl0 * N);
     using fac_t = typename std::conditional<FM == FM_F32, float, double>::type;
     fac_t smth[K3_EPT];
-    auto row_kk = [&](int rl, int &ki, int &kj) {                // wave numbers of the chunk's rl-th row
-        int j = j0 + rl;
+    // per row of the chunk: kx^2 + ky^2 and the packed wave numbers (a chunk holds whole rows plus, at most, two cut ones)
+    __shared__ int c_s[K3_FLAT_MAX_ROWS], kk_s[K3_FLAT_MAX_ROWS];
+    __shared__ int fast_s;
+    const int rows = (zb + nel + L - 1) / L;
+    if (threadIdx.x == 0) fast_s = 1;
+    __syncthreads();
+    if ((int) threadIdx.x < rows) {
+        int j = j0 + (int) threadIdx.x;
         long long gi = plane0 + pl0;
         if (j >= N) { const int q = j / N; j -= q * N; gi += q; }
-        ki = gi <= N / 2 ? (int) gi : (int) (gi - N);
-        kj = j <= N / 2 ? j : j - N;
-    };
-    // does every row of this chunk lie where all segments are narrow (all but the rows around the k_x = k_y = 0 axis)?
-    bool fast = true;
-    {
-        const int rows = (zb + nel + L - 1) / L;
-        for (int rl = 0; rl < rows; rl++) {
-            int ki, kj;
-            row_kk(rl, ki, kj);
-            fast = fast && (unsigned) (ki * ki + kj * kj) >= prm.k2_narrow;
-        }
+        const int ki = gi <= N / 2 ? (int) gi : (int) (gi - N);
+        const int kj = j <= N / 2 ? j : j - N;
+        c_s[threadIdx.x] = ki * ki + kj * kj;
+        kk_s[threadIdx.x] = (ki << 16) | (kj & 0xffff);
+        if ((unsigned) (ki * ki + kj * kj) < prm.k2_narrow) fast_s = 0;        // (a benign race: everybody writes 0)
     }
-    if (fast) {
+    __syncthreads();
+    // row of a mode: floor((zb + e) / L) by a multiply (exact for (zb + e) * L < 2^32: both are below 2^15 here)
+    const unsigned magic = 0xffffffffu / (unsigned) L + 1u;
+    if (fast_s) {
+        // every row of this chunk lies where all segments are narrow (all but the rows around the k_x = k_y = 0 axis)
         const int nfull = nel / THREADS;
 #pragma unroll
         for (int k = 0; k < K3_EPT; k++) {
             const int e = threadIdx.x + THREADS * k;
             smth[k] = FM == FM_F32 ? (fac_t) 0 : (fac_t) 1;
             if (k < nfull || e < nel) {
-                int z = zb + e, rl = 0;
-                if (z >= L) { z -= L; rl = 1; if (z >= L) { const int q = z / L; z -= q * L; rl += q; } }
-                int ki, kj;
-                row_kk(rl, ki, kj);
-                const int k2i = ki * ki + kj * kj + z * z;
+                const int zz = zb + e, rl = (int) __umulhi((unsigned) zz, magic), z = zz - rl * L;
+                const int k2i = c_s[rl] + z * z;
                 if constexpr (FM == FM_F32) {
                     smth[k] = k3_delta_f32_narrow(k2i, tab, prm);
                 } else {
                     smth[k] = k3_factor_narrow<FM>(k2i, tab, prm);
-                    if (gr.on) smth[k] *= k3_greens(gr, k2i, k3_greens_row(gr, ki, kj), z);
+                    if (gr.on) { const int kk = kk_s[rl]; smth[k] *= k3_greens(gr, k2i, k3_greens_row(gr, kk >> 16, (int) (short) (kk & 0xffff)), z); }
                 }
             }
         }
@@ -447,16 +448,16 @@ k3_scale_flat_kernel(C2<real> *__restrict__ grid, long long total, int chunk, in
             const int e = threadIdx.x + THREADS * k;
             smth[k] = FM == FM_F32 ? (fac_t) 0 : (fac_t) 1;            // FM_F32 holds factor - 1
             if (e < nel) {
-                int z = zb + e, rl = 0;
-                if (z >= L) { z -= L; rl = 1; if (z >= L) { const int q = z / L; z -= q * L; rl += q; } }
-                int ki, kj;
-                row_kk(rl, ki, kj);
-                const int k2i = ki * ki + kj * kj + z * z;
+                const int zz = zb + e, rl = (int) __umulhi((unsigned) zz, magic), z = zz - rl * L;
+                const int k2i = c_s[rl] + z * z;
                 if constexpr (FM == FM_F32) {
                     if (k2i > 0) smth[k] = k3_delta_f32(k2i, tab, prm);       // (never launched with the Green's function on)
                 } else {
                     if (k2i > 0) smth[k] = k3_factor<FM>(k2i, tab, prm);                                         // F(0,0,0) keeps factor 1 ...
-                    if (gr.on) smth[k] = k2i > 0 ? smth[k] * k3_greens(gr, k2i, k3_greens_row(gr, ki, kj), z) : 0.0;   // ... or is zeroed
+                    if (gr.on) {                                                                                 // ... or is zeroed
+                        const int kk = kk_s[rl];
+                        smth[k] = k2i > 0 ? smth[k] * k3_greens(gr, k2i, k3_greens_row(gr, kk >> 16, (int) (short) (kk & 0xffff)), z) : 0.0;
+                    }
                 }
             }
         }
@@ -563,7 +564,7 @@ int k3_upload_table(int dims, double boxsize, const double *logkk, const double 
     kthr[nbins] = kthr[nbins + 1] = 0xffffffffu;
     // how much arithmetic the table needs.  Narrow segments (u = k2/K2_i - 1 < 2^-5 over the whole segment) use a series
     // for ln(1+u): to u^5 where |B| u_max^6 / 6 <= 1e-14 on every one of them (four orders below the 1e-10 bar), else to u^9.  The all-float pass over a
-    // float grid: error of delta = factor - 1 about 2^-23 (|B| (1 + 3 u) + |delta|), wanted below 2^-28.
+    // float grid: error of delta = factor - 1 about 2^-23 (|B| (1 + 3 u) + |delta|), wanted below 2^-26 (a quarter of a float ulp of the product).
     double worst_d5 = 0, worst_f32 = 0;
     for (int i = 0; i < nbins; i++) {
         const double umax = i + 1 < nbins ? seg[i + 1].K2 * seg[i].inv - 1.0 : 0.0;
@@ -575,7 +576,7 @@ int k3_upload_table(int dims, double boxsize, const double *logkk, const double 
     }
     segf[nbins] = segf[nbins - 1]; segf[nbins].B = 0; segf[nbins].inv = 0;
     g_k3_fm_double = worst_d5 <= 1e-14 ? FM_D5 : FM_D9;
-    g_k3_f32_ok = worst_f32 <= 1.0 / 32 && 3.0 * (double) dims * dims / 4 < 16777216.0 && seg[0].K2 > 1e-30;
+    g_k3_f32_ok = worst_f32 <= 1.0 / 8 && 3.0 * (double) dims * dims / 4 < 16777216.0 && seg[0].K2 > 1e-30;
     g_k3prm.n = nbins;
     g_k3prm.cells = cells;
     g_k3prm.cell_lo = (float) lo;
@@ -665,7 +666,7 @@ int k3_launch(void *dgrid, int real_bytes, int dims, long long plane0_global, lo
         const size_t row_bytes = (size_t) L * 16;
         int rpc = segs > 1 ? 1 : cap / L;
         while (rpc > 1 && rpc * row_bytes > 18432) rpc--;
-        if (segs == 1 && rpc > 1) {
+        if (segs == 1 && rpc > 1 && rpc + 2 <= K3_FLAT_MAX_ROWS) {
             const int chunk = rpc * L;
             const size_t smem = (size_t) chunk * 16 + 128;
             const long long nct = (total + chunk - 1) / chunk;
@@ -701,7 +702,7 @@ int k3_launch(void *dgrid, int real_bytes, int dims, long long plane0_global, lo
         // whole row pairs (~16-18 KB of them) where a pair fits one CTA, else the largest even piece
         const int chunk = pair <= capf ? pair * max(1, min(capf / pair, (int) (18432 / ((size_t) pair * 8)))) : (capf & ~1);
         const long long nct = (total + chunk - 1) / chunk;
-        if (nct <= 0x7fffffffLL) {
+        if (nct <= 0x7fffffffLL && chunk / L + 2 <= K3_FLAT_MAX_ROWS) {
             const size_t smem = (size_t) chunk * 8 + 128;
             auto go = [&](auto kern) -> int {
                 int rc = shared_cfg(kern, smem);

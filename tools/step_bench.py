@@ -45,4 +45,4 @@ modes = n * n * (n // 2 + 1)
 k1, k2, k3 = t.k1_ms / steps, t.k2_ms / steps, t.k3_ms / steps
 print(f"PMGRID {n} {'double' if rb == 8 else 'float'} grid ({modes * 2 * rb / 1e9:.1f} GB): {wall:.3f} ms per step = {modes / wall / 1e6:.1f} Gmodes/s = "
       f"{6 * rb * modes / wall / 1e6:.0f} GB/s of algorithmic traffic;  K1 {k1:.3f} ms ({2 * rb * modes / k1 / 1e6:.0f} GB/s)  "
-      f"K2 {k2:.3f} ms  K3 {k3:.3f} ms ({4 * rb * modes / k3 / 1e6:.0f} GB/s)  [{L.ksn_last_k1_kernel().decode()}]")
+      f"K2 {k2:.3f} ms  K3 {k3:.3f} ms ({4 * rb * modes / k3 / 1e6:.0f} GB/s)  [{L.ksn_last_k1_kernel().decode()}]  [{L.ksn_last_k3_kernel().decode()}]")

@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-greens", action="store_true", help="skip the fused Green's-function side measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi during the timed region (diagnostics)")
     ap.add_argument("--no-check", action="store_true", help="skip the end-of-run parity check against the CPU oracle (outside the timed region)")
     ap.add_argument("--ref-budget-s", type=float, default=float(os.environ.get("KSN_REF_BUDGET_S", "420")),
                     help="--impl reference: wall-clock budget for the warm-up + timed steps; the full slab is timed when it fits "
@@ -276,24 +277,28 @@ def ours(args):
     n_calls = max(3, args.warmup) + args.steps + (0 if args.no_e2e else args.e2e_steps + 1) + 4
     da = min(0.001, (0.9995 - a) / n_calls)
     sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()                          # nvidia-smi needs ~1 s to deliver its first sample
-    for _ in range(max(3, args.warmup)):
+    if rank == 0 and not args.no_clocks:
+        sampler.start()
+        time.sleep(1.0)                          # nvidia-smi needs ~1 s to deliver its first sample: wait BEFORE the
+    barrier()                                    # warm-up, so that no GPU idles between the warm-up and the timed steps
+    L.ksn_timing_enable(1)                       # (the phase timers' events are created on first use: in the warm-up)
+    for _ in range(max(3, args.warmup)):         # (an idle second there cost the first timed step 15-40 ms)
         a += da
         sim.add_nu_power_to_rhogrid(a, grid.ptr, slab)
     if rank == 0:
-        time.sleep(1.0)
         sampler.rows.clear()                     # keep only samples taken during the timed region
     stream = torch.cuda.ExternalStream(L.ksn_stream())
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    L.ksn_timing_enable(1)
     L.ksn_timing_reset()
     barrier()
     ev0.record(stream)
     t0 = time.perf_counter()
+    step_wall = []
     for _ in range(args.steps):
         a += da
-        sim.add_nu_power_to_rhogrid(a, grid.ptr, slab)
+        ts = time.perf_counter()
+        sim.add_nu_power_to_rhogrid(a, grid.ptr, slab)       # (returns after K3: the entry is synchronous, like the reference's)
+        step_wall.append((time.perf_counter() - ts) * 1e3)
     ev1.record(stream)
     barrier()
     wall = time.perf_counter() - t0
@@ -477,7 +482,9 @@ def ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(n, world, None, args.mnu, not args.no_hybrid), "collective": comm_backend, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-            "roofline": roofline, "wall_ms_per_step": wall_ms / args.steps}
+            "roofline": roofline, "wall_ms_per_step": wall_ms / args.steps,
+            "step_wall_ms_rank0": {"min": min(step_wall), "median": statistics.median(step_wall), "max": max(step_wall),
+                                   "slowest_step": step_wall.index(max(step_wall))}}
     if check is not None:
         line["parity_check"] = check
     if greens is not None:

@@ -215,6 +215,8 @@ int ksn_fft_export(void *d_kspace, void *d_real, void *handles128);
 int ksn_fft_attach(void *d_kspace, void *d_real, const void *handles);
 int ksn_fft_forward(void *d_real, void *d_kspace);
 int ksn_fft_inverse(void *d_kspace, void *d_real);
+/* stages of this rank's most recent transform (ms): 2-D pass, wait for the peers, transpose + exchange, 1-D pass */
+int ksn_fft_timing(float *ms4);
 void ksn_fft_destroy(void);
 
 /* ---- introspection for bench.py --------------------------------------------------- */

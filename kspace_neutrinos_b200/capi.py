@@ -132,6 +132,7 @@ PROTOTYPES = {
     "ksn_fft_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "ksn_fft_forward": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ksn_fft_inverse": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ksn_fft_timing": (C.c_int, [C.POINTER(C.c_float)]),
     "ksn_fft_destroy": (None, []),
     "ksn_timing_enable": (C.c_int, [C.c_int]),
     "ksn_timing_reset": (C.c_int, []),

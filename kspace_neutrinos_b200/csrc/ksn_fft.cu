@@ -88,6 +88,9 @@ struct FftState {
     void *real[KSN_P2P_MAX_RANKS] = {};
     bool ropened[KSN_P2P_MAX_RANKS] = {};
     double *d_token = nullptr;            // one double: the payload of the barrier rounds
+    cudaEvent_t ev[5] = {};               // stage boundaries of the last transform (ksn_fft_timing)
+    bool have_ev = false;
+    float stage_ms[4] = {};               // 2-D pass | wait for the peers | transpose + exchange (+ its fence) | 1-D pass
 };
 static FftState g_fft;
 
@@ -149,10 +152,31 @@ static void fft_unmap()
     }
 }
 
+static void fft_mark(int i)
+{
+    FftState &f = g_fft;
+    if (!f.have_ev) {
+        for (auto &e : f.ev) cudaEventCreate(&e);
+        f.have_ev = true;
+    }
+    cudaEventRecord(f.ev[i], ctx().stream);
+}
+
+static void fft_collect(bool inverse)
+{
+    FftState &f = g_fft;
+    float t[4] = {};
+    for (int i = 0; i < 4; i++) cudaEventElapsedTime(&t[i], f.ev[i], f.ev[i + 1]);
+    // stages in the order of the forward transform
+    if (!inverse) { for (int i = 0; i < 4; i++) f.stage_ms[i] = t[i]; }
+    else { f.stage_ms[0] = t[3]; f.stage_ms[1] = t[1]; f.stage_ms[2] = t[2]; f.stage_ms[3] = t[0]; }
+}
+
 void fft_shutdown()
 {
     fft_release_plans();
     fft_unmap();
+    if (g_fft.have_ev) for (auto &e : g_fft.ev) cudaEventDestroy(e);
     if (g_fft.d_token) cudaFree(g_fft.d_token);
     g_fft = FftState();
 }
@@ -303,13 +327,16 @@ extern "C" int ksn_fft_forward(void *d_real, void *d_kspace)
     const int N = f.N, L = N / 2 + 1;
     const long long x0 = f.xs[f.rank], nx = f.xs[f.rank + 1] - x0, ny = f.ys[f.rank + 1] - f.ys[f.rank];
     // 1. 2-D r2c of every local x plane, in place in the padded grid
+    fft_mark(0);
     for (long long p = 0; p < nx; p += f.batch2d) {
         double *plane = (double *) d_real + (size_t) p * N * 2 * L;
         KSN_FFT(g_cufft.ExecD2Z(f.p2d_f, plane, plane));
     }
     // 2. transpose + exchange: nobody writes into a slab its owner may still be using ...
+    fft_mark(1);
     rc = fft_barrier();
     if (rc) return rc;
+    fft_mark(2);
     if (nx > 0) {
         ExchangePlan p;
         for (int r = 0; r < KSN_P2P_MAX_RANKS; r++) p.peer[r] = (double2 *) f.slab[r];
@@ -324,11 +351,14 @@ extern "C" int ksn_fft_forward(void *d_real, void *d_kspace)
     rc = fft_barrier();
     if (rc) return rc;
     // 3. 1-D c2c along x of every column of the received slab
+    fft_mark(3);
     for (long long y = 0; y < ny; y++) {
         void *plane = (char *) d_kspace + (size_t) y * N * L * 16;
         KSN_FFT(g_cufft.ExecZ2Z(f.p1d, plane, plane, CUFFT_FWD));
     }
+    fft_mark(4);
     KSN_CUDA(cudaStreamSynchronize(c.stream));
+    fft_collect(false);
     if (f.R > 1) { rc = p2p_status_async(); if (!rc) { KSN_CUDA(cudaStreamSynchronize(c.stream)); rc = p2p_status_result(); } }
     return rc;
 }
@@ -341,12 +371,15 @@ extern "C" int ksn_fft_inverse(void *d_kspace, void *d_real)
     Ctx &c = ctx();
     const int N = f.N, L = N / 2 + 1;
     const long long y0 = f.ys[f.rank], ny = f.ys[f.rank + 1] - y0, nx = f.xs[f.rank + 1] - f.xs[f.rank];
+    fft_mark(0);
     for (long long y = 0; y < ny; y++) {
         void *plane = (char *) d_kspace + (size_t) y * N * L * 16;
         KSN_FFT(g_cufft.ExecZ2Z(f.p1d, plane, plane, CUFFT_INV));
     }
+    fft_mark(1);
     rc = fft_barrier();
     if (rc) return rc;
+    fft_mark(2);
     if (ny > 0) {
         ExchangePlan p;
         for (int r = 0; r < KSN_P2P_MAX_RANKS; r++) p.peer[r] = (double2 *) f.real[r];
@@ -359,13 +392,25 @@ extern "C" int ksn_fft_inverse(void *d_kspace, void *d_real)
     }
     rc = fft_barrier();
     if (rc) return rc;
+    fft_mark(3);
     for (long long p = 0; p < nx; p += f.batch2d) {
         double *plane = (double *) d_real + (size_t) p * N * 2 * L;
         KSN_FFT(g_cufft.ExecZ2D(f.p2d_i, plane, plane));
     }
+    fft_mark(4);
     KSN_CUDA(cudaStreamSynchronize(c.stream));
+    fft_collect(true);
     if (f.R > 1) { rc = p2p_status_async(); if (!rc) { KSN_CUDA(cudaStreamSynchronize(c.stream)); rc = p2p_status_result(); } }
     return rc;
+}
+
+// stages of the most recent transform on this rank, in ms: 2-D pass | waiting for the peers before the exchange |
+// transpose + exchange kernel and its closing fence | 1-D pass
+extern "C" int ksn_fft_timing(float *ms4)
+{
+    if (!ms4 || !g_fft.have_ev) return set_error(KSN_EINVAL, "ksn_fft_timing: no transform yet");
+    for (int i = 0; i < 4; i++) ms4[i] = g_fft.stage_ms[i];
+    return KSN_OK;
 }
 
 extern "C" void ksn_fft_destroy(void) { fft_shutdown(); }

@@ -76,6 +76,7 @@ def main():
         a = sample(fft.real, p)[:, :n]
         worst = max(worst, float(np.max(np.abs(a / float(n) ** 3 - b)) / np.max(np.abs(b))))
     t_f, t_i = [], []
+    stages = (C.c_float * 4)()
     for _ in range(reps):
         fill()
         barrier()
@@ -83,6 +84,8 @@ def main():
         fft.forward()
         barrier()
         t1 = time.perf_counter()
+        L.ksn_fft_timing(stages)
+        st_f = [float(x) for x in stages]
         fft.inverse()
         barrier()
         t2 = time.perf_counter()
@@ -116,6 +119,7 @@ def main():
         # bytes the transform must move per rank: 2-D pass r+w, exchange r+w, 1-D pass r+w of the 16 B/mode grid
         print(json.dumps({"pmgrid": n, "gpus": world, "forward_ms": f_ms, "inverse_ms": i_ms, "fft_plus_step_ms": s_ms,
                           "modes_per_s_fft_plus_step": modes / (s_ms * 1e-3), "forward_GBps_per_gpu_of_6_passes": 6 * 16 * modes / world / (f_ms * 1e-3) / 1e9,
+                          "forward_stages_ms_rank0": {"fft2d": st_f[0], "wait_for_peers": st_f[1], "transpose_exchange": st_f[2], "fft1d_along_x": st_f[3]},
                           "round_trip_max_rel_err": worst, "k1": L.ksn_last_k1_kernel().decode(), "k3": L.ksn_last_k3_kernel().decode()}), flush=True)
     barrier()
     fft.free()

@@ -25,7 +25,7 @@ for mode in ("p2p", "p2p-unfused", "nccl"):
     a = 0.98
     L.ksn_timing_enable(1)
     for i in range(6):
-        a += 0.001
+        a += 0.0002
         dist.barrier(); torch.cuda.synchronize()
         L.ksn_timing_reset()
         t0 = time.perf_counter()
@@ -38,7 +38,7 @@ for mode in ("p2p", "p2p-unfused", "nccl"):
     rows = []
     t00 = time.perf_counter()
     for i in range(12):
-        a += 0.001
+        a += 0.0002
         L.ksn_timing_reset()
         t0 = time.perf_counter()
         sim.add_nu_power_to_rhogrid(a, grid.ptr, slab)
@@ -50,7 +50,7 @@ for mode in ("p2p", "p2p-unfused", "nccl"):
     dist.barrier(); torch.cuda.synchronize()
     t00 = time.perf_counter()
     for i in range(12):
-        a += 0.001
+        a += 0.0002
         sim.add_nu_power_to_rhogrid(a, grid.ptr, slab)
     print(f"[{mode} rank {rank}] 12 steps back to back, library timing off: {(time.perf_counter() - t00) * 1e3 / 12:.3f} ms per step", flush=True)
     L.ksn_timing_enable(0)

@@ -157,6 +157,16 @@ typedef struct ksn_delta_nu_args {
 /* out: nspecies*nk doubles, species-major.  n_evals (may be NULL): integrand evaluations. */
 int ksn_delta_nu_integrate(const ksn_delta_nu_args *args, double *out, unsigned long long *n_evals);
 
+/* Optional: start the part of the integral that depends only on the scale factor and the stored knots -- the free-streaming
+ * table (16 Na quadratures of 1/(a^2 H)) and the spline factorisations -- on a side stream, so that it runs beside K1
+ * instead of between K1 and K3.  scalefact: the Na knots (log a) the coming ksn_delta_nu_integrate call will pass,
+ * i.e. the stored rows followed by log(a) of the step; namax: row capacity (sizes the buffers once).  The integrate call
+ * uses the result only if a, TimeTransfer, light, every knot and the background table are bit for bit what it is
+ * called with; otherwise it computes the tables itself.  Never needed for correctness. */
+int ksn_delta_nu_prefetch(double a, double TimeTransfer, double light, const double *scalefact, int Na, int namax);
+/* 1 if the most recent ksn_delta_nu_integrate call took its a-only tables from a prefetch */
+int ksn_last_k2_prefetch_used(void);
+
 /* the tile shape K1's tile kernel takes for (dims, nrbins) on a device with smem_budget bytes of opt-in shared memory per
  * CTA and `sms` SMs (host arithmetic only): warps per CTA, modes per lane, stages, tiles per row, first bin kept in shared
  * memory (0 = all).  Returns 0 when no tile shape fits. */
@@ -215,7 +225,8 @@ int ksn_fft_export(void *d_kspace, void *d_real, void *handles128);
 int ksn_fft_attach(void *d_kspace, void *d_real, const void *handles);
 int ksn_fft_forward(void *d_real, void *d_kspace);
 int ksn_fft_inverse(void *d_kspace, void *d_real);
-/* stages of this rank's most recent transform (ms): 2-D pass, wait for the peers, transpose + exchange, 1-D pass */
+/* stages of this rank's most recent transform (ms).  Forward: wait for the peers, 2-D pass with the transpose + exchange
+ * behind it, closing fence, 1-D pass; inverse: wait, 1-D pass with the exchange behind it, fence, 2-D pass */
 int ksn_fft_timing(float *ms4);
 void ksn_fft_destroy(void);
 

@@ -113,6 +113,8 @@ PROTOTYPES = {
     "ksn_step_staged_greens": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_longlong,
                                          C.POINTER(C.c_uint), c_double_p, C.c_double, C.c_void_p, C.c_void_p, C.c_double]),
     "ksn_delta_nu_integrate": (C.c_int, [C.POINTER(DeltaNuArgs), c_double_p, C.POINTER(C.c_ulonglong)]),
+    "ksn_delta_nu_prefetch": (C.c_int, [C.c_double, C.c_double, C.c_double, c_double_p, C.c_int, C.c_int]),
+    "ksn_last_k2_prefetch_used": (C.c_int, []),
     "ksn_k1_tile_plan": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.c_int] + [C.POINTER(C.c_int)] * 5),
     "ksn_k1_tile_plan_ex": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 5),
     "ksn_last_k1_kernel": (C.c_char_p, []),

@@ -913,7 +913,7 @@ static int k1_launch_t(const void *dgrid, int dims, int nrbins, long long plane0
     const double binsperunit = (nrbins - 1) / log(sqrt(3.0) * dims / 2.0);
     const float binscale = (float) (binsperunit * 0.5 * M_LN2);
     auto launch = [&](auto kern) -> int {
-        KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        { const int rca = func_attributes((const void *) kern, smem, -1); if (rca) return rca; }
         kern<<<ctas, nwarps * 32, smem, c.stream>>>((const Cplx<real> *) dgrid, nrows, dims, nrbins, plane0, binscale,
                                                     c.d_thr, c.d_iw, c.d_partial, accumulate ? 1 : 0);
         c.launches++;
@@ -933,7 +933,7 @@ static int k1_launch_t(const void *dgrid, int dims, int nrbins, long long plane0
             if (rc) return rc;
         }
         auto go = [&](auto kern) -> int {
-            KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc.smem));
+            { const int rca = func_attributes((const void *) kern, tc.smem, -1); if (rca) return rca; }
             kern<<<ctas, tc.W * 32, tc.smem, c.stream>>>((const Cplx<real> *) dgrid, nrows, dims, nrbins, plane0, binscale,
                                                          c.d_thr, c.d_iw, c.d_partial, accumulate ? 1 : 0, tc.C, tc.T, tc.S, tc.stage_bytes,
                                                          g_k1_k2_single, log2N, tc.hot_lo, c.d_cold);

@@ -857,6 +857,8 @@ static int k2_spec_auto(int nspecies_launched, const double *qc)
 }
 
 static unsigned long long g_last_evals = 0;
+static int g_last_prefetch_hit = 0;
+extern "C" int ksn_last_k2_prefetch_used(void) { return g_last_prefetch_hit; }
 static unsigned g_max_passes = 0, g_max_trips = 0;
 extern "C" unsigned ksn_last_k2_max_passes(void) { return g_max_passes; }
 extern "C" unsigned ksn_last_k2_max_trips(void) { return g_max_trips; }
@@ -971,6 +973,116 @@ extern "C" int ksn_fslength_device(const double *logai, int n, double logaf, dou
     return rc;
 }
 
+// ---------------------------------------------------------------- the part of K2 that depends on `a` and the stored knots only
+// fs_knots + fslength (16 Na quadratures of 1/(a^2 H)) + the spline solves of k2_prep_splines need neither the power
+// spectrum of this step nor the delta_tot rows: a host that knows the scale factor of the coming step (the PM hook does:
+// it is an argument of add_nu_power_to_rhogrid) can have them computed on a side stream WHILE K1 sweeps the grid.
+// ksn_delta_nu_integrate uses the prefetched tables if -- and only if -- every input they depend on is bit-for-bit what
+// it is called with (a, TimeTransfer, light, the Na knots, the background table); otherwise it computes them itself.
+struct K2Prefetch {
+    bool valid = false;
+    double a = 0, a0 = 0, light = 0;
+    int Na = 0;
+    double *sf = nullptr; int sf_cap = 0;     // host copy of the knots the tables were built for
+    const double *bg = nullptr; int bg_n = 0; double bg_lo = 0, bg_h = 0; int bg_npatch = 0;
+    double *d_buf = nullptr; size_t cap = 0;  // device: knots | fsscales | fslengths | fs_c | sa | sg | fs_b | fs_d | dta | dtg | evals | status
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr, main_idle = nullptr;
+    double *h_sf = nullptr; size_t h_cap = 0; // pinned staging of the knots
+};
+static K2Prefetch g_pre;
+
+struct K2PreLayout { double *knots, *fsscales, *fslengths, *fsc, *sa, *sg, *fsb, *fsd, *dta, *dtg; unsigned long long *evals; int *status; size_t bytes; };
+static K2PreLayout k2_pre_layout(double *base, int Na)
+{
+    const size_t Nfs = (size_t) 16 * Na;
+    Bump bp{ (char *) base };
+    K2PreLayout l;
+    l.knots = bp.take<double>(Na);
+    l.fsscales = bp.take<double>(Nfs); l.fslengths = bp.take<double>(Nfs); l.fsc = bp.take<double>(Nfs);
+    l.sa = bp.take<double>(Nfs); l.sg = bp.take<double>(Nfs); l.fsb = bp.take<double>(Nfs); l.fsd = bp.take<double>(Nfs);
+    l.dta = bp.take<double>(Na); l.dtg = bp.take<double>(Na);
+    l.evals = bp.take<unsigned long long>(1);
+    l.status = bp.take<int>(Nfs);
+    l.bytes = bp.off + 64;
+    return l;
+}
+
+namespace ksn {
+void k2_prefetch_shutdown()
+{
+    K2Prefetch &q = g_pre;
+    if (q.d_buf) cudaFree(q.d_buf);
+    if (q.h_sf) cudaFreeHost(q.h_sf);
+    if (q.done) cudaEventDestroy(q.done);
+    if (q.main_idle) cudaEventDestroy(q.main_idle);
+    if (q.stream) cudaStreamDestroy(q.stream);
+    free(q.sf);
+    q = K2Prefetch();
+}
+}  // namespace ksn
+
+extern "C" int ksn_delta_nu_prefetch(double a, double TimeTransfer, double light, const double *scalefact, int Na, int namax)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    Ctx &c = ctx();
+    K2Prefetch &q = g_pre;
+    q.valid = false;
+    if (!scalefact || Na < 1 || namax < Na || !(a > 0) || !(TimeTransfer > 0)) return set_error(KSN_EINVAL, "ksn_delta_nu_prefetch: bad arguments");
+    if (!c.d_bg) return set_error(KSN_EINVAL, "ksn_delta_nu_prefetch: call ksn_set_background first");
+    const double loga0 = log(TimeTransfer), loga = log(a);
+    if (loga0 < c.bg_lo + 2 * c.bg_h || loga > c.bg_hi - 2 * c.bg_h) return set_error(KSN_EINVAL, "ksn_delta_nu_prefetch: outside the background table");
+    if (!q.stream) {
+        KSN_CUDA(cudaStreamCreateWithFlags(&q.stream, cudaStreamNonBlocking));
+        KSN_CUDA(cudaEventCreateWithFlags(&q.done, cudaEventDisableTiming));
+        KSN_CUDA(cudaEventCreateWithFlags(&q.main_idle, cudaEventDisableTiming));
+    }
+    // sized for a full history the first time (no reallocation during a run: see ksn_delta_nu_integrate)
+    const K2PreLayout full = k2_pre_layout(nullptr, namax);
+    if (full.bytes > q.cap) {
+        KSN_CUDA(cudaStreamSynchronize(q.stream));
+        if (q.d_buf) cudaFree(q.d_buf);
+        q.d_buf = nullptr; q.cap = 0;
+        KSN_CUDA(cudaMalloc((void **) &q.d_buf, full.bytes));
+        q.cap = full.bytes;
+    }
+    if ((size_t) namax * sizeof(double) > q.h_cap) {
+        KSN_CUDA(cudaStreamSynchronize(q.stream));
+        if (q.h_sf) cudaFreeHost(q.h_sf);
+        q.h_sf = nullptr; q.h_cap = 0;
+        KSN_CUDA(cudaHostAlloc((void **) &q.h_sf, (size_t) namax * sizeof(double), cudaHostAllocDefault));
+        q.h_cap = (size_t) namax * sizeof(double);
+    }
+    if (q.sf_cap < namax) {
+        free(q.sf);
+        q.sf = (double *) malloc(sizeof(double) * namax);
+        q.sf_cap = q.sf ? namax : 0;
+        if (!q.sf) return set_error(KSN_ENOMEM, "ksn_delta_nu_prefetch: out of host memory");
+    }
+    // the previous tables may still be read by a K2 launch on the main stream: order this prefetch behind it
+    KSN_CUDA(cudaEventRecord(q.main_idle, c.stream));
+    KSN_CUDA(cudaStreamWaitEvent(q.stream, q.main_idle, 0));
+    KSN_CUDA(cudaStreamSynchronize(q.stream));          // the pinned knots of the previous prefetch have been consumed
+    memcpy(q.h_sf, scalefact, sizeof(double) * Na);
+    memcpy(q.sf, scalefact, sizeof(double) * Na);
+    const K2PreLayout l = k2_pre_layout(q.d_buf, Na);
+    const int Nfs = 16 * Na;
+    KSN_CUDA(cudaMemcpyAsync(l.knots, q.h_sf, sizeof(double) * Na, cudaMemcpyHostToDevice, q.stream));
+    KSN_CUDA(cudaMemsetAsync(l.evals, 0, sizeof(unsigned long long) + 8 + (size_t) Nfs * sizeof(int), q.stream));   // evals | status (adjacent)
+    const BgTable bg = bg_table();
+    fs_knots_kernel<<<(Nfs + 127) / 128, 128, 0, q.stream>>>(loga0, loga, Nfs, l.fsscales);
+    fslength_kernel<<<Nfs, K2_THREADS, 0, q.stream>>>(bg, l.fsscales, Nfs, loga, light, l.fslengths, l.status, l.evals);
+    k2_prep_splines_kernel<<<2, 256, 0, q.stream>>>(l.fsscales, l.fslengths, Nfs, l.fsc, l.fsb, l.fsd, l.sa, l.sg, l.knots, Na, l.dta, l.dtg);
+    c.launches += 3;
+    KSN_CUDA(cudaGetLastError());
+    KSN_CUDA(cudaEventRecord(q.done, q.stream));
+    q.a = a; q.a0 = TimeTransfer; q.light = light; q.Na = Na;
+    q.bg = c.d_bg; q.bg_n = c.bg_n; q.bg_lo = c.bg_lo; q.bg_h = c.bg_h; q.bg_npatch = g_bg_npatch;
+    q.valid = true;
+    return KSN_OK;
+}
+
 extern "C" int ksn_delta_nu_integrate(const ksn_delta_nu_args *A, double *out, unsigned long long *n_evals)
 {
     int rc = ensure_init();
@@ -980,34 +1092,46 @@ extern "C" int ksn_delta_nu_integrate(const ksn_delta_nu_args *A, double *out, u
         !A->scalefact || !A->delta_tot || !A->wavenum || !A->delta_nu_init || !(A->a > 0) || !(A->TimeTransfer > 0))
         return set_error(KSN_EINVAL, "ksn_delta_nu_integrate: bad arguments");
     if (!c.d_bg) return set_error(KSN_EINVAL, "ksn_delta_nu_integrate: call ksn_set_background first");
-    const int nk = A->nk, Na = A->Na, ns = A->nspecies, Nfs = 16 * Na;
+    const int nk = A->nk, Na = A->Na, ns = A->nspecies, Nfs = 16 * Na, namax = A->namax;
     const double loga0 = log(A->TimeTransfer), loga = log(A->a);
     if (loga0 < c.bg_lo + 2 * c.bg_h || loga > c.bg_hi - 2 * c.bg_h)
         return set_error(KSN_EINVAL, "ksn_delta_nu_integrate: [%g,%g] outside the background table [%g,%g]", loga0, loga, c.bg_lo, c.bg_hi);
     bool any_integral = false;
     for (int s = 0; s < ns; s++) any_integral |= A->integrate[s] != 0;
 
-    // one pinned staging block -> one device block.  Both are sized for a FULL history (namax rows, three species) the
-    // first time, so that no step of a run ever reallocates: cudaFree / cudaMalloc / cudaHostAlloc cost ~0.1 s each once
-    // peer access between the GPUs of the box is on (measured: one 104 ms step when the 100th row arrived)
-    const size_t n_in = (size_t) Na + (size_t) nk * A->namax + 2 * (size_t) nk;
+    // Were the a-only tables prefetched for exactly these inputs (ksn_delta_nu_prefetch)?
+    K2Prefetch &q = g_pre;
+    const bool hit = q.valid && q.a == A->a && q.a0 == A->TimeTransfer && q.light == A->light && q.Na == Na &&
+                     q.bg == c.d_bg && q.bg_n == c.bg_n && q.bg_lo == c.bg_lo && q.bg_h == c.bg_h && q.bg_npatch == g_bg_npatch &&
+                     memcmp(q.sf, A->scalefact, sizeof(double) * Na) == 0;
+    q.valid = false;                     // single use either way
+    g_last_prefetch_hit = hit ? 1 : 0;
+
+    // Device block: [scalefact: namax slots | delta_tot: nk rows of namax | wavenum nk | delta_nu_init nk], the reference's own
+    // layout of the first two (delta_tot_table.c:40-46), so that a table whose block is page-locked (the host layer
+    // registers it, src/deltatot.c) goes up in ONE DMA without a staging copy.  Sized for a full history (three species)
+    // the first time, so that no step of a run ever reallocates: cudaFree / cudaMalloc / cudaHostAlloc cost ~0.1 s each
+    // once peer access between the GPUs of the box is on (measured: one 104 ms step when the 100th row arrived).
+    const size_t n_blk = (size_t) namax + (size_t) nk * namax, n_in = n_blk + 2 * (size_t) nk;
+    const size_t n_res = (size_t) 3 * nk + 8 + ((size_t) 3 * nk + 16 * (size_t) namax + 8) / 2;     // out | evals | status, in doubles
     {
-        const size_t cNa = (size_t) A->namax, cNfs = 16 * cNa, cns = 3;
-        const size_t c_in = cNa + (size_t) nk * A->namax + 2 * (size_t) nk;
-        const size_t dev_doubles = c_in + 3 * cNfs + 4 * cNfs + 2 * cNa + cns * nk + 16;
-        const size_t dev_bytes = dev_doubles * sizeof(double) + (cns * nk + cNfs) * sizeof(int) + 256;
-        rc = ensure_device_buffer((void **) &c.d_k2, &c.k2_cap, dev_bytes);
+        const size_t cNfs = 16 * (size_t) namax;
+        const size_t dev_doubles = n_in + 3 * cNfs + 4 * cNfs + 2 * (size_t) namax + n_res + 32;
+        rc = ensure_device_buffer((void **) &c.d_k2, &c.k2_cap, dev_doubles * sizeof(double) + 256);
         if (rc) return rc;
-        const size_t h_bytes = c_in * sizeof(double) + cns * nk * sizeof(double) + (cns * nk + cNfs) * sizeof(int) + 64;
-        rc = ensure_pinned_buffer((void **) &c.h_k2, &c.h_k2_cap, h_bytes);
+        rc = ensure_pinned_buffer((void **) &c.h_k2, &c.h_k2_cap, (n_in + n_res + 16) * sizeof(double));
         if (rc) return rc;
     }
     KSN_CUDA(cudaStreamSynchronize(c.stream));
+    const bool contiguous = A->delta_tot == A->scalefact + namax;
+    const bool direct = contiguous && host_range_registered(A->scalefact, n_blk * sizeof(double));
     double *h = c.h_k2;
-    memcpy(h, A->scalefact, sizeof(double) * Na);
-    memcpy(h + Na, A->delta_tot, sizeof(double) * (size_t) nk * A->namax);
-    memcpy(h + Na + (size_t) nk * A->namax, A->wavenum, sizeof(double) * nk);
-    memcpy(h + Na + (size_t) nk * A->namax + nk, A->delta_nu_init, sizeof(double) * nk);
+    if (!direct) {
+        memcpy(h, A->scalefact, sizeof(double) * Na);
+        memcpy(h + namax, A->delta_tot, sizeof(double) * (size_t) nk * namax);
+    }
+    memcpy(h + n_blk, A->wavenum, sizeof(double) * nk);
+    memcpy(h + n_blk + nk, A->delta_nu_init, sizeof(double) * nk);
 
     Bump bp{ (char *) c.d_k2 };
     double *d_in = bp.take<double>(n_in);
@@ -1015,24 +1139,40 @@ extern "C" int ksn_delta_nu_integrate(const ksn_delta_nu_args *A, double *out, u
     double *d_sa = bp.take<double>(Nfs), *d_sg = bp.take<double>(Nfs);
     double *d_fsb = bp.take<double>(Nfs), *d_fsd = bp.take<double>(Nfs);
     double *d_dta = bp.take<double>(Na), *d_dtg = bp.take<double>(Na);
+    // results, one contiguous span (one memset, one copy back): delta_nu | evaluations | per-bin status | fslength status
     double *d_out = bp.take<double>((size_t) ns * nk);
     unsigned long long *d_evals = bp.take<unsigned long long>(1);
     int *d_status = bp.take<int>((size_t) ns * nk + Nfs);
-    if (bp.off > c.k2_cap) return set_error(KSN_ENOMEM, "K2 workspace accounting error");
+    const size_t res_bytes = (size_t) ((char *) (d_status + (size_t) ns * nk + Nfs) - (char *) d_out);
+    if (bp.off > c.k2_cap || res_bytes > n_res * sizeof(double)) return set_error(KSN_ENOMEM, "K2 workspace accounting error");
+    int *d_fs_status = d_status + (size_t) ns * nk;
+    if (hit) {
+        const K2PreLayout l = k2_pre_layout(q.d_buf, Na);
+        d_fsscales = l.fsscales; d_fslengths = l.fslengths; d_fsc = l.fsc; d_fsb = l.fsb; d_fsd = l.fsd; d_dta = l.dta; d_dtg = l.dtg;
+    }
 
     phase_begin(PH_K2);
-    KSN_CUDA(cudaMemcpyAsync(d_in, h, n_in * sizeof(double), cudaMemcpyHostToDevice, c.stream));
-    KSN_CUDA(cudaMemsetAsync(d_evals, 0, sizeof(unsigned long long), c.stream));
-    KSN_CUDA(cudaMemsetAsync(d_status, 0, ((size_t) ns * nk + Nfs) * sizeof(int), c.stream));
+    if (direct) KSN_CUDA(cudaMemcpyAsync(d_in, A->scalefact, n_blk * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    else KSN_CUDA(cudaMemcpyAsync(d_in, h, n_blk * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    KSN_CUDA(cudaMemcpyAsync(d_in + n_blk, h + n_blk, 2 * (size_t) nk * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    KSN_CUDA(cudaMemsetAsync(d_evals, 0, (size_t) ((char *) (d_status + (size_t) ns * nk + Nfs) - (char *) d_evals), c.stream));
     const BgTable bg = bg_table();
-    // The fs table is needed for the initial-condition term too (its knot 0 is fslength(log a0, log a)).
-    fs_knots_kernel<<<(Nfs + 127) / 128, 128, 0, c.stream>>>(loga0, loga, Nfs, d_fsscales);
-    fslength_kernel<<<any_integral ? Nfs : 1, K2_THREADS, 0, c.stream>>>(bg, d_fsscales, any_integral ? Nfs : 1, loga, A->light,
-                                                                        d_fslengths, d_status + (size_t) ns * nk, d_evals);
-    c.launches += 2;
-    if (any_integral) {
-        k2_prep_splines_kernel<<<2, 256, 0, c.stream>>>(d_fsscales, d_fslengths, Nfs, d_fsc, d_fsb, d_fsd, d_sa, d_sg, d_in, Na, d_dta, d_dtg);
-        c.launches++;
+    if (hit) {
+        // tables, their quadrature status and evaluation count come from the prefetch (side stream, beside K1)
+        KSN_CUDA(cudaStreamWaitEvent(c.stream, q.done, 0));
+        const K2PreLayout l = k2_pre_layout(q.d_buf, Na);
+        KSN_CUDA(cudaMemcpyAsync(d_fs_status, l.status, (size_t) Nfs * sizeof(int), cudaMemcpyDeviceToDevice, c.stream));
+        KSN_CUDA(cudaMemcpyAsync(d_evals, l.evals, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c.stream));
+    } else {
+        // The fs table is needed for the initial-condition term too (its knot 0 is fslength(log a0, log a)).
+        fs_knots_kernel<<<(Nfs + 127) / 128, 128, 0, c.stream>>>(loga0, loga, Nfs, d_fsscales);
+        fslength_kernel<<<any_integral ? Nfs : 1, K2_THREADS, 0, c.stream>>>(bg, d_fsscales, any_integral ? Nfs : 1, loga, A->light,
+                                                                            d_fslengths, d_fs_status, d_evals);
+        c.launches += 2;
+        if (any_integral) {
+            k2_prep_splines_kernel<<<2, 256, 0, c.stream>>>(d_fsscales, d_fslengths, Nfs, d_fsc, d_fsb, d_fsd, d_sa, d_sg, d_in, Na, d_dta, d_dtg);
+            c.launches++;
+        }
     }
     const int k_first = 0, k_count = nk;
     K2Dev p;
@@ -1043,7 +1183,7 @@ extern "C" int ksn_delta_nu_integrate(const ksn_delta_nu_args *A, double *out, u
         p.mnubykT[s] = s < ns ? A->mnubykT[s] : 0; p.qc[s] = s < ns ? A->qc[s] : 0;
         p.relerr[s] = s < ns ? A->relerr[s] : 1e-6; p.integrate[s] = s < ns ? A->integrate[s] : 0;
     }
-    p.scalefact = d_in; p.delta_tot = d_in + Na; p.wavenum = d_in + Na + (size_t) nk * A->namax;
+    p.scalefact = d_in; p.delta_tot = d_in + namax; p.wavenum = d_in + n_blk;
     p.delta_nu_init = p.wavenum + nk;
     p.fsscales = d_fsscales; p.fslengths = d_fslengths; p.fs_c = d_fsc; p.fs_b = d_fsb; p.fs_d = d_fsd; p.dt_alpha = d_dta; p.dt_gamma = d_dtg;
     p.out = d_out; p.status = d_status; p.evals = d_evals; p.bg = bg;
@@ -1061,12 +1201,10 @@ extern "C" int ksn_delta_nu_integrate(const ksn_delta_nu_args *A, double *out, u
     }
     c.launches++;
     KSN_CUDA(cudaGetLastError());
-    double *h_out = h + n_in;
-    int *h_status = (int *) (h_out + (size_t) ns * nk);
-    unsigned long long *h_evals = (unsigned long long *) (h_status + (size_t) ns * nk + Nfs + ((ns * nk + Nfs) & 1));
-    KSN_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(double) * ns * nk, cudaMemcpyDeviceToHost, c.stream));
-    KSN_CUDA(cudaMemcpyAsync(h_status, d_status, sizeof(int) * ((size_t) ns * nk + Nfs), cudaMemcpyDeviceToHost, c.stream));
-    KSN_CUDA(cudaMemcpyAsync(h_evals, d_evals, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
+    double *h_out = h + n_in + (16 - (n_in & 15)) % 16;                 // the result span, laid out as on the device
+    int *h_status = (int *) ((char *) h_out + ((char *) d_status - (char *) d_out));
+    unsigned long long *h_evals = (unsigned long long *) ((char *) h_out + ((char *) d_evals - (char *) d_out));
+    KSN_CUDA(cudaMemcpyAsync(h_out, d_out, res_bytes, cudaMemcpyDeviceToHost, c.stream));
     phase_end(PH_K2);
     KSN_CUDA(cudaStreamSynchronize(c.stream));
     phase_collect();

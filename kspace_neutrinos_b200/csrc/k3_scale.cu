@@ -523,7 +523,9 @@ int k3_upload_table(int dims, double boxsize, const double *logkk, const double 
     // the cells run from the first knot to the largest k^2 of the grid (or the last knot, whichever is larger), so that a
     // mode at or above the first knot needs no bound on its cell index
     const double k2max = 3.0 * (double) (dims / 2) * (double) (dims / 2);
-    const double lo = log2(seg[0].K2), hi = fmax(log2(seg[nbins - 1].K2), log2(fmax(k2max, 2.0)) + 1e-3);
+    const double lunit = log(unit);
+    auto lg2K2 = [&](int i) { return 2.0 * (logkk[i] + lunit) * (1.0 / M_LN2); };     // log2(K2_i) without a libm call per knot
+    const double lo = lg2K2(0), hi = fmax(lg2K2(nbins - 1), log2(fmax(k2max, 2.0)) + 1e-3);
     // cells narrow enough that (with the float-rounding guard) no cell sees two knots; where the knots are closer than the
     // finest cells (keff values are data-dependent means: nothing forbids it, and gsl_interp has no such limit) the
     // segment search steps over the extra knots in a loop instead
@@ -537,7 +539,7 @@ int k3_upload_table(int dims, double boxsize, const double *logkk, const double 
     {
         int k = 0;
         for (int i = 1; i < nbins; i++) {
-            int first = (int) ceil((log2(seg[i].K2) - lo) * scale + 0.02);
+            int first = (int) ceil((lg2K2(i) - lo) * scale + 0.02);
             if (first > cells) first = cells;
             for (; k < first; k++) cell[k] = (unsigned short) (i - 1);
         }
@@ -569,9 +571,9 @@ int k3_upload_table(int dims, double boxsize, const double *logkk, const double 
     for (int i = 0; i < nbins; i++) {
         const double umax = i + 1 < nbins ? seg[i + 1].K2 * seg[i].inv - 1.0 : 0.0;
         const double ab = fabs(seg[i].B);
-        if (umax < 0.03125) worst_d5 = fmax(worst_d5, ab * pow(umax, 6) / 6.0);
-        else worst_d5 = fmax(worst_d5, ab * pow(0.03125, 6) / 6.0);        // the part of a wide segment below the log1p switch
-        worst_f32 = fmax(worst_f32, ab * (1.0 + 3.0 * fmin(umax, 1.0)) + fabs(seg[i].A - 1.0) + ab * log1p(fmin(umax, 1e30)));
+        const double uc = umax < 0.03125 ? umax : 0.03125, uc2 = uc * uc;   // (of a wide segment: the part below the log1p switch)
+        worst_d5 = fmax(worst_d5, ab * (uc2 * uc2 * uc2) * (1.0 / 6.0));
+        worst_f32 = fmax(worst_f32, ab * (1.0 + 3.0 * fmin(umax, 1.0)) + fabs(seg[i].A - 1.0) + ab * fmin(umax, 1e30));   // (ln(1+u) <= u)
         segf[i].inv = (float) seg[i].inv; segf[i].A1 = (float) (norm * ratio[i]); segf[i].B = (float) seg[i].B; segf[i].pad = 0;
     }
     segf[nbins] = segf[nbins - 1]; segf[nbins].B = 0; segf[nbins].inv = 0;
@@ -651,9 +653,7 @@ int k3_launch(void *dgrid, int real_bytes, int dims, long long plane0_global, lo
     const bool aligned = ((uintptr_t) dgrid & 15) == 0;
     const bool bulk = !getenv("KSN_K3_NOTMA") && aligned;       // bulk copies need 16-byte granules
     auto shared_cfg = [&](auto kern, size_t smem) -> int {
-        KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 58));   // ~132 of 228 KB: L1 keeps the tables
-        return KSN_OK;
+        return func_attributes((const void *) kern, smem, 58);      // carve-out ~132 of 228 KB: L1 keeps the tables
     };
     auto done = [&]() -> int {
         c.launches++;

@@ -329,6 +329,26 @@ int ensure_host_pinned(const void *p, size_t bytes)
     return 1;
 }
 
+// cudaFuncSetAttribute once per (kernel, value): the launchers run every PM step, and the attribute calls are a few
+// microseconds each of host time between two kernels (forgotten at ksn_shutdown: a new context starts from defaults)
+static std::map<const void *, std::pair<size_t, int>> g_func_attr;
+int func_attributes(const void *kern, size_t dyn_smem, int carveout)
+{
+    auto it = g_func_attr.find(kern);
+    if (it != g_func_attr.end() && it->second.first == dyn_smem && it->second.second == carveout) return KSN_OK;
+    KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn_smem));
+    if (carveout >= 0) KSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
+    g_func_attr[kern] = std::make_pair(dyn_smem, carveout);
+    return KSN_OK;
+}
+
+// was exactly this range page-locked through ksn_host_register (and not unregistered since)?
+bool host_range_registered(const void *p, size_t bytes)
+{
+    auto it = g_registered.find((uintptr_t) p);
+    return it != g_registered.end() && it->second >= bytes;
+}
+
 // ---------------------------------------------------------------- synthetic grid
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x)
 {
@@ -392,6 +412,8 @@ void ksn_shutdown(void)
     cudaSetDevice(c.device);
     cudaDeviceSynchronize();
     fft_shutdown();
+    k2_prefetch_shutdown();
+    g_func_attr.clear();
     drop_comm();
     k1_tables_invalidate();
     for (auto &kv : g_registered) cudaHostUnregister((void *) kv.first);

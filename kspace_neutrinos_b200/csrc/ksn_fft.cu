@@ -18,6 +18,8 @@
 //     written once, at its final address.  Two rounds of the peer-memory flag protocol (ksn_p2p.cuh) fence it: nobody
 //     writes into a slab its owner may still be reading, nobody reads its slab before every peer's rows have landed;
 //  3. 1-D c2c along x (stride N/2+1) of every (y, kz) column of the received slab, in place (cuFFT, one call per y plane).
+// The stages overlap: the exchange of a batch of planes runs on a stream of its own while cuFFT transforms the next batch
+// (the 2-D pass is HBM-bound, the exchange NVLink-bound), and the per-plane 1-D calls are dealt to four streams.
 // The inverse runs the same steps backwards (c2c inverse, the mirrored exchange, 2-D c2r); unnormalised like FFTW.
 // One rank: the same kernels with every row local.
 #include "ksn_internal.cuh"
@@ -77,10 +79,15 @@ struct FftState {
     bool planned = false;
     int N = 0, R = 1, rank = 0;
     long long xs[KSN_P2P_MAX_RANKS + 1] = {}, ys[KSN_P2P_MAX_RANKS + 1] = {};   // FFTW-style partitions of x and y planes
-    cufft_handle p2d_f = 0, p2d_i = 0, p1d = 0;
+    static constexpr int K1D = 4;         // streams (and plans) the per-plane 1-D transforms are dealt to
+    static constexpr int G1D = 8;         // y planes per 1-D batch (the unit the inverse hands to the exchange)
+    cufft_handle p2d_f = 0, p2d_i = 0, p1d[K1D] = {};
     bool have2d = false, have1d = false;
     int batch2d = 0;
     void *work = nullptr; size_t work_bytes = 0;
+    void *work1d[K1D] = {};
+    cudaStream_t xstream = nullptr, s1d[K1D] = {};    // exchange stream, 1-D streams
+    cudaEvent_t *evp = nullptr; int nevp = 0;         // event pool: one per batch in flight
     // the k-space slabs of all ranks as mapped in this process (slab[rank] = the pointer the caller registered)
     void *slab[KSN_P2P_MAX_RANKS] = {};
     bool opened[KSN_P2P_MAX_RANKS] = {};
@@ -90,7 +97,7 @@ struct FftState {
     double *d_token = nullptr;            // one double: the payload of the barrier rounds
     cudaEvent_t ev[5] = {};               // stage boundaries of the last transform (ksn_fft_timing)
     bool have_ev = false;
-    float stage_ms[4] = {};               // 2-D pass | wait for the peers | transpose + exchange (+ its fence) | 1-D pass
+    float stage_ms[4] = {};               // wait for the peers | 2-D pass with the exchange behind it | closing fence | 1-D pass
 };
 static FftState g_fft;
 
@@ -135,10 +142,11 @@ static void fft_release_plans()
 {
     FftState &f = g_fft;
     if (f.have2d && g_cufft.Destroy) { g_cufft.Destroy(f.p2d_f); g_cufft.Destroy(f.p2d_i); }
-    if (f.have1d && g_cufft.Destroy) g_cufft.Destroy(f.p1d);
+    if (f.have1d && g_cufft.Destroy) for (int k = 0; k < FftState::K1D; k++) g_cufft.Destroy(f.p1d[k]);
     f.have2d = f.have1d = false;
     if (f.work) cudaFree(f.work);
     f.work = nullptr; f.work_bytes = 0;
+    for (int k = 0; k < FftState::K1D; k++) { if (f.work1d[k]) cudaFree(f.work1d[k]); f.work1d[k] = nullptr; }
 }
 
 static void fft_unmap()
@@ -167,9 +175,8 @@ static void fft_collect(bool inverse)
     FftState &f = g_fft;
     float t[4] = {};
     for (int i = 0; i < 4; i++) cudaEventElapsedTime(&t[i], f.ev[i], f.ev[i + 1]);
-    // stages in the order of the forward transform
-    if (!inverse) { for (int i = 0; i < 4; i++) f.stage_ms[i] = t[i]; }
-    else { f.stage_ms[0] = t[3]; f.stage_ms[1] = t[1]; f.stage_ms[2] = t[2]; f.stage_ms[3] = t[0]; }
+    (void) inverse;
+    for (int i = 0; i < 4; i++) f.stage_ms[i] = t[i];
 }
 
 void fft_shutdown()
@@ -177,6 +184,10 @@ void fft_shutdown()
     fft_release_plans();
     fft_unmap();
     if (g_fft.have_ev) for (auto &e : g_fft.ev) cudaEventDestroy(e);
+    for (int i = 0; i < g_fft.nevp; i++) cudaEventDestroy(g_fft.evp[i]);
+    free(g_fft.evp);
+    if (g_fft.xstream) cudaStreamDestroy(g_fft.xstream);
+    for (auto &st : g_fft.s1d) if (st) cudaStreamDestroy(st);
     if (g_fft.d_token) cudaFree(g_fft.d_token);
     g_fft = FftState();
 }
@@ -235,22 +246,36 @@ extern "C" int ksn_fft_plan(int dims, int nranks, int rank)
         KSN_FFT(g_cufft.SetStream(f.p2d_f, c.stream));
         KSN_FFT(g_cufft.SetStream(f.p2d_i, c.stream));
     }
+    if (!f.xstream) KSN_CUDA(cudaStreamCreateWithFlags(&f.xstream, cudaStreamNonBlocking));
+    for (auto &st : f.s1d) if (!st) KSN_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     if (ny > 0) {
         int n1[1] = { N }, embed[1] = { N };
-        size_t ws = 0;
-        KSN_FFT(g_cufft.Create(&f.p1d));
-        f.have1d = true;
-        KSN_FFT(g_cufft.SetAutoAllocation(f.p1d, 0));
-        // along x inside one y plane [x][kz]: element stride L, the L columns one after the other
-        KSN_FFT(g_cufft.MakePlanMany(f.p1d, 1, n1, embed, L, 1, embed, L, 1, CUFFT_Z2Z_, L, &ws));
-        if (ws > ws_max) ws_max = ws;
-        KSN_FFT(g_cufft.SetStream(f.p1d, c.stream));
+        for (int k = 0; k < FftState::K1D; k++) {
+            size_t ws = 0;
+            KSN_FFT(g_cufft.Create(&f.p1d[k]));
+            if (k == 0) f.have1d = true;
+            KSN_FFT(g_cufft.SetAutoAllocation(f.p1d[k], 0));
+            // along x inside one y plane [x][kz]: element stride L, the L columns one after the other
+            KSN_FFT(g_cufft.MakePlanMany(f.p1d[k], 1, n1, embed, L, 1, embed, L, 1, CUFFT_Z2Z_, L, &ws));
+            if (ws) { KSN_CUDA(cudaMalloc(&f.work1d[k], ws)); KSN_FFT(g_cufft.SetWorkArea(f.p1d[k], f.work1d[k])); }
+            KSN_FFT(g_cufft.SetStream(f.p1d[k], f.s1d[k]));
+        }
     }
     if (ws_max) {
         KSN_CUDA(cudaMalloc(&f.work, ws_max));
         f.work_bytes = ws_max;
         if (f.have2d) { KSN_FFT(g_cufft.SetWorkArea(f.p2d_f, f.work)); KSN_FFT(g_cufft.SetWorkArea(f.p2d_i, f.work)); }
-        if (f.have1d) KSN_FFT(g_cufft.SetWorkArea(f.p1d, f.work));
+    }
+    {
+        const long long nb2 = nx > 0 ? nx / f.batch2d + 1 : 1, nb1 = ny / FftState::G1D + 2;
+        const int want = (int) (nb2 > nb1 ? nb2 : nb1) + FftState::K1D + 4;
+        if (want > f.nevp) {
+            cudaEvent_t *np = (cudaEvent_t *) realloc(f.evp, sizeof(cudaEvent_t) * want);
+            if (!np) return set_error(KSN_ENOMEM, "ksn_fft_plan: out of host memory");
+            f.evp = np;
+            for (int i = f.nevp; i < want; i++) KSN_CUDA(cudaEventCreateWithFlags(&f.evp[i], cudaEventDisableTiming));
+            f.nevp = want;
+        }
     }
     f.planned = true;
     return KSN_OK;
@@ -318,6 +343,42 @@ static int fft_check(const char *who, void *d_real, void *d_kspace)
     return KSN_OK;
 }
 
+// rows [p0, p0 + np) x N of `src` (complex view, L per row) to their owners, on f.xstream
+static int fft_exchange(const void *src, void *const *dest, const long long *lo, long long own0, long long p0, long long np)
+{
+    FftState &f = g_fft;
+    const int N = f.N, L = N / 2 + 1;
+    if (np <= 0) return KSN_OK;
+    if (np * N > 0x7fffffffLL) return set_error(KSN_EINVAL, "ksn_fft: %lld rows in one exchange batch", np * N);
+    ExchangePlan p;
+    for (int r = 0; r < KSN_P2P_MAX_RANKS; r++) p.peer[r] = (double2 *) dest[r];
+    for (int r = 0; r <= f.R; r++) p.lo[r] = lo[r];
+    p.R = f.R; p.N = N; p.L = L; p.own0 = own0 + p0; p.nown = np;
+    fft_exchange_kernel<<<(unsigned) (np * N), 256, 0, f.xstream>>>((const double2 *) src + (size_t) p0 * N * L, p);
+    ctx().launches++;
+    KSN_CUDA(cudaGetLastError());
+    return KSN_OK;
+}
+
+// the per-plane 1-D transforms of planes [0, ny), batch j (G1D planes) on stream j % K1D; batch j's event is evp[j]
+static int fft_1d_batches(void *d_kspace, long long ny, int dir, cudaEvent_t after)
+{
+    FftState &f = g_fft;
+    const int N = f.N, L = N / 2 + 1;
+    for (int k = 0; k < FftState::K1D; k++) KSN_CUDA(cudaStreamWaitEvent(f.s1d[k], after, 0));
+    int j = 0;
+    for (long long y0 = 0; y0 < ny; y0 += FftState::G1D, j++) {
+        const int k = j % FftState::K1D;
+        const long long y1 = y0 + FftState::G1D < ny ? y0 + FftState::G1D : ny;
+        for (long long y = y0; y < y1; y++) {
+            void *plane = (char *) d_kspace + (size_t) y * N * L * 16;
+            KSN_FFT(g_cufft.ExecZ2Z(f.p1d[k], plane, plane, dir));
+        }
+        KSN_CUDA(cudaEventRecord(f.evp[j], f.s1d[k]));
+    }
+    return KSN_OK;
+}
+
 extern "C" int ksn_fft_forward(void *d_real, void *d_kspace)
 {
     int rc = fft_check("ksn_fft_forward", d_real, d_kspace);
@@ -326,35 +387,39 @@ extern "C" int ksn_fft_forward(void *d_real, void *d_kspace)
     Ctx &c = ctx();
     const int N = f.N, L = N / 2 + 1;
     const long long x0 = f.xs[f.rank], nx = f.xs[f.rank + 1] - x0, ny = f.ys[f.rank + 1] - f.ys[f.rank];
-    // 1. 2-D r2c of every local x plane, in place in the padded grid
+    cudaEvent_t *ev = f.evp, go = f.evp[f.nevp - 1], joined = f.evp[f.nevp - 2];
+    // nobody writes into a slab its owner may still be using (every rank is past whatever it did with its k-space slab)
     fft_mark(0);
-    for (long long p = 0; p < nx; p += f.batch2d) {
+    rc = fft_barrier();
+    if (rc) return rc;
+    fft_mark(1);
+    KSN_CUDA(cudaEventRecord(go, c.stream));
+    KSN_CUDA(cudaStreamWaitEvent(f.xstream, go, 0));
+    // 1. 2-D r2c of the local x planes, batch by batch, in place in the padded grid; 2. behind each batch, on the exchange
+    // stream, its rows go to the k-space slabs of their owners (transposed)
+    int j = 0;
+    for (long long p = 0; p < nx; p += f.batch2d, j++) {
         double *plane = (double *) d_real + (size_t) p * N * 2 * L;
         KSN_FFT(g_cufft.ExecD2Z(f.p2d_f, plane, plane));
+        KSN_CUDA(cudaEventRecord(ev[j], c.stream));
+        KSN_CUDA(cudaStreamWaitEvent(f.xstream, ev[j], 0));
+        rc = fft_exchange(d_real, f.slab, f.ys, x0, p, f.batch2d);
+        if (rc) return rc;
     }
-    // 2. transpose + exchange: nobody writes into a slab its owner may still be using ...
-    fft_mark(1);
-    rc = fft_barrier();
-    if (rc) return rc;
-    fft_mark(2);
-    if (nx > 0) {
-        ExchangePlan p;
-        for (int r = 0; r < KSN_P2P_MAX_RANKS; r++) p.peer[r] = (double2 *) f.slab[r];
-        for (int r = 0; r <= f.R; r++) p.lo[r] = f.ys[r];
-        p.R = f.R; p.N = N; p.L = L; p.own0 = x0; p.nown = nx;
-        if (nx * N > 0x7fffffffLL) return set_error(KSN_EINVAL, "ksn_fft_forward: %lld rows in one slab", nx * N);
-        fft_exchange_kernel<<<(unsigned) (nx * N), 256, 0, c.stream>>>((const double2 *) d_real, p);
-        c.launches++;
-        KSN_CUDA(cudaGetLastError());
-    }
+    KSN_CUDA(cudaEventRecord(joined, f.xstream));
+    KSN_CUDA(cudaStreamWaitEvent(c.stream, joined, 0));
     // ... and nobody reads its slab before every peer's rows have landed
+    fft_mark(2);
     rc = fft_barrier();
     if (rc) return rc;
-    // 3. 1-D c2c along x of every column of the received slab
     fft_mark(3);
-    for (long long y = 0; y < ny; y++) {
-        void *plane = (char *) d_kspace + (size_t) y * N * L * 16;
-        KSN_FFT(g_cufft.ExecZ2Z(f.p1d, plane, plane, CUFFT_FWD));
+    // 3. 1-D c2c along x of every column of the received slab
+    KSN_CUDA(cudaEventRecord(go, c.stream));
+    rc = fft_1d_batches(d_kspace, ny, CUFFT_FWD, go);
+    if (rc) return rc;
+    for (int k = 0; k < FftState::K1D; k++) {
+        KSN_CUDA(cudaEventRecord(joined, f.s1d[k]));
+        KSN_CUDA(cudaStreamWaitEvent(c.stream, joined, 0));
     }
     fft_mark(4);
     KSN_CUDA(cudaStreamSynchronize(c.stream));
@@ -371,25 +436,25 @@ extern "C" int ksn_fft_inverse(void *d_kspace, void *d_real)
     Ctx &c = ctx();
     const int N = f.N, L = N / 2 + 1;
     const long long y0 = f.ys[f.rank], ny = f.ys[f.rank + 1] - y0, nx = f.xs[f.rank + 1] - f.xs[f.rank];
+    cudaEvent_t *ev = f.evp, go = f.evp[f.nevp - 1], joined = f.evp[f.nevp - 2];
     fft_mark(0);
-    for (long long y = 0; y < ny; y++) {
-        void *plane = (char *) d_kspace + (size_t) y * N * L * 16;
-        KSN_FFT(g_cufft.ExecZ2Z(f.p1d, plane, plane, CUFFT_INV));
-    }
-    fft_mark(1);
-    rc = fft_barrier();
+    rc = fft_barrier();                   // every rank is past whatever it did with its real-space grid
     if (rc) return rc;
-    fft_mark(2);
-    if (ny > 0) {
-        ExchangePlan p;
-        for (int r = 0; r < KSN_P2P_MAX_RANKS; r++) p.peer[r] = (double2 *) f.real[r];
-        for (int r = 0; r <= f.R; r++) p.lo[r] = f.xs[r];
-        p.R = f.R; p.N = N; p.L = L; p.own0 = y0; p.nown = ny;
-        if (ny * N > 0x7fffffffLL) return set_error(KSN_EINVAL, "ksn_fft_inverse: %lld rows in one slab", ny * N);
-        fft_exchange_kernel<<<(unsigned) (ny * N), 256, 0, c.stream>>>((const double2 *) d_kspace, p);
-        c.launches++;
-        KSN_CUDA(cudaGetLastError());
+    fft_mark(1);
+    KSN_CUDA(cudaEventRecord(go, c.stream));
+    // 1-D inverse along x, batch by batch on the 1-D streams; behind each batch its rows go back to the x-slabs of their owners
+    rc = fft_1d_batches(d_kspace, ny, CUFFT_INV, go);
+    if (rc) return rc;
+    int j = 0;
+    for (long long y = 0; y < ny; y += FftState::G1D, j++) {
+        KSN_CUDA(cudaStreamWaitEvent(f.xstream, ev[j], 0));
+        rc = fft_exchange(d_kspace, f.real, f.xs, y0, y, y + FftState::G1D < ny ? FftState::G1D : ny - y);
+        if (rc) return rc;
     }
+    if (ny == 0) KSN_CUDA(cudaStreamWaitEvent(f.xstream, go, 0));
+    KSN_CUDA(cudaEventRecord(joined, f.xstream));
+    KSN_CUDA(cudaStreamWaitEvent(c.stream, joined, 0));
+    fft_mark(2);
     rc = fft_barrier();
     if (rc) return rc;
     fft_mark(3);
@@ -404,8 +469,8 @@ extern "C" int ksn_fft_inverse(void *d_kspace, void *d_real)
     return rc;
 }
 
-// stages of the most recent transform on this rank, in ms: 2-D pass | waiting for the peers before the exchange |
-// transpose + exchange kernel and its closing fence | 1-D pass
+// stages of the most recent transform on this rank, in ms.  Forward: waiting for the peers | 2-D pass with the transpose +
+// exchange behind it | closing fence | 1-D pass.  Inverse: waiting | 1-D pass with the exchange behind it | fence | 2-D pass
 extern "C" int ksn_fft_timing(float *ms4)
 {
     if (!ms4 || !g_fft.have_ev) return set_error(KSN_EINVAL, "ksn_fft_timing: no transform yet");

@@ -31,6 +31,9 @@ void allocate_delta_tot_table(_delta_tot_table *d_tot, const int nk_in, const do
     d_tot->delta_tot = (double **) mymalloc("kspace_delta_tot", nk_in * sizeof(double *));
     d_tot->scalefact = (double *) mymalloc("kspace_scalefact", d_tot->namax * (nk_in + 1) * sizeof(double));
     for (int k = 0; k < nk_in; k++) d_tot->delta_tot[k] = d_tot->scalefact + (size_t) d_tot->namax * (k + 1);
+    /* page-lock the history block where there is a device: K2 then copies it up in one DMA, without a staging copy
+     * (unregistered again in free_delta_tot_table; a failure only means the staged path is taken) */
+    if (ksn_device_available()) ksn_host_register(d_tot->scalefact, (size_t) d_tot->namax * (nk_in + 1) * sizeof(double));
     d_tot->delta_nu_init = (double *) mymalloc("kspace_delta_nu_init", 3 * nk_in * sizeof(double));
     d_tot->delta_nu_last = d_tot->delta_nu_init + nk_in;
     d_tot->wavenum = d_tot->delta_nu_init + 2 * nk_in;
@@ -43,6 +46,7 @@ void allocate_delta_tot_table(_delta_tot_table *d_tot, const int nk_in, const do
 
 void free_delta_tot_table(_delta_tot_table *d_tot)
 {
+    if (ksn_device_available()) ksn_host_unregister(d_tot->scalefact);
     myfree(d_tot->delta_tot);
     myfree(d_tot->scalefact);
     myfree(d_tot->delta_nu_init);
@@ -293,6 +297,21 @@ void ksn_ensure_background(double a_lo, double a_hi)
     bgc.a_hi = hi;
     bgc.probe_a[0] = lo; bgc.probe_a[1] = sqrt(lo * hi); bgc.probe_a[2] = hi;
     for (int i = 0; i < 3; i++) bgc.probe_h[i] = hubble_function(bgc.probe_a[i]);
+}
+
+/* The step's scale factor is known before its power spectrum is: have the a-only tables of K2 computed on a side stream
+ * while K1 sweeps the grid (ksn_delta_nu_prefetch).  Predicts what get_delta_nu_update will ask for -- the stored rows plus
+ * the provisional row at log(a) -- and is simply not used if the prediction is off (first step, repeated a, full table). */
+void ksn_prefetch_delta_nu(const _delta_tot_table *const d_tot, const double a)
+{
+    if (!d_tot->delta_tot_init_done || d_tot->ia < 2 || d_tot->ia >= d_tot->namax || d_tot->namax > 4096) return;
+    if (log(a) - d_tot->scalefact[d_tot->ia - 1] < FLOAT_ACC) return;          /* same a: the stored answer is returned */
+    double sf[4096];
+    memcpy(sf, d_tot->scalefact, sizeof(double) * d_tot->ia);
+    sf[d_tot->ia] = log(a);
+    const double a_hi = fmax(a, d_tot->TimeTransfer + (d_tot->namax - 2) / 100.);
+    ksn_ensure_background(fmin(d_tot->TimeTransfer, a), a_hi);                  /* (the range delta_nu_on_device asks for) */
+    ksn_delta_nu_prefetch(a, d_tot->TimeTransfer, d_tot->light, sf, d_tot->ia + 1, d_tot->namax);   /* failure: K2 computes them itself */
 }
 
 /* integrate `ns` species with masses mnu[] in one launch; out is species-major [ns][nk] */

@@ -77,6 +77,7 @@ static void add_nu_power_any(int real_bytes, const double Time, const double Box
     const double *iw;
     struct step_ctx s = { Time, BoxSize, delta_tot_table.nk_allocated };
     if (ksn_bin_tables(pmgrid, s.nk_allocated, &thr, &iw)) terminate(1, "Could not allocate temporary memory for power spectra\n");
+    ksn_prefetch_delta_nu(&delta_tot_table, Time);
     const int rc = asmth2 < 0 ? ksn_step_staged(grid, real_bytes, pmgrid, s.nk_allocated, slabstart_y, nslab_y, thr, iw, BoxSize, between_passes, &s)
                               : ksn_step_staged_greens(grid, real_bytes, pmgrid, s.nk_allocated, slabstart_y, nslab_y, thr, iw, BoxSize, between_passes, &s, asmth2);
     if (rc) ksn_fatal_device(rc, "add_nu_power_to_rhogrid");

@@ -25,6 +25,8 @@ int ksn_bin_tables(int dims, int nrbins, const unsigned int **thresholds, const 
 /* make sure the device table of 1/(aH) covers [a_lo, a_hi] and matches the current hubble_function */
 void ksn_ensure_background(double a_lo, double a_hi);
 void ksn_invalidate_background(void);
+/* start K2's a-only tables for the step at scale factor a on a side stream (beside K1) */
+void ksn_prefetch_delta_nu(const _delta_tot_table *const d_tot, const double a);
 
 /* The collective for the bin sums on the communicator a reference-named entry was handed (-DKSN_HAVE_MPI: the first call
  * with more than one rank picks the backend collectively, later calls return at once; without MPI the handle is an int and

@@ -97,6 +97,14 @@ int ksn_set_background(ksn_hubble_fn hub, void *user, double loga_lo, double log
 }
 
 int ksn_background_loaded(void) { return bg_hub != NULL; }
+/* no device here: nothing to page-lock, nothing to prefetch */
+int ksn_host_register(void *ptr, size_t bytes) { (void) ptr; (void) bytes; return KSN_ENODEV; }
+int ksn_host_unregister(void *ptr) { (void) ptr; return KSN_ENODEV; }
+int ksn_delta_nu_prefetch(double a, double a0, double light, const double *sf, int Na, int namax)
+{
+    (void) a; (void) a0; (void) light; (void) sf; (void) Na; (void) namax;
+    return KSN_ENODEV;
+}
 
 static double inv_a2H(double loga, void *unused)                                   /* delta_tot_table.c:378-384 */
 {

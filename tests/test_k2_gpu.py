@@ -253,3 +253,36 @@ def test_speculative_bisection_is_bit_identical(gpu, masses, hybrid):
         for (g1, p1, ia1), (gm, pm, iam) in zip(runs[1], runs[width]):
             assert ia1 == iam and p1 == pm, (width, p1, pm)
             assert np.array_equal(g1, gm), (width, float(np.max(np.abs(gm / g1 - 1))))
+
+
+@pytest.mark.parametrize("masses,hybrid", [((0.1, 0.1, 0.1), True), ((0.2, 0.1, 0.3), False)])
+def test_prefetched_tables_give_bit_identical_delta_nu(gpu, masses, hybrid):
+    """ksn_delta_nu_prefetch computes the a-only part of K2 (free-streaming table, spline factorisations) on a side stream
+    ahead of the call -- the PM hook uses it to run them beside K1.  Same kernels on the same inputs: delta_nu must equal the
+    un-prefetched call's BIT FOR BIT; a prefetch for other inputs (another a, a changed knot) must simply be ignored."""
+    om = refs.make_omnu(gpu, masses)
+    if hybrid:
+        gpu.init_hybrid_nu(C.byref(om.hybnu), (C.c_double * 3)(*masses), 500.0, 2.99792458e10 / 1e5, 0.333, om.kBtnu)
+    refs.set_background(gpu, om)
+    runs = {}
+    for mode in ("plain", "prefetch", "other_a", "other_knot"):
+        d, kk, dcdm, tr = _benchmark_state(gpu, om)
+        outs = []
+        for i, a in enumerate((0.9805, 0.981, 0.982, 0.9915)):
+            if mode != "plain" and i > 0:                 # (the first call builds the background table the prefetch needs)
+                sf = np.array([d.scalefact[j] for j in range(d.ia)] + [math.log(a)])
+                if mode == "other_a":
+                    sf[-1] = math.log(a * 1.00001)
+                if mode == "other_knot":
+                    sf[3] += 1e-12
+                capi.check(gpu.ksn_delta_nu_prefetch(a * (1.00001 if mode == "other_a" else 1.0), d.TimeTransfer, d.light, refs.dptr(sf), len(sf), d.namax))
+            g = np.zeros(len(kk))
+            gpu.get_delta_nu_update(C.byref(d), a, len(kk), refs.dptr(kk), refs.dptr(dcdm), refs.dptr(g), C.byref(tr))
+            if i > 0:
+                assert gpu.ksn_last_k2_prefetch_used() == (1 if mode == "prefetch" else 0), (mode, i)
+            outs.append((g.copy(), d.ia, gpu.ksn_last_k2_evals()))
+        runs[mode] = outs
+    for mode in ("prefetch", "other_a", "other_knot"):
+        for (g0, ia0, ev0), (g1, ia1, ev1) in zip(runs["plain"], runs[mode]):
+            assert ia0 == ia1 and ev0 == ev1, mode
+            assert np.array_equal(g0, g1), (mode, float(np.max(np.abs(g1 / g0 - 1))))

@@ -119,7 +119,7 @@ def main():
         # bytes the transform must move per rank: 2-D pass r+w, exchange r+w, 1-D pass r+w of the 16 B/mode grid
         print(json.dumps({"pmgrid": n, "gpus": world, "forward_ms": f_ms, "inverse_ms": i_ms, "fft_plus_step_ms": s_ms,
                           "modes_per_s_fft_plus_step": modes / (s_ms * 1e-3), "forward_GBps_per_gpu_of_6_passes": 6 * 16 * modes / world / (f_ms * 1e-3) / 1e9,
-                          "forward_stages_ms_rank0": {"fft2d": st_f[0], "wait_for_peers": st_f[1], "transpose_exchange": st_f[2], "fft1d_along_x": st_f[3]},
+                          "forward_stages_ms_rank0": {"wait_for_peers": st_f[0], "fft2d_with_exchange_behind": st_f[1], "closing_fence": st_f[2], "fft1d_along_x": st_f[3]},
                           "round_trip_max_rel_err": worst, "k1": L.ksn_last_k1_kernel().decode(), "k3": L.ksn_last_k3_kernel().decode()}), flush=True)
     barrier()
     fft.free()

@@ -484,7 +484,7 @@ def ours(args):
             "data": "synthetic", "config": workload_config(n, world, None, args.mnu, not args.no_hybrid), "collective": comm_backend, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "wall_ms_per_step": wall_ms / args.steps,
             "step_wall_ms_rank0": {"min": min(step_wall), "median": statistics.median(step_wall), "max": max(step_wall),
-                                   "slowest_step": step_wall.index(max(step_wall))}}
+                                   "slowest_step": step_wall.index(max(step_wall)), "all": [round(x, 3) for x in step_wall]}}
     if check is not None:
         line["parity_check"] = check
     if greens is not None:

@@ -666,7 +666,8 @@ int k3_launch(void *dgrid, int real_bytes, int dims, long long plane0_global, lo
         const size_t row_bytes = (size_t) L * 16;
         int rpc = segs > 1 ? 1 : cap / L;
         while (rpc > 1 && rpc * row_bytes > 18432) rpc--;
-        if (segs == 1 && rpc > 1 && rpc + 2 <= K3_FLAT_MAX_ROWS) {
+        rpc = min(rpc, K3_FLAT_MAX_ROWS - 2);                      // (tiny grids: the kernel's per-row table is that long)
+        if (segs == 1 && rpc > 1) {
             const int chunk = rpc * L;
             const size_t smem = (size_t) chunk * 16 + 128;
             const long long nct = (total + chunk - 1) / chunk;
@@ -700,7 +701,7 @@ int k3_launch(void *dgrid, int real_bytes, int dims, long long plane0_global, lo
     if (real_bytes == 4 && bulk && total % 2 == 0) {
         const int capf = K3_FLAT_THREADS * K3_EPT, pair = 2 * L;
         // whole row pairs (~16-18 KB of them) where a pair fits one CTA, else the largest even piece
-        const int chunk = pair <= capf ? pair * max(1, min(capf / pair, (int) (18432 / ((size_t) pair * 8)))) : (capf & ~1);
+        const int chunk = pair <= capf ? pair * max(1, min(min(capf / pair, (K3_FLAT_MAX_ROWS - 2) / 2), (int) (18432 / ((size_t) pair * 8)))) : (capf & ~1);
         const long long nct = (total + chunk - 1) / chunk;
         if (nct <= 0x7fffffffLL && chunk / L + 2 <= K3_FLAT_MAX_ROWS) {
             const size_t smem = (size_t) chunk * 8 + 128;

@@ -10,13 +10,14 @@ logic -- which bytes a bulk copy covers, where a thread finds its mode -- is pin
 import pytest
 
 K3_EPT = 9
+K3_FLAT_MAX_ROWS = 64          # rows a chunk may touch (csrc/k3_scale.cu)
 
 
 def k3_flat_chunk(L, threads):
     """k3_launch: whole row pairs (~16-18 KB of them) where a pair fits one CTA, else the largest even piece."""
     capf, pair = threads * K3_EPT, 2 * L
     if pair <= capf:
-        return pair * max(1, min(capf // pair, 18432 // (pair * 8)))
+        return pair * max(1, min(capf // pair, (K3_FLAT_MAX_ROWS - 2) // 2, 18432 // (pair * 8)))
     return capf & ~1
 
 
@@ -39,19 +40,22 @@ def test_k3_flat_chunks_cover_the_slab_and_find_every_mode(n, nplanes):
         zb = e0 - r0 * L
         pl0 = r0 // n
         j0 = r0 - pl0 * n
-        for e in range(nel):                                      # the kernel's per-mode code
-            z, j, gi = zb + e, j0, plane0 + pl0
-            if z >= L:
-                z -= L
-                j += 1
-                if z >= L:
-                    q = z // L
-                    z -= q * L
-                    j += q
+        rows = (zb + nel + L - 1) // L
+        assert rows <= K3_FLAT_MAX_ROWS
+        magic = (0xffffffff // L + 1) & 0xffffffff                # row of a mode by a multiply instead of a division
+        rowtab = []
+        for rl in range(rows):                                    # the kernel's per-row table (threads 0 .. rows-1)
+            j, gi = j0 + rl, plane0 + pl0
             if j >= n:
                 q = j // n
                 j -= q * n
                 gi += q
+            rowtab.append((gi, j))
+        for e in range(nel):                                      # the kernel's per-mode code
+            zz = zb + e
+            rl = (zz * magic) >> 32
+            z = zz - rl * L
+            gi, j = rowtab[rl]
             g = e0 + e
             row = g // L
             assert (gi - plane0, j, z) == (row // n, row % n, g % L)

@@ -342,7 +342,3 @@ def finish_powerspectrum(power_sum: np.ndarray, keff_sum: np.ndarray, count: np.
     n = L.ksn_finish_powerspectrum(len(p), float(total_mass2), p.ctypes.data_as(capi.c_double_p),
                                    c.ctypes.data_as(capi.c_longlong_p), k.ctypes.data_as(capi.c_double_p))
     return n, p, c, k
-
-
-def default_transfer_file() -> str:
-    return os.path.join(os.path.dirname(capi.PKG_DIR), "tests", "golden", "ics_transfer_99.dat")

@@ -57,7 +57,7 @@ def main():
         nret, P, Cn, K = refs.total_powerspectrum(L, g0, nb, startslab=start, nslab=cnt, fn="total_powerspectrum_f64", pointer=grid.ptr)
         spectra.append((nret, P[:nret].copy(), K[:nret].copy(), Cn[:nret].astype(np.float64)))
         k1_names.append(L.ksn_last_k1_kernel().decode())
-    sim = host.KspaceNeutrinos(host.Cosmology(transfer_file=host.default_transfer_file(), mnu=masses, hybrid_neutrinos_on=hybrid), n, rank=rank)
+    sim = host.KspaceNeutrinos(host.Cosmology(transfer_file=refs.default_transfer_file(), mnu=masses, hybrid_neutrinos_on=hybrid), n, rank=rank)
     dnus = []
     for t in times:
         sim.add_nu_power_to_rhogrid(t, grid.ptr, slab)

@@ -71,6 +71,11 @@ def oracle_lib():
     return _cache["oracle"]
 
 
+def default_transfer_file():
+    """The CAMB transfer table of the reference's own tests (testdata/ics_transfer_99.dat, copied into tests/golden/)."""
+    return os.path.join(GOLDEN, "ics_transfer_99.dat")
+
+
 def dptr(a):
     return a.ctypes.data_as(capi.c_double_p)
 

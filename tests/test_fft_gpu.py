@@ -106,7 +106,7 @@ for n in (int(x) for x in os.environ["KSN_TEST_SIZES"].split(",")):
     # the device-resident PM step on this rank's y-slab: FFT -> neutrino correction (+ the bin sums over NVLink peer memory)
     fft.upload_real(rho[xs.start:xs.start + xs.count])
     fft.forward()
-    sim = host.KspaceNeutrinos(host.Cosmology(transfer_file=host.default_transfer_file(), mnu=(0.15, 0.15, 0.15)), n, rank=rank)
+    sim = host.KspaceNeutrinos(host.Cosmology(transfer_file=refs.default_transfer_file(), mnu=(0.15, 0.15, 0.15)), n, rank=rank)
     o = refs.orc()
     m = refs.orc_module(n, masses=(0.15, 0.15, 0.15))
     full = want.copy()

@@ -60,7 +60,7 @@ if backend == "p2p":
     assert nret2 == nret1 == nret and np.array_equal(P2, P1)
     np.testing.assert_allclose(P1[:nret], P[:nret], rtol=1e-12)
 # whole step, device-resident slab, several PM steps
-sim = host.KspaceNeutrinos(host.Cosmology(transfer_file=host.default_transfer_file(), mnu=(0.15, 0.15, 0.15), hybrid_neutrinos_on=1), n, rank=rank)
+sim = host.KspaceNeutrinos(host.Cosmology(transfer_file=refs.default_transfer_file(), mnu=(0.15, 0.15, 0.15), hybrid_neutrinos_on=1), n, rank=rank)
 dev = refs.DeviceBuffer(L, sub)
 m = refs.orc_module(n, masses=(0.15, 0.15, 0.15), hybrid=True)
 want = g.copy()

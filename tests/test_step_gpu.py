@@ -95,7 +95,7 @@ def test_full_size_properties_1024(gpu):
     slab = host.Slab(0, n)
     grid = host.DeviceGrid(n, slab)
     grid.fill_synthetic(seed=7, slope=-1.0)
-    sim = host.KspaceNeutrinos(host.Cosmology(transfer_file=host.default_transfer_file(), mnu=(0.1, 0.1, 0.1)), n)
+    sim = host.KspaceNeutrinos(host.Cosmology(transfer_file=refs.default_transfer_file(), mnu=(0.1, 0.1, 0.1)), n)
     L = n // 2 + 1
 
     def rows(i, js):      # a few rows of plane i, copied back

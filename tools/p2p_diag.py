@@ -11,7 +11,7 @@ torch.cuda.set_device(local)
 L = capi.lib(); capi.check(L.ksn_init(local)); L.ksn_set_quiet(1)
 dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
 slab = host.slab_partition(n, world)[rank]
-cosmo = host.Cosmology(transfer_file=host.default_transfer_file(), mnu=(0.1, 0.1, 0.1), hybrid_neutrinos_on=1)
+cosmo = host.Cosmology(transfer_file=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "ics_transfer_99.dat"), mnu=(0.1, 0.1, 0.1), hybrid_neutrinos_on=1)
 grid = host.DeviceGrid(n, slab); grid.fill_synthetic()
 tm = capi.Timing()
 for mode in ("p2p", "p2p-unfused", "nccl"):

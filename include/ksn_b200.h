@@ -181,6 +181,12 @@ const char *ksn_last_k3_kernel(void);
  * library, valid until the next pass.  For checkers: a pass can then be compared with the CPU restatement of
  * interface_gadget.c:163-188 on exactly the table it applied. */
 int ksn_last_k3_table(const double **logkk, const double **ratio, int *nbins, double *norm, double *boxsize);
+/* how the scaling passes would evaluate this table (host arithmetic only, no device needed): series = 5 or 9 terms of
+ * ln(1+u) in the double passes; f32_ok = 1 if a float grid's pass may evaluate the factor in float; k2_narrow = the k^2 from
+ * which on every table segment is narrow, i.e. rows with kx^2 + ky^2 >= k2_narrow take the branch-free path (0xffffffff:
+ * none); cells = lookup cells in log2(k^2); multi = 1 if some cell holds more than one knot.  Any output may be NULL. */
+int ksn_k3_table_plan(int dims, double boxsize, const double *logkk, const double *ratio, int nbins, double norm,
+                      int *series, int *f32_ok, unsigned *k2_narrow, int *cells, int *multi);
 /* integrand evaluations of the most recent ksn_delta_nu_integrate call (fslength table included) */
 unsigned long long ksn_last_k2_evals(void);
 /* largest number of 61-point rule applications any single k bin needed in that call (the kernel's critical path) */

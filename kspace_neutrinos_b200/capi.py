@@ -119,6 +119,8 @@ PROTOTYPES = {
     "ksn_k1_tile_plan_ex": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 5),
     "ksn_last_k1_kernel": (C.c_char_p, []),
     "ksn_last_k3_kernel": (C.c_char_p, []),
+    "ksn_k3_table_plan": (C.c_int, [C.c_int, C.c_double, c_double_p, c_double_p, C.c_int, C.c_double,
+                                    C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ksn_last_k3_table": (C.c_int, [C.POINTER(c_double_p), C.POINTER(c_double_p), C.POINTER(C.c_int), c_double_p, c_double_p]),
     "ksn_last_k2_evals": (C.c_ulonglong, []),
     "ksn_last_k2_max_passes": (C.c_uint, []),

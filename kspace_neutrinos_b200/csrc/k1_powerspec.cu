@@ -1150,6 +1150,9 @@ int k1_sums(const void *dgrid, const void *hgrid, int real_bytes, int dims, int 
             rc = k1_over_host_grid(hgrid, real_bytes, dims, nrbins, startslab, nslab, full, &ctas, &stride, &origin);
         }
         if (rc) return rc;
+        // K1 is in flight: now is the time for the side-stream work that wants to run beside it (K2's a-only tables)
+        rc = k2_prefetch_launch_pending();
+        if (rc) return rc;
     } else {
         // a rank that owns no planes still takes part in the collective with zeros
         rc = ensure_device_buffer((void **) &c.d_partial, &c.partial_cap, (size_t) 3 * nrbins * sizeof(double));

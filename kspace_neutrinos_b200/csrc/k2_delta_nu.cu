@@ -980,9 +980,10 @@ extern "C" int ksn_fslength_device(const double *logai, int n, double logaf, dou
 // ksn_delta_nu_integrate uses the prefetched tables if -- and only if -- every input they depend on is bit-for-bit what
 // it is called with (a, TimeTransfer, light, the Na knots, the background table); otherwise it computes them itself.
 struct K2Prefetch {
-    bool valid = false;
+    bool valid = false;          // tables for (a, a0, light, sf[0..Na)) are on the device (or on their way: `done`)
+    bool pending = false;        // a request has been recorded and not launched yet
     double a = 0, a0 = 0, light = 0;
-    int Na = 0;
+    int Na = 0, namax = 0;
     double *sf = nullptr; int sf_cap = 0;     // host copy of the knots the tables were built for
     const double *bg = nullptr; int bg_n = 0; double bg_lo = 0, bg_h = 0; int bg_npatch = 0;
     double *d_buf = nullptr; size_t cap = 0;  // device: knots | fsscales | fslengths | fs_c | sa | sg | fs_b | fs_d | dta | dtg | evals | status
@@ -1022,6 +1023,9 @@ void k2_prefetch_shutdown()
 }
 }  // namespace ksn
 
+// The request is only RECORDED here; the kernels are launched by k2_prefetch_launch_pending() -- which K1's launcher calls
+// right after the sweep is in flight (so the host time of these launches does not delay K1), and ksn_delta_nu_integrate
+// itself if nobody has by then.
 extern "C" int ksn_delta_nu_prefetch(double a, double TimeTransfer, double light, const double *scalefact, int Na, int namax)
 {
     int rc = ensure_init();
@@ -1029,10 +1033,33 @@ extern "C" int ksn_delta_nu_prefetch(double a, double TimeTransfer, double light
     Ctx &c = ctx();
     K2Prefetch &q = g_pre;
     q.valid = false;
+    q.pending = false;
     if (!scalefact || Na < 1 || namax < Na || !(a > 0) || !(TimeTransfer > 0)) return set_error(KSN_EINVAL, "ksn_delta_nu_prefetch: bad arguments");
     if (!c.d_bg) return set_error(KSN_EINVAL, "ksn_delta_nu_prefetch: call ksn_set_background first");
     const double loga0 = log(TimeTransfer), loga = log(a);
     if (loga0 < c.bg_lo + 2 * c.bg_h || loga > c.bg_hi - 2 * c.bg_h) return set_error(KSN_EINVAL, "ksn_delta_nu_prefetch: outside the background table");
+    if (q.sf_cap < namax) {
+        free(q.sf);
+        q.sf = (double *) malloc(sizeof(double) * namax);
+        q.sf_cap = q.sf ? namax : 0;
+        if (!q.sf) return set_error(KSN_ENOMEM, "ksn_delta_nu_prefetch: out of host memory");
+    }
+    memcpy(q.sf, scalefact, sizeof(double) * Na);
+    q.a = a; q.a0 = TimeTransfer; q.light = light; q.Na = Na; q.namax = namax;
+    q.pending = true;
+    return KSN_OK;
+}
+
+namespace ksn {
+int k2_prefetch_launch_pending()
+{
+    K2Prefetch &q = g_pre;
+    if (!q.pending) return KSN_OK;
+    q.pending = false;
+    Ctx &c = ctx();
+    if (!c.d_bg) return KSN_OK;
+    const int Na = q.Na, namax = q.namax;
+    const double loga0 = log(q.a0), loga = log(q.a);
     if (!q.stream) {
         KSN_CUDA(cudaStreamCreateWithFlags(&q.stream, cudaStreamNonBlocking));
         KSN_CUDA(cudaEventCreateWithFlags(&q.done, cudaEventDisableTiming));
@@ -1054,34 +1081,26 @@ extern "C" int ksn_delta_nu_prefetch(double a, double TimeTransfer, double light
         KSN_CUDA(cudaHostAlloc((void **) &q.h_sf, (size_t) namax * sizeof(double), cudaHostAllocDefault));
         q.h_cap = (size_t) namax * sizeof(double);
     }
-    if (q.sf_cap < namax) {
-        free(q.sf);
-        q.sf = (double *) malloc(sizeof(double) * namax);
-        q.sf_cap = q.sf ? namax : 0;
-        if (!q.sf) return set_error(KSN_ENOMEM, "ksn_delta_nu_prefetch: out of host memory");
-    }
-    // the previous tables may still be read by a K2 launch on the main stream: order this prefetch behind it
-    KSN_CUDA(cudaEventRecord(q.main_idle, c.stream));
-    KSN_CUDA(cudaStreamWaitEvent(q.stream, q.main_idle, 0));
-    KSN_CUDA(cudaStreamSynchronize(q.stream));          // the pinned knots of the previous prefetch have been consumed
-    memcpy(q.h_sf, scalefact, sizeof(double) * Na);
-    memcpy(q.sf, scalefact, sizeof(double) * Na);
+    // The previous tables may still be read by a K2 launch on the main stream: they were, at the latest, when that call
+    // returned (it synchronises), so only the prefetch stream's own previous work is waited for (it finished long ago).
+    KSN_CUDA(cudaStreamSynchronize(q.stream));
+    memcpy(q.h_sf, q.sf, sizeof(double) * Na);
     const K2PreLayout l = k2_pre_layout(q.d_buf, Na);
     const int Nfs = 16 * Na;
     KSN_CUDA(cudaMemcpyAsync(l.knots, q.h_sf, sizeof(double) * Na, cudaMemcpyHostToDevice, q.stream));
     KSN_CUDA(cudaMemsetAsync(l.evals, 0, sizeof(unsigned long long) + 8 + (size_t) Nfs * sizeof(int), q.stream));   // evals | status (adjacent)
     const BgTable bg = bg_table();
     fs_knots_kernel<<<(Nfs + 127) / 128, 128, 0, q.stream>>>(loga0, loga, Nfs, l.fsscales);
-    fslength_kernel<<<Nfs, K2_THREADS, 0, q.stream>>>(bg, l.fsscales, Nfs, loga, light, l.fslengths, l.status, l.evals);
+    fslength_kernel<<<Nfs, K2_THREADS, 0, q.stream>>>(bg, l.fsscales, Nfs, loga, q.light, l.fslengths, l.status, l.evals);
     k2_prep_splines_kernel<<<2, 256, 0, q.stream>>>(l.fsscales, l.fslengths, Nfs, l.fsc, l.fsb, l.fsd, l.sa, l.sg, l.knots, Na, l.dta, l.dtg);
     c.launches += 3;
     KSN_CUDA(cudaGetLastError());
     KSN_CUDA(cudaEventRecord(q.done, q.stream));
-    q.a = a; q.a0 = TimeTransfer; q.light = light; q.Na = Na;
     q.bg = c.d_bg; q.bg_n = c.bg_n; q.bg_lo = c.bg_lo; q.bg_h = c.bg_h; q.bg_npatch = g_bg_npatch;
     q.valid = true;
     return KSN_OK;
 }
+}  // namespace ksn
 
 extern "C" int ksn_delta_nu_integrate(const ksn_delta_nu_args *A, double *out, unsigned long long *n_evals)
 {
@@ -1101,6 +1120,7 @@ extern "C" int ksn_delta_nu_integrate(const ksn_delta_nu_args *A, double *out, u
 
     // Were the a-only tables prefetched for exactly these inputs (ksn_delta_nu_prefetch)?
     K2Prefetch &q = g_pre;
+    if (q.pending) { rc = k2_prefetch_launch_pending(); if (rc) return rc; }      // (nobody launched the request: do it now)
     const bool hit = q.valid && q.a == A->a && q.a0 == A->TimeTransfer && q.light == A->light && q.Na == Na &&
                      q.bg == c.d_bg && q.bg_n == c.bg_n && q.bg_lo == c.bg_lo && q.bg_h == c.bg_h && q.bg_npatch == g_bg_npatch &&
                      memcmp(q.sf, A->scalefact, sizeof(double) * Na) == 0;

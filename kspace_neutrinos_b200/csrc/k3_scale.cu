@@ -498,16 +498,12 @@ static int g_k3_fm_double = FM_D9;         // series length the double passes ma
 static bool g_k3_f32_ok = false;           // the current table qualifies for the all-float pass over float grids
 static bool g_k3_multi = false;            // some lookup cell holds more than one knot: the segment search loops
 
-int k3_upload_table(int dims, double boxsize, const double *logkk, const double *ratio, int nbins, double norm)
+// Build the device table for (logkk, ratio, norm) in the host buffer `hbuf` (k3_tab_doubles(nbins, K3_MAX_CELLS) doubles)
+// and decide how the passes may evaluate it; pure host arithmetic, no device involved (ksn_k3_table_plan exports the
+// decisions so that a CPU test can pin them).  Returns the doubles to upload.
+static size_t k3_build_table(void *hbuf, int dims, double boxsize, const double *logkk, const double *ratio, int nbins, double norm)
 {
-    Ctx &c = ctx();
-    const size_t nd_max = k3_tab_doubles(nbins, K3_MAX_CELLS);
-    int rc = ensure_device_buffer((void **) &c.d_k3tab, &c.k3tab_cap, nd_max * sizeof(double));
-    if (rc) return rc;
-    rc = ensure_pinned_buffer((void **) &c.h_k3tab, &c.h_k3tab_cap, nd_max * sizeof(double));
-    if (rc) return rc;
-    // the pinned table may still be in flight from the previous step
-    KSN_CUDA(cudaStreamSynchronize(c.stream));
+    struct { double *h_k3tab; } c = { (double *) hbuf };
     K3Seg *seg = (K3Seg *) c.h_k3tab;
     const double unit = boxsize / (2 * M_PI);
     double min_gap = 1e300;
@@ -594,7 +590,21 @@ int k3_upload_table(int dims, double boxsize, const double *logkk, const double 
             if (!(seg[i + 1].K2 * seg[i].inv - 1.0 < 0.03125)) j = i + 1;
         g_k3prm.k2_narrow = g_k3_multi || getenv("KSN_K3_NOFAST") ? 0xffffffffu : kthr[j];
     }
-    KSN_CUDA(cudaMemcpyAsync(c.d_k3tab, c.h_k3tab, k3_tab_doubles(nbins, cells) * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    return k3_tab_doubles(nbins, cells);
+}
+
+int k3_upload_table(int dims, double boxsize, const double *logkk, const double *ratio, int nbins, double norm)
+{
+    Ctx &c = ctx();
+    const size_t nd_max = k3_tab_doubles(nbins, K3_MAX_CELLS);
+    int rc = ensure_device_buffer((void **) &c.d_k3tab, &c.k3tab_cap, nd_max * sizeof(double));
+    if (rc) return rc;
+    rc = ensure_pinned_buffer((void **) &c.h_k3tab, &c.h_k3tab_cap, nd_max * sizeof(double));
+    if (rc) return rc;
+    // the pinned table may still be in flight from the previous step
+    KSN_CUDA(cudaStreamSynchronize(c.stream));
+    const size_t nd = k3_build_table(c.h_k3tab, dims, boxsize, logkk, ratio, nbins, norm);
+    KSN_CUDA(cudaMemcpyAsync(c.d_k3tab, c.h_k3tab, nd * sizeof(double), cudaMemcpyHostToDevice, c.stream));
     return KSN_OK;
 }
 
@@ -800,6 +810,27 @@ int k1_sums(const void *dgrid, const void *hgrid, int real_bytes, int dims, int 
 using namespace ksn;
 
 extern "C" const char *ksn_last_k3_kernel(void) { return g_k3_last; }
+
+// What k3_build_table decides for a table (host arithmetic only, no device needed): series = 5 or 9 (terms of ln(1+u) the
+// double passes use), f32_ok = 1 if float grids may evaluate the factor in float, k2_narrow = the k^2 from which on every
+// segment is narrow (rows at or above it take the branch-free path; 0xffffffff: none), cells = lookup cells in log2(k^2),
+// multi = 1 if some cell holds more than one knot (the segment search loops).
+extern "C" int ksn_k3_table_plan(int dims, double boxsize, const double *logkk, const double *ratio, int nbins, double norm,
+                                 int *series, int *f32_ok, unsigned *k2_narrow, int *cells, int *multi)
+{
+    if (!logkk || !ratio || nbins < 2 || nbins > 65535 || dims < 2 || !(boxsize > 0)) return KSN_EINVAL;
+    for (int i = 1; i < nbins; i++) if (!(logkk[i] > logkk[i - 1])) return KSN_EINVAL;
+    void *buf = malloc(k3_tab_doubles(nbins, K3_MAX_CELLS) * sizeof(double));
+    if (!buf) return KSN_ENOMEM;
+    k3_build_table(buf, dims, boxsize, logkk, ratio, nbins, norm);
+    free(buf);
+    if (series) *series = g_k3_fm_double == FM_D5 ? 5 : 9;
+    if (f32_ok) *f32_ok = g_k3_f32_ok ? 1 : 0;
+    if (k2_narrow) *k2_narrow = g_k3prm.k2_narrow;
+    if (cells) *cells = g_k3prm.cells;
+    if (multi) *multi = g_k3prm.multi;
+    return KSN_OK;
+}
 
 extern "C" int ksn_last_k3_table(const double **logkk, const double **ratio, int *nbins, double *norm, double *boxsize)
 {

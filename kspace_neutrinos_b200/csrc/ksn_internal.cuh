@@ -97,6 +97,7 @@ int k1_finish(int real_bytes, int dims, int nrbins, bool full, int ctas, int str
 void k1_tables_invalidate();   // somebody else wrote c.d_iw / c.d_thr, or the context is gone
 void fft_shutdown();           // plans, work area and peer mappings of ksn_fft_* (ksn_fft.cu)
 void k2_prefetch_shutdown();   // side stream and tables of ksn_delta_nu_prefetch (k2_delta_nu.cu)
+int k2_prefetch_launch_pending();   // launch a recorded prefetch request on its side stream (called once K1 is in flight)
 bool host_range_registered(const void *p, size_t bytes);   // page-locked through ksn_host_register?
 int func_attributes(const void *kern, size_t dyn_smem, int carveout);   // cudaFuncSetAttribute, once per value (carveout < 0: leave)
 int k3_launch(void *dgrid, int real_bytes, int dims, long long plane0_global, long long nplanes, int nknots);

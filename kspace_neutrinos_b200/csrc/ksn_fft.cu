@@ -246,7 +246,12 @@ extern "C" int ksn_fft_plan(int dims, int nranks, int rank)
         KSN_FFT(g_cufft.SetStream(f.p2d_f, c.stream));
         KSN_FFT(g_cufft.SetStream(f.p2d_i, c.stream));
     }
-    if (!f.xstream) KSN_CUDA(cudaStreamCreateWithFlags(&f.xstream, cudaStreamNonBlocking));
+    if (!f.xstream) {
+        // the exchange runs BEHIND cuFFT's batches, whose kernels fill the device: give its CTAs the first free slots
+        int lo_pri = 0, hi_pri = 0;
+        KSN_CUDA(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+        KSN_CUDA(cudaStreamCreateWithPriority(&f.xstream, cudaStreamNonBlocking, hi_pri));
+    }
     for (auto &st : f.s1d) if (!st) KSN_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     if (ny > 0) {
         int n1[1] = { N }, embed[1] = { N };

@@ -16,8 +16,12 @@
  *
  * usage: ref_bench N P R STEPS HYBRID TRANSFER_FILE [WARMUP [BUDGET_S [m0 m1 m2]]]
  *   WARMUP   untimed steps before the STEPS timed ones (default 1)
- *   BUDGET_S > 0: after the first warm-up step the planes per rank are cut so that WARMUP+STEPS steps fit this many
- *            seconds (never grown; the JSON says how many planes the timed steps used)
+ *   BUDGET_S > 0: wall-clock budget for the WARMUP + STEPS steps.  The initialising call at a = TimeTransfer (same grid
+ *            passes, a trivial integral) shows what a step costs: if WARMUP + STEPS of them would not fit, the planes per
+ *            rank are cut -- for EVERY step, warm-up included, and the module is initialised again on the shallower slabs:
+ *            the set of non-empty k bins depends on the slab depth, and the reference terminates when it changes between
+ *            steps (delta_tot_table.c:198, "Number of kbins ... != stored delta_tot").  The JSON says how many planes
+ *            the steps used.
  * prints one JSON line on rank 0.
  */
 #include "synthetic_grid.h"
@@ -61,7 +65,7 @@ int main(int argc, char **argv)
     const int L = N / 2 + 1;
     const int total = warmup + steps;
     double *times = ksn_minimpi_shared_alloc(sizeof(double) * 4 * (total + 1));
-    int *planes = ksn_minimpi_shared_alloc(sizeof(int) * (total + 1));
+    int *planes = ksn_minimpi_shared_alloc(sizeof(int) * (total + 2));
     const int rank = ksn_minimpi_fork(R);
     ThisTask = rank;
     ksn_ref_quiet = 2;                  /* record time stamps, print nothing */
@@ -86,8 +90,29 @@ int main(int argc, char **argv)
     orc_fill_synthetic_slab((double *) grid, N, startslab, P, SEED, SLOPE);
     const double t_gen = now() - tg0;
 
-    /* first call: delta_tot_init at a = TimeTransfer (untimed) */
-    add_nu_power_to_rhogrid(0.01, BOX, grid, N, (int) startslab, P, MPI_COMM_WORLD);
+    /* first call: delta_tot_init at a = TimeTransfer (untimed) -- and the yardstick for the budget */
+    {
+        MPI_Barrier(MPI_COMM_WORLD);
+        const double t0 = now();
+        add_nu_power_to_rhogrid(0.01, BOX, grid, N, (int) startslab, P, MPI_COMM_WORLD);
+        const double t_init = now() - t0;
+        if (rank == 0) {
+            planes[total] = P;
+            /* a full-history step adds the integral (~0.3 s on these cores at nk ~ 800) to the grid passes */
+            if (budget > 0 && (t_init + 0.4) * total > budget) {
+                int p2 = (int) (P * (budget / total - 0.4) / t_init);
+                if (p2 < 1) p2 = 1;
+                if (p2 < P) planes[total] = p2;
+            }
+        }
+        MPI_Barrier(MPI_COMM_WORLD);
+        if (planes[total] < P) {
+            P = planes[total];
+            delta_tot_table.delta_tot_init_done = 0;        /* initialise again on the slabs the steps will see */
+            delta_tot_table.ia = 0;
+            add_nu_power_to_rhogrid(0.01, BOX, grid, N, (int) startslab, P, MPI_COMM_WORLD);
+        }
+    }
     /* long stored history without stepping 100 times: rows at a = 0.01 ... 0.98, delta_tot ~ a */
     {
         const int nk = delta_tot_table.nk, ia = 98;
@@ -112,19 +137,8 @@ int main(int argc, char **argv)
             times[4 * s + 2] = ksn_ref_t_nupower - ksn_ref_t_mass;     /* integral */
             times[4 * s + 3] = t1 - ksn_ref_t_nupower;                 /* scaling loop + barrier */
             planes[s] = P;
-            /* after the first step: do the remaining ones fit the budget?  If not, fewer planes per rank from here on
-             * (decided by rank 0, read by all after the barrier below) */
-            planes[total] = P;
-            if (s == 0 && budget > 0 && (t1 - t0) * total > budget) {
-                const double grid_t = times[1] + times[3], fixed = times[2];
-                const double per_plane = grid_t / P, room = budget / total - fixed;
-                int p2 = room > 0 ? (int) (room / per_plane) : 1;
-                if (p2 < 1) p2 = 1;
-                if (p2 < P) planes[total] = p2;
-            }
         }
         MPI_Barrier(MPI_COMM_WORLD);
-        P = planes[total];
     }
     if (rank == 0) {
         printf("{\"N\": %d, \"P\": %d, \"P_full\": %d, \"R\": %d, \"nk\": %d, \"Na\": %d, \"warmup\": %d, \"gen_s\": %.3f, \"same_generator_as_gpu_arm\": true, \"steps\": [",

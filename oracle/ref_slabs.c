@@ -10,7 +10,8 @@
  *
  *   ref_slabs N hybrid m0 m1 m2 TRANSFER IN OUT  R start_0 n_0 ... start_{R-1} n_{R-1}  T a_0 ... a_{T-1}
  *
- * IN:  the slabs in rank order, raw fftw_complex (double), n_r * N * (N/2+1) elements each.
+ * IN:  the slabs in rank order, raw fftw_complex (double; float in the build without -DDOUBLEPRECISION_FFTW,
+ *      _ref/ref_slabs_single), n_r * N * (N/2+1) elements each.
  * OUT: (rank 0) int32 {N, nret, nk, ia, T}; double power[nret], keffs[nret], count[nret] of total_powerspectrum on the
  *      input (nrbins = N/2, as compute_neutrino_power_spectrum passes it); then per time step delta_nu_last[nk_t] preceded
  *      by a double nk_t; OUT.grid: the slabs after the T calls of add_nu_power_to_rhogrid, rank order.

@@ -29,6 +29,8 @@ def main():
     T = int(a[8 + 2 * R])
     times = [float(x) for x in a[9 + 2 * R:9 + 2 * R + T]]
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    rb = int(os.environ.get("KSN_TEST_REAL_BYTES", "8"))            # 4: float grids (the *_f32 entries)
+    sfx = "_f64" if rb == 8 else "_f32"
     assert world == R
     L = capi.lib()
     capi.check(L.ksn_init(0), "ksn_init")
@@ -38,14 +40,14 @@ def main():
     start, cnt = slabs[rank]
     slab = host.Slab(start, cnt)
     plane = n * (n // 2 + 1)
-    off = sum(c for _, c in slabs[:rank]) * plane * 16
-    grid = host.DeviceGrid(n, slab)
+    off = sum(c for _, c in slabs[:rank]) * plane * 2 * rb
+    grid = host.DeviceGrid(n, slab, rb)
     grid.fill_synthetic()
     g0 = grid.to_host()
     # the same bytes for the reference
     if rank == 0:
         with open(in_path, "wb") as f:
-            f.truncate(sum(c for _, c in slabs) * plane * 16)
+            f.truncate(sum(c for _, c in slabs) * plane * 2 * rb)
     dist.barrier()
     with open(in_path, "r+b") as f:
         f.seek(off)
@@ -54,13 +56,13 @@ def main():
     spectra = []
     k1_names = []
     for sweep in range(2):           # first sweep of a geometry: the three-sum kernel; second: the tile kernel + cached geometry
-        nret, P, Cn, K = refs.total_powerspectrum(L, g0, nb, startslab=start, nslab=cnt, fn="total_powerspectrum_f64", pointer=grid.ptr)
+        nret, P, Cn, K = refs.total_powerspectrum(L, g0, nb, startslab=start, nslab=cnt, fn="total_powerspectrum" + sfx, pointer=grid.ptr)
         spectra.append((nret, P[:nret].copy(), K[:nret].copy(), Cn[:nret].astype(np.float64)))
         k1_names.append(L.ksn_last_k1_kernel().decode())
     sim = host.KspaceNeutrinos(host.Cosmology(transfer_file=refs.default_transfer_file(), mnu=masses, hybrid_neutrinos_on=hybrid), n, rank=rank)
     dnus = []
     for t in times:
-        sim.add_nu_power_to_rhogrid(t, grid.ptr, slab)
+        sim.add_nu_power_to_rhogrid(t, grid.ptr, slab, rb)
         dnus.append(sim.delta_nu_last().copy())
     k3_name = L.ksn_last_k3_kernel().decode()
     k1_step = L.ksn_last_k1_kernel().decode()
@@ -73,7 +75,7 @@ def main():
                 for d in dnus:
                     f.write(np.array([float(len(d))]).tobytes()); f.write(d.tobytes())
         with open(out_path + ".grid", "wb") as f:
-            f.truncate(sum(c for _, c in slabs) * plane * 16)
+            f.truncate(sum(c for _, c in slabs) * plane * 2 * rb)
         with open(out_path + ".json", "w") as f:
             json.dump({"k1_first": k1_names[0], "k1_cached": k1_names[1], "k1_step": k1_step, "k3": k3_name}, f)
     dist.barrier()

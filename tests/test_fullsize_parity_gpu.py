@@ -19,6 +19,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_SLABS = os.path.join(ROOT, "oracle", "_ref", "ref_slabs")
+REF_SLABS_SINGLE = os.path.join(ROOT, "oracle", "_ref", "ref_slabs_single")
 TRANSFER = os.path.join(ROOT, "tests", "golden", "ics_transfer_99.dat")
 pytestmark = pytest.mark.gpu
 
@@ -55,19 +56,23 @@ def assert_delta_nu_close(got, ref, rtol, msg):
     np.testing.assert_allclose(got[full], ref[full], rtol=2 * rtol, atol=0, err_msg=msg)
 
 
-def run_case(tmp_path, n, slabs, masses, hybrid, times, world_port):
-    if not os.path.exists(REF_SLABS):
+def run_case(tmp_path, n, slabs, masses, hybrid, times, world_port, real_bytes=8):
+    """real_bytes = 4: float grids -- the product's *_f32 entries against the reference's float build (its default,
+    powerspectrum.h:6-14), tolerance 1e-5 (BASELINE.json north_star) instead of 1e-10."""
+    ref_slabs = REF_SLABS if real_bytes == 8 else REF_SLABS_SINGLE
+    tol = 1e-10 if real_bytes == 8 else 1e-5
+    if not os.path.exists(ref_slabs):
         pytest.skip("oracle/_ref/ref_slabs not built (needs /root/reference at build time)")
     inp, out_p, out_r = str(tmp_path / "in.bin"), str(tmp_path / "prod.bin"), str(tmp_path / "ref.bin")
     tail = [str(len(slabs))] + [str(x) for s in slabs for x in s] + [str(len(times))] + [repr(t) for t in times]
     head = [str(n), str(int(hybrid))] + [repr(m) for m in masses]
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", KSN_TEST_REAL_BYTES=str(real_bytes))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={len(slabs)}",
                         "--master-addr", "127.0.0.1", "--master-port", str(world_port),
                         os.path.join(ROOT, "tests", "fullsize_worker.py"), *head, inp, out_p, *tail],
                        capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and r.stdout.count(" ok") == len(slabs), r.stdout[-2000:] + r.stderr[-3000:]
-    r = subprocess.run([REF_SLABS, *head, TRANSFER, inp, out_r, *tail], capture_output=True, text=True, timeout=900)
+    r = subprocess.run([ref_slabs, *head, TRANSFER, inp, out_r, *tail], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-2000:]
     ref = read_out(out_r)
     names = json.load(open(out_p + ".json"))
@@ -75,17 +80,18 @@ def run_case(tmp_path, n, slabs, masses, hybrid, times, world_port):
         got = read_out(which)
         assert got["nret"] == ref["nret"], which
         assert np.array_equal(got["C"], ref["C"]), which                              # mode counts: bit-exact
-        np.testing.assert_allclose(got["P"], ref["P"], rtol=1e-10, atol=0, err_msg=which)
+        np.testing.assert_allclose(got["P"], ref["P"], rtol=tol, atol=0, err_msg=which)
         np.testing.assert_allclose(got["K"], ref["K"], rtol=1e-10, atol=0, err_msg=which)
     assert (got["nk"], got["ia"]) == (ref["nk"], ref["ia"])
     for t, (a, b) in enumerate(zip(got["dnu"], ref["dnu"])):
-        assert_delta_nu_close(a, b, 1e-10, f"delta_nu after step {t}")
-    g_ref = np.fromfile(out_r + ".grid")
-    g_got = np.fromfile(out_p + ".grid")
-    g_in = np.fromfile(inp)
+        assert_delta_nu_close(a, b, tol, f"delta_nu after step {t}")
+    dt = np.float64 if real_bytes == 8 else np.float32
+    g_ref = np.fromfile(out_r + ".grid", dtype=dt)
+    g_got = np.fromfile(out_p + ".grid", dtype=dt)
+    g_in = np.fromfile(inp, dtype=dt)
     assert g_ref.size == g_got.size == g_in.size
     assert not np.array_equal(g_ref, g_in)                                            # the steps did change the grid
-    np.testing.assert_allclose(g_got, g_ref, rtol=1e-10, atol=0)
+    np.testing.assert_allclose(g_got, g_ref, rtol=tol, atol=0)
     return names
 
 
@@ -110,3 +116,17 @@ def test_pmgrid_1024_rows_sharing_a_cta(tmp_path):
     names = run_case(tmp_path, 1024, [(0, 4), (509, 7), (1020, 4)], (0.1, 0.1, 0.1), False, (0.01, 0.02, 0.05, 0.0505), 29813)
     assert "k1_tile_kernel" in names["k1_cached"], names
     assert "k3_scale_flat_kernel<double> (2 rows" in names["k3"], names
+
+
+def test_pmgrid_2048_float_grid(tmp_path):
+    """Gadget-2's default build has float grids (powerspectrum.h:6-14): the float K1 tile kernel (a whole row per tile) and
+    the float flat-chunk K3 (factor in float where the step's table allows it) against the reference's float build."""
+    names = run_case(tmp_path, 2048, [(0, 3), (1022, 5)], (0.1, 0.1, 0.1), True, (0.01, 0.02, 0.34), 29814, real_bytes=4)
+    assert "k1_tile_kernel<float> (8 warps x 33 modes per lane, 2 stages, 1 tiles per row)" in names["k1_cached"], names
+    assert "k3_scale_flat_kernel<float>" in names["k3"], names
+
+
+def test_pmgrid_4096_float_grid(tmp_path):
+    names = run_case(tmp_path, 4096, [(0, 2), (2046, 3)], (0.2, 0.1, 0.3), False, (0.01, 0.02), 29815, real_bytes=4)
+    assert "k1_tile_kernel<float>" in names["k1_cached"], names
+    assert "k3_scale_flat_kernel<float>" in names["k3"], names

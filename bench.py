@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi during the timed region (diagnostics)")
     ap.add_argument("--no-check", action="store_true", help="skip the end-of-run parity check against the CPU oracle (outside the timed region)")
-    ap.add_argument("--ref-budget-s", type=float, default=float(os.environ.get("KSN_REF_BUDGET_S", "300")),
+    ap.add_argument("--ref-budget-s", type=float, default=float(os.environ.get("KSN_REF_BUDGET_S", "420")),
                     help="--impl reference: wall-clock budget for the warm-up + timed steps; the full slab is timed when it fits "
                          "host memory and this budget, else fewer planes per rank (reported)")
     ap.add_argument("--cpu-planes", type=int, default=0, help="planes per rank in the CPU sample (0 = auto)")

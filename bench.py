@@ -141,7 +141,7 @@ def cpu_throughput(n, steps, planes=0, warmup=1, budget_s=0.0, full_slab=False, 
     grid fits host memory (and stays below 2^31 elements per rank, the reference's `int` indices) -- nothing extrapolated;
     ref_bench itself cuts the planes per rank after the first warm-up step if warmup+steps would not fit budget_s.
     Otherwise a bounded sample (P planes per rank, ~6 s of CPU work per step), grid passes scaled to the full slab."""
-    ranks = os.cpu_count() or 1
+    ranks = min(os.cpu_count() or 1, 256)          # mini-MPI's limit (oracle/mini_mpi.c)
     while n % ranks:
         ranks -= 1
     whole = n // ranks

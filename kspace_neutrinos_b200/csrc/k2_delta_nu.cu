@@ -240,6 +240,39 @@ __device__ void spline_solve_seq(int n, const double *alpha, const double *gamma
     for (int i = N - 2; i >= 0; i--) z[i] = z[i] - gamma[i] * z[i + 1];
 }
 
+// The same solve by a whole CTA, for the per-bin delta_tot spline at the head of the K2 kernels (it sits on the critical path
+// of every bin): identical operations in identical order -- the two recurrences stay on one thread, but with the factors
+// staged in shared memory (`ga`, n doubles of scratch) so that no iteration waits for a global load, and the divisions in
+// between, which are independent, are dealt to all threads.  rhs in c[1..n-2] on entry; ends with a barrier.
+__device__ __forceinline__ void spline_solve_cta(int n, const double *__restrict__ alpha, const double *__restrict__ gamma,
+                                                 double *__restrict__ c, double *__restrict__ ga)
+{
+    const int N = n - 2, tid = threadIdx.x, T = blockDim.x;
+    if (N < 2) {
+        if (tid == 0) spline_solve_seq(n, alpha, gamma, c);
+        __syncthreads();
+        return;
+    }
+    double *z = c + 1;
+    for (int i = tid; i < N - 1; i += T) ga[i] = gamma[i];
+    if (tid == 0) { c[0] = 0.0; c[n - 1] = 0.0; }
+    __syncthreads();
+    if (tid == 0) {
+        double prev = z[0];
+#pragma unroll 8
+        for (int i = 1; i < N; i++) { prev = z[i] - ga[i - 1] * prev; z[i] = prev; }
+    }
+    __syncthreads();
+    for (int i = tid; i < N; i += T) z[i] = z[i] / alpha[i];
+    __syncthreads();
+    if (tid == 0) {
+        double next = z[N - 1];
+#pragma unroll 8
+        for (int i = N - 2; i >= 0; i--) { next = z[i] - ga[i] * next; z[i] = next; }
+    }
+    __syncthreads();
+}
+
 // ---------------------------------------------------------------- block-wide QK61 / QAG
 struct QkOut { double result, abserr, resabs, resasc; };
 
@@ -572,8 +605,7 @@ k2_delta_nu_kernel(const __grid_constant__ K2Dev p)
         if (p.Na > 2) {
             for (int i = threadIdx.x; i < p.Na - 2; i += blockDim.x) sc[i + 1] = spline_rhs(sx, sy, i);
             __syncthreads();
-            if (threadIdx.x == 0) spline_solve_seq(p.Na, p.dt_alpha, p.dt_gamma, sc);
-            __syncthreads();
+            spline_solve_cta(p.Na, p.dt_alpha, p.dt_gamma, sc, sb);          // (sb is free until the segments are formed)
             for (int i = threadIdx.x; i < p.Na - 1; i += blockDim.x) cspline_segment(sx, sy, sc, i, sb[i], sd[i]);
             __syncthreads();
         }
@@ -611,20 +643,22 @@ struct SpecShared {
     unsigned trips;            // passes through the integrand (the CTA's critical path)
 };
 
-// 2M groups of 64 threads: group g integrates half (g & 1) of slot sel[g >> 1]; `whole`: group 0 integrates slot 0 itself.
+// 2M groups of 64 threads: group g integrates half (g & 1) of slot sel[g >> 1]; `whole`: group 0 integrates slot 0 itself
+// and groups 1 and 2 its two halves (the whole interval is bisected in all but trivial cases: one trip saved per bin).
 // Same arithmetic, same reduction tree as qk61_pair.  Must be called by all 128 M threads; ends with a barrier.
 template <int M, class F>
 __device__ void qk61_groups(const F &f, SpecShared<M> &S, bool whole)
 {
     const int tid = threadIdx.x, g = tid >> 6, n = tid & 63, warp = tid >> 5;
-    const int which = g >> 1, child = g & 1;
-    const bool gactive = whole ? g == 0 : which < S.nsel;
+    const int which = whole ? 0 : g >> 1, child = whole ? g - 1 : g & 1;
+    const bool gactive = whole ? g <= 2 : which < S.nsel;
+    const bool parent = whole && g == 0;
     int slot = 0;
     double a = 0.0, b = 0.0;
     if (gactive) {
         slot = whole ? 0 : S.sel[which];
         const double a_i = S.L.a[slot], b_i = S.L.b[slot];
-        if (whole) {
+        if (parent) {
             a = a_i; b = b_i;
         } else {
             const double mid = 0.5 * (a_i + b_i);
@@ -659,7 +693,7 @@ __device__ void qk61_groups(const F &f, SpecShared<M> &S, bool whole)
         o.resabs = rabs * fabs(half_length);
         o.resasc = rasc * fabs(half_length);
         o.abserr = rescale_error_d((kron - gaus) * half_length, o.resabs, o.resasc);
-        if (whole) {
+        if (parent) {
             S.q0[0] = o.result; S.q0[1] = o.abserr; S.q0[2] = o.resabs; S.q0[3] = o.resasc;
         } else {
             S.L.cr[2 * slot + child] = o.result;
@@ -681,16 +715,29 @@ __device__ __forceinline__ int warp_argmax_err(const double *e, const unsigned c
         const double v = e[k];
         if (best < 0 || v > bv) { bv = v; best = k; }
     }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, bv, d);
-        const int oi = __shfl_xor_sync(0xffffffffu, best, d);
-        if (oi >= 0 && (best < 0 || ov > bv || (ov == bv && oi < best))) { bv = ov; best = oi; }
-    }
-    return best;
+    // Error estimates are non-negative, so they order like their bit patterns: the warp's maximum in two 32-bit redux steps
+    // (high word, then the low word among the lanes that hold it), the lowest index among its holders in a third -- three
+    // instructions instead of five rounds of two 64-bit shuffles each, on the serial path of every trip.
+    const unsigned long long key = best >= 0 ? (unsigned long long) __double_as_longlong(bv) + 1ull : 0ull;   // 0: no candidate
+    const unsigned hi = (unsigned) (key >> 32), lo = (unsigned) key;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    const unsigned cand = (best >= 0 && hi == mh && lo == ml) ? (unsigned) best : 0xffffffffu;
+    const unsigned win = __reduce_min_sync(0xffffffffu, cand);
+    return win == 0xffffffffu ? -1 : (int) win;
 }
 
 // gsl_integration_qag (key 6) by a CTA of 128 M threads; all threads return the same values.
+#ifdef KSN_K2_TRACE
+// Developer build (make EXTRA_NVFLAGS=-DKSN_K2_TRACE; tools/k2_trace.py): where the CTA of the deepest bin -- the kernel's
+// critical path -- spends its cycles.  [0] integrand passes, [1] replay of QAG's loop, [2] passes, [3] set-up before the
+// quadrature, [4] whole CTA, [5..6] its start/end (globaltimer ns), [7] end of the last CTA, [8] start of the first.
+__device__ unsigned long long g_k2_trace[16];
+#define K2_TRACE(...) __VA_ARGS__
+#else
+#define K2_TRACE(...)
+#endif
+
 template <int M, class F>
 __device__ int qag61_spec(const F &f, double a, double b, double epsabs, double epsrel, int limit,
                           SpecShared<M> &S, double *result, double *abserr, unsigned *passes, unsigned *rules, unsigned *trips)
@@ -698,27 +745,33 @@ __device__ int qag61_spec(const F &f, double a, double b, double epsabs, double 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) { S.L.a[0] = a; S.L.b[0] = b; S.nsel = 0; S.done = 0; }
     __syncthreads();
-    qk61_groups<M>(f, S, true);
+    qk61_groups<M>(f, S, true);           // the whole interval and, ahead of time, its two halves
     QagSpecState s;                       // lives in lane 0 of warp 0
-    unsigned nrules = 1, ntrips = 1;
+    unsigned nrules = 3, ntrips = 1;
     int size = 1;                         // uniform in warp 0
     if (warp == 0) {
         if (lane == 0) {
             int st = QAGS_OK;
             if (qags_begin(s, S.L, a, b, epsabs, epsrel, limit, S.q0[0], S.q0[1], S.q0[2], S.q0[3], &st)) {
-                S.result = S.q0[0]; S.abserr = S.q0[1]; S.status = st; S.passes = 1; S.rules = 1; S.trips = 1; S.done = 1;
+                S.result = S.q0[0]; S.abserr = S.q0[1]; S.status = st; S.passes = 1; S.rules = 3; S.trips = 1; S.done = 1;
             } else {
-                S.L.cached[0] = 1; S.sel[0] = 0; S.nsel = 1;
+                S.L.cached[0] = 1; S.sel[0] = 0; S.nsel = 0;
             }
         }
     }
+    bool have_children = true;            // uniform in the CTA: the halves the replay starts with are in the cache already
+    K2_TRACE(const bool tr = blockIdx.x == 0 && blockIdx.y == 0 && tid == 0; long long t0 = clock64(), t_eval = 0, t_replay = 0, n_eval = 0;)
     for (;;) {
         __syncthreads();                  // selection (or the verdict) of warp 0 is visible
+        K2_TRACE(if (tr) { const long long t = clock64(); t_replay += t - t0; t0 = t; })
         if (S.done) break;
-        qk61_groups<M>(f, S, false);
-        if (warp != 0) continue;
-        nrules += 2 * S.nsel;
-        ntrips++;
+        if (!have_children) {
+            qk61_groups<M>(f, S, false);
+            K2_TRACE(if (tr) { const long long t = clock64(); t_eval += t - t0; t0 = t; n_eval++; })
+        }
+        if (warp != 0) { have_children = false; continue; }
+        if (!have_children) { nrules += 2 * S.nsel; ntrips++; }
+        have_children = false;
         // replay QAG's loop over the cached halves
         for (;;) {
             const int i = warp_argmax_err(S.L.e, nullptr, 0.0, size, lane);
@@ -754,6 +807,7 @@ __device__ int qag61_spec(const F &f, double a, double b, double epsabs, double 
             break;
         }
     }
+    K2_TRACE(if (tr) { g_k2_trace[0] = t_eval; g_k2_trace[1] = t_replay; g_k2_trace[2] = n_eval; })
     *result = S.result;
     *abserr = S.abserr;
     if (passes) *passes = S.passes;
@@ -774,6 +828,7 @@ k2_delta_nu_spec_kernel(const __grid_constant__ K2Dev p)
     __shared__ double jt_s[JT_DOUBLES];
     const int ik = p.k_first + (int) (gridDim.x - 1 - blockIdx.x);      // deepest (highest-k) bins are scheduled first
     const int sp = blockIdx.y;
+    K2_TRACE(const long long tk0 = clock64(); unsigned long long gt0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0));)
     jfrac_table_init(jt_s, p.qc[sp], p.nufrac_low0);
     for (int i = threadIdx.x; i < p.Na; i += blockDim.x) {
         sx[i] = p.scalefact[i];
@@ -790,8 +845,7 @@ k2_delta_nu_spec_kernel(const __grid_constant__ K2Dev p)
         if (p.Na > 2) {
             for (int i = threadIdx.x; i < p.Na - 2; i += blockDim.x) sc[i + 1] = spline_rhs(sx, sy, i);
             __syncthreads();
-            if (threadIdx.x == 0) spline_solve_seq(p.Na, p.dt_alpha, p.dt_gamma, sc);
-            __syncthreads();
+            spline_solve_cta(p.Na, p.dt_alpha, p.dt_gamma, sc, sb);          // (sb is free until the segments are formed)
             for (int i = threadIdx.x; i < p.Na - 1; i += blockDim.x) cspline_segment(sx, sy, sc, i, sb[i], sd[i]);
             __syncthreads();
         }
@@ -801,10 +855,18 @@ k2_delta_nu_spec_kernel(const __grid_constant__ K2Dev p)
         f.fs_x0 = p.loga0;
         f.fs_inv_dx = (p.Nfs - 1.) / (p.loga - p.loga0);
         double res, err;
+        K2_TRACE(if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_k2_trace[3] = clock64() - tk0;)
         st = qag61_spec<M>(f, p.loga0, p.loga, 0.0, p.relerr[sp], QAG_LIMIT, S, &res, &err, &passes, &rules, &trips);
         dnu += p.delta_nu_prefac * res;
     }
     if (threadIdx.x == 0) {
+#ifdef KSN_K2_TRACE
+        unsigned long long gt1;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt1));
+        if (blockIdx.x == 0 && blockIdx.y == 0) { g_k2_trace[4] = clock64() - tk0; g_k2_trace[5] = gt0; g_k2_trace[6] = gt1; }
+        atomicMax(&g_k2_trace[7], gt1);
+        atomicMin(&g_k2_trace[8], gt0);
+#endif
         p.out[(size_t) sp * p.nk + ik] = dnu;
         // bits 8-19: the SEQUENTIAL algorithm's rule count, as k2_delta_nu_kernel reports it; bits 20+: passes through the integrand
         p.status[(size_t) sp * p.nk + ik] = st | ((int) passes << 8) | ((int) trips << 20);
@@ -845,6 +907,14 @@ static int k2_spec_width(void)
     return m >= 0 && m <= 4 ? m : 1;
 }
 extern "C" int ksn_k2_spec_width(void) { return k2_spec_width(); }
+#ifdef KSN_K2_TRACE
+extern "C" int ksn_k2_trace(unsigned long long *out16, int reset)
+{
+    if (out16) cudaMemcpyFromSymbol(out16, ksn::g_k2_trace, 16 * sizeof(unsigned long long));
+    if (reset) { unsigned long long z[16] = {}; z[8] = ~0ull; cudaMemcpyToSymbol(ksn::g_k2_trace, z, sizeof z); }
+    return 0;
+}
+#endif
 
 // Measured (profiles/r1_k2_widths.txt, nk = 788, Na = 99): integrating ahead pays where the kernel's time is the critical
 // path of a few deep bins -- hybrid neutrinos, one species: 57 sequential bisections on the highest-k bins -- and costs

@@ -775,6 +775,7 @@ __device__ int qag61_spec(const F &f, double a, double b, double epsabs, double 
         // replay QAG's loop over the cached halves
         for (;;) {
             const int i = warp_argmax_err(S.L.e, nullptr, 0.0, size, lane);
+            __syncwarp();                 // every lane has read the list before lane 0 changes it
             int act = 1;                  // 0: one trip made, go on; 1: slot i must be integrated first; 2: finished
             double floor_ = 0.0;
             if (lane == 0) {
@@ -800,6 +801,7 @@ __device__ int qag61_spec(const F &f, double a, double b, double epsabs, double 
             for (; ns < M; ns++) {
                 __syncwarp();
                 const int jn = warp_argmax_err(S.L.e, S.L.cached, floor_, size, lane);
+                __syncwarp();
                 if (jn < 0) break;
                 if (lane == 0) { S.L.cached[jn] = 1; S.sel[ns] = jn; }
             }

@@ -727,7 +727,6 @@ __device__ __forceinline__ int warp_argmax_err(const double *e, const unsigned c
     return win == 0xffffffffu ? -1 : (int) win;
 }
 
-// gsl_integration_qag (key 6) by a CTA of 128 M threads; all threads return the same values.
 #ifdef KSN_K2_TRACE
 // Developer build (make EXTRA_NVFLAGS=-DKSN_K2_TRACE; tools/k2_trace.py): where the CTA of the deepest bin -- the kernel's
 // critical path -- spends its cycles.  [0] integrand passes, [1] replay of QAG's loop, [2] passes, [3] set-up before the
@@ -738,6 +737,7 @@ __device__ unsigned long long g_k2_trace[16];
 #define K2_TRACE(...)
 #endif
 
+// gsl_integration_qag (key 6) by a CTA of 128 M threads; all threads return the same values.
 template <int M, class F>
 __device__ int qag61_spec(const F &f, double a, double b, double epsabs, double epsrel, int limit,
                           SpecShared<M> &S, double *result, double *abserr, unsigned *passes, unsigned *rules, unsigned *trips)

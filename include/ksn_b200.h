@@ -187,6 +187,11 @@ int ksn_last_k3_table(const double **logkk, const double **ratio, int *nbins, do
  * none); cells = lookup cells in log2(k^2); multi = 1 if some cell holds more than one knot.  Any output may be NULL. */
 int ksn_k3_table_plan(int dims, double boxsize, const double *logkk, const double *ratio, int nbins, double norm,
                       int *series, int *f32_ok, unsigned *k2_narrow, int *cells, int *multi);
+/* FNV-1a hash of everything the host builds for this table -- the words uploaded to the device, the kernels' parameters,
+ * the decisions above.  The part that depends on the knots alone is kept from one build to the next (the knots are
+ * log(keff): the same every step); fresh != 0 forgets it first, so a test can pin cached == fresh, bit for bit. */
+int ksn_k3_table_hash(int dims, double boxsize, const double *logkk, const double *ratio, int nbins, double norm,
+                      int fresh, unsigned long long *hash);
 /* integrand evaluations of the most recent ksn_delta_nu_integrate call (fslength table included) */
 unsigned long long ksn_last_k2_evals(void);
 /* largest number of 61-point rule applications any single k bin needed in that call (the kernel's critical path) */

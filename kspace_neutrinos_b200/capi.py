@@ -121,6 +121,7 @@ PROTOTYPES = {
     "ksn_last_k3_kernel": (C.c_char_p, []),
     "ksn_k3_table_plan": (C.c_int, [C.c_int, C.c_double, c_double_p, c_double_p, C.c_int, C.c_double,
                                     C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "ksn_k3_table_hash": (C.c_int, [C.c_int, C.c_double, c_double_p, c_double_p, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_ulonglong)]),
     "ksn_last_k3_table": (C.c_int, [C.POINTER(c_double_p), C.POINTER(c_double_p), C.POINTER(C.c_int), c_double_p, c_double_p]),
     "ksn_last_k2_evals": (C.c_ulonglong, []),
     "ksn_last_k2_max_passes": (C.c_uint, []),

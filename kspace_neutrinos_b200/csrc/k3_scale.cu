@@ -18,6 +18,7 @@
 // sized by the host so that no cell holds two knots) plus one compare, all in shared memory.
 // Sweep: one warp per row, 32 consecutive z per step, rows dealt round-robin to a persistent grid.
 #include "ksn_internal.cuh"
+#include <vector>
 
 #include <math.h>
 #include <stdio.h>
@@ -501,21 +502,39 @@ static bool g_k3_multi = false;            // some lookup cell holds more than o
 // Build the device table for (logkk, ratio, norm) in the host buffer `hbuf` (k3_tab_doubles(nbins, K3_MAX_CELLS) doubles)
 // and decide how the passes may evaluate it; pure host arithmetic, no device involved (ksn_k3_table_plan exports the
 // decisions so that a CPU test can pin them).  Returns the doubles to upload.
-static size_t k3_build_table(void *hbuf, int dims, double boxsize, const double *logkk, const double *ratio, int nbins, double norm)
+// Everything in the table that depends on the knots alone.  The knots are log(keff) of the non-empty bins: the same numbers
+// step after step for as long as the slab geometry stands, while the ratios change every step -- and this half is the one
+// with a libm call and a division per knot (35 of the 50 us the whole build took on the host, between K2 and K3 of every
+// step).  Kept from one build to the next, compared by content.
+struct K3Knots {
+    bool valid = false;
+    int dims = 0, nbins = 0, cells = 0;
+    double boxsize = 0, lo = 0, scale = 0;
+    bool multi = false;
+    unsigned k2_narrow = 0xffffffffu;      // (without the KSN_K3_NOFAST / multi override)
+    std::vector<double> logkk, K2, inv, den, umax;
+    std::vector<unsigned> kthr;            // nbins + 2
+    std::vector<unsigned short> cell;
+};
+static K3Knots g_k3_knots;
+static void k3_forget_knots() { g_k3_knots.valid = false; }
+
+static void k3_build_knots(K3Knots &kn, int dims, double boxsize, const double *logkk, int nbins)
 {
-    struct { double *h_k3tab; } c = { (double *) hbuf };
-    K3Seg *seg = (K3Seg *) c.h_k3tab;
+    kn.valid = false;
+    kn.dims = dims; kn.nbins = nbins; kn.boxsize = boxsize;
+    kn.logkk.assign(logkk, logkk + nbins);
+    kn.K2.resize(nbins); kn.inv.resize(nbins); kn.den.resize(nbins); kn.umax.resize(nbins); kn.kthr.resize(nbins + 2);
     const double unit = boxsize / (2 * M_PI);
     double min_gap = 1e300;
     for (int i = 0; i < nbins; i++) {
         const double kg = exp(logkk[i]) * unit;     // knot in integer-wave-number units
-        seg[i].K2 = kg * kg;
-        seg[i].inv = 1.0 / seg[i].K2;
-        seg[i].A = 1.0 + norm * ratio[i];
-        seg[i].B = (i + 1 < nbins) ? norm * (ratio[i + 1] - ratio[i]) / (2.0 * (logkk[i + 1] - logkk[i])) : 0.0;
+        kn.K2[i] = kg * kg;
+        kn.inv[i] = 1.0 / kn.K2[i];
+        kn.den[i] = (i + 1 < nbins) ? 2.0 * (logkk[i + 1] - logkk[i]) : 0.0;
         if (i > 0) min_gap = fmin(min_gap, 2.0 * (logkk[i] - logkk[i - 1]) / M_LN2);   // gap in log2(k2)
     }
-    seg[nbins].K2 = INFINITY; seg[nbins].inv = 0; seg[nbins].A = seg[nbins - 1].A; seg[nbins].B = 0;
+    for (int i = 0; i < nbins; i++) kn.umax[i] = i + 1 < nbins ? kn.K2[i + 1] * kn.inv[i] - 1.0 : 0.0;
     // the cells run from the first knot to the largest k^2 of the grid (or the last knot, whichever is larger), so that a
     // mode at or above the first knot needs no bound on its cell index
     const double k2max = 3.0 * (double) (dims / 2) * (double) (dims / 2);
@@ -527,9 +546,10 @@ static size_t k3_build_table(void *hbuf, int dims, double boxsize, const double 
     // segment search steps over the extra knots in a loop instead
     int cells = 1024;
     while (cells < K3_MAX_CELLS && (hi - lo) / cells * 1.05 >= min_gap) cells *= 2;
-    g_k3_multi = (hi - lo) / cells * 1.05 >= min_gap;
+    kn.multi = (hi - lo) / cells * 1.05 >= min_gap;
     const double scale = cells / (hi - lo);
-    unsigned short *cell = (unsigned short *) (seg + nbins + 1);
+    kn.cells = cells; kn.lo = lo; kn.scale = scale;
+    kn.cell.resize(cells);
     // cell[k] = last knot at or below the lower edge of cell k, minus a guard (0.02 cell) for the float log2 on the
     // device.  One log2 per knot: knot i starts to count from cell ceil((log2 K2_i - lo) * scale + 0.02).
     {
@@ -537,10 +557,60 @@ static size_t k3_build_table(void *hbuf, int dims, double boxsize, const double 
         for (int i = 1; i < nbins; i++) {
             int first = (int) ceil((lg2K2(i) - lo) * scale + 0.02);
             if (first > cells) first = cells;
-            for (; k < first; k++) cell[k] = (unsigned short) (i - 1);
+            for (; k < first; k++) kn.cell[k] = (unsigned short) (i - 1);
         }
-        for (; k < cells; k++) cell[k] = (unsigned short) (nbins - 1);
+        for (; k < cells; k++) kn.cell[k] = (unsigned short) (nbins - 1);
     }
+    // integer knot thresholds: for integer k2,  k2 >= K2_i  <=>  k2 >= ceil(K2_i)
+    for (int i = 0; i < nbins; i++) kn.kthr[i] = kn.K2[i] >= 4294967295.0 ? 0xffffffffu : (unsigned) ceil(kn.K2[i]);
+    kn.kthr[nbins] = kn.kthr[nbins + 1] = 0xffffffffu;
+    {
+        // first knot from which on all segments are narrow (the last one, clamped above, has B = 0: any u will do)
+        int j = 0;
+        for (int i = 0; i + 1 < nbins; i++)
+            if (!(kn.umax[i] < 0.03125)) j = i + 1;
+        kn.k2_narrow = kn.kthr[j];
+    }
+    kn.valid = true;
+}
+
+// Build the device table for (logkk, ratio, norm) in the host buffer `hbuf` (k3_tab_doubles(nbins, K3_MAX_CELLS) doubles)
+// and decide how the passes may evaluate it; pure host arithmetic, no device involved (ksn_k3_table_plan exports the
+// decisions so that a CPU test can pin them, ksn_k3_table_hash the bytes).  Returns the doubles to upload.
+static size_t k3_build_table(void *hbuf, int dims, double boxsize, const double *logkk, const double *ratio, int nbins, double norm)
+{
+    K3Knots &kn = g_k3_knots;
+    if (!(kn.valid && kn.dims == dims && kn.nbins == nbins && kn.boxsize == boxsize &&
+          memcmp(kn.logkk.data(), logkk, sizeof(double) * nbins) == 0))
+        k3_build_knots(kn, dims, boxsize, logkk, nbins);
+    K3Seg *seg = (K3Seg *) hbuf;
+    const int cells = kn.cells;
+    int off_kthr, off_segf;
+    k3_tab_words(nbins, cells, &off_kthr, &off_segf);
+    K3SegF *segf = (K3SegF *) ((unsigned *) hbuf + off_segf);
+    // how much arithmetic the table needs.  Narrow segments (u = k2/K2_i - 1 < 2^-5 over the whole segment) use a series
+    // for ln(1+u): to u^5 where |B| u_max^6 / 6 <= 1e-14 on every one of them (four orders below the 1e-10 bar), else to u^9.  The all-float pass over a
+    // float grid: error of delta = factor - 1 about 2^-23 (|B| (1 + 3 u) + |delta|), wanted below 2^-26 (a quarter of a float ulp of the product).
+    double worst_d5 = 0, worst_f32 = 0;
+    for (int i = 0; i < nbins; i++) {
+        seg[i].K2 = kn.K2[i];
+        seg[i].inv = kn.inv[i];
+        seg[i].A = 1.0 + norm * ratio[i];
+        seg[i].B = (i + 1 < nbins) ? norm * (ratio[i + 1] - ratio[i]) / kn.den[i] : 0.0;
+        const double umax = kn.umax[i];
+        const double ab = fabs(seg[i].B);
+        const double uc = umax < 0.03125 ? umax : 0.03125, uc2 = uc * uc;   // (of a wide segment: the part below the log1p switch)
+        // (plain comparisons where fmax / fmin would be calls into libm on this path; same values, NaNs included)
+        const double d5 = ab * (uc2 * uc2 * uc2) * (1.0 / 6.0);
+        const double f32 = ab * (1.0 + 3.0 * (umax < 1.0 ? umax : 1.0)) + fabs(seg[i].A - 1.0) + ab * (umax < 1e30 ? umax : 1e30);   // (ln(1+u) <= u)
+        worst_d5 = d5 > worst_d5 ? d5 : worst_d5;
+        worst_f32 = f32 > worst_f32 ? f32 : worst_f32;
+        segf[i].inv = (float) seg[i].inv; segf[i].A1 = (float) (norm * ratio[i]); segf[i].B = (float) seg[i].B; segf[i].pad = 0;
+    }
+    seg[nbins].K2 = INFINITY; seg[nbins].inv = 0; seg[nbins].A = seg[nbins - 1].A; seg[nbins].B = 0;
+    segf[nbins] = segf[nbins - 1]; segf[nbins].B = 0; segf[nbins].inv = 0;
+    memcpy(seg + nbins + 1, kn.cell.data(), sizeof(unsigned short) * cells);
+    memcpy((unsigned *) hbuf + off_kthr, kn.kthr.data(), sizeof(unsigned) * (nbins + 2));
     if (g_k3_tab_copy.cap < nbins) {
         free(g_k3_tab_copy.logkk); free(g_k3_tab_copy.ratio);
         g_k3_tab_copy.logkk = (double *) malloc(sizeof(double) * nbins);
@@ -553,43 +623,18 @@ static size_t k3_build_table(void *hbuf, int dims, double boxsize, const double 
         memcpy(g_k3_tab_copy.ratio, ratio, sizeof(double) * nbins);
         g_k3_tab_copy.nbins = nbins; g_k3_tab_copy.norm = norm; g_k3_tab_copy.boxsize = boxsize;
     }
-    int off_kthr, off_segf;
-    k3_tab_words(nbins, cells, &off_kthr, &off_segf);
-    unsigned *kthr = (unsigned *) c.h_k3tab + off_kthr;
-    K3SegF *segf = (K3SegF *) ((unsigned *) c.h_k3tab + off_segf);
-    // integer knot thresholds: for integer k2,  k2 >= K2_i  <=>  k2 >= ceil(K2_i)
-    for (int i = 0; i < nbins; i++) kthr[i] = seg[i].K2 >= 4294967295.0 ? 0xffffffffu : (unsigned) ceil(seg[i].K2);
-    kthr[nbins] = kthr[nbins + 1] = 0xffffffffu;
-    // how much arithmetic the table needs.  Narrow segments (u = k2/K2_i - 1 < 2^-5 over the whole segment) use a series
-    // for ln(1+u): to u^5 where |B| u_max^6 / 6 <= 1e-14 on every one of them (four orders below the 1e-10 bar), else to u^9.  The all-float pass over a
-    // float grid: error of delta = factor - 1 about 2^-23 (|B| (1 + 3 u) + |delta|), wanted below 2^-26 (a quarter of a float ulp of the product).
-    double worst_d5 = 0, worst_f32 = 0;
-    for (int i = 0; i < nbins; i++) {
-        const double umax = i + 1 < nbins ? seg[i + 1].K2 * seg[i].inv - 1.0 : 0.0;
-        const double ab = fabs(seg[i].B);
-        const double uc = umax < 0.03125 ? umax : 0.03125, uc2 = uc * uc;   // (of a wide segment: the part below the log1p switch)
-        worst_d5 = fmax(worst_d5, ab * (uc2 * uc2 * uc2) * (1.0 / 6.0));
-        worst_f32 = fmax(worst_f32, ab * (1.0 + 3.0 * fmin(umax, 1.0)) + fabs(seg[i].A - 1.0) + ab * fmin(umax, 1e30));   // (ln(1+u) <= u)
-        segf[i].inv = (float) seg[i].inv; segf[i].A1 = (float) (norm * ratio[i]); segf[i].B = (float) seg[i].B; segf[i].pad = 0;
-    }
-    segf[nbins] = segf[nbins - 1]; segf[nbins].B = 0; segf[nbins].inv = 0;
+    g_k3_multi = kn.multi;
     g_k3_fm_double = worst_d5 <= 1e-14 ? FM_D5 : FM_D9;
     g_k3_f32_ok = worst_f32 <= 1.0 / 8 && 3.0 * (double) dims * dims / 4 < 16777216.0 && seg[0].K2 > 1e-30;
     g_k3prm.n = nbins;
     g_k3prm.cells = cells;
-    g_k3prm.cell_lo = (float) lo;
-    g_k3prm.cell_scale = (float) scale;
+    g_k3prm.cell_lo = (float) kn.lo;
+    g_k3prm.cell_scale = (float) kn.scale;
     g_k3prm.off_kthr = off_kthr;
     g_k3prm.off_segf = off_segf;
     g_k3prm.multi = g_k3_multi ? 1 : 0;
-    g_k3prm.cell_off = (float) (-lo * scale);
-    {
-        // first knot from which on all segments are narrow (the last one, clamped above, has B = 0: any u will do)
-        int j = 0;
-        for (int i = 0; i + 1 < nbins; i++)
-            if (!(seg[i + 1].K2 * seg[i].inv - 1.0 < 0.03125)) j = i + 1;
-        g_k3prm.k2_narrow = g_k3_multi || getenv("KSN_K3_NOFAST") ? 0xffffffffu : kthr[j];
-    }
+    g_k3prm.cell_off = (float) (-kn.lo * kn.scale);
+    g_k3prm.k2_narrow = g_k3_multi || getenv("KSN_K3_NOFAST") ? 0xffffffffu : kn.k2_narrow;
     return k3_tab_doubles(nbins, cells);
 }
 
@@ -829,6 +874,33 @@ extern "C" int ksn_k3_table_plan(int dims, double boxsize, const double *logkk, 
     if (k2_narrow) *k2_narrow = g_k3prm.k2_narrow;
     if (cells) *cells = g_k3prm.cells;
     if (multi) *multi = g_k3prm.multi;
+    return KSN_OK;
+}
+
+// FNV-1a hash of everything k3_build_table produces for a table -- the words that go to the device, the kernel parameters,
+// the decisions -- so that a CPU test can pin that a build from the cached knot geometry equals a fresh one bit for bit.
+// fresh != 0: forget the cached knot geometry first.
+extern "C" int ksn_k3_table_hash(int dims, double boxsize, const double *logkk, const double *ratio, int nbins, double norm,
+                                 int fresh, unsigned long long *hash)
+{
+    if (!hash || !logkk || !ratio || nbins < 2 || nbins > 65535 || dims < 2 || !(boxsize > 0)) return KSN_EINVAL;
+    for (int i = 1; i < nbins; i++) if (!(logkk[i] > logkk[i - 1])) return KSN_EINVAL;
+    const size_t cap = k3_tab_doubles(nbins, K3_MAX_CELLS) * sizeof(double);
+    unsigned char *buf = (unsigned char *) calloc(cap, 1);
+    if (!buf) return KSN_ENOMEM;
+    if (fresh) k3_forget_knots();
+    const size_t nd = k3_build_table(buf, dims, boxsize, logkk, ratio, nbins, norm);
+    unsigned long long h = 1469598103934665603ull;
+    auto eat = [&](const void *p, size_t n) { for (size_t i = 0; i < n; i++) { h ^= ((const unsigned char *) p)[i]; h *= 1099511628211ull; } };
+    // (the table has no holes except the two bytes of padding per K3SegF and the alignment words, zeroed by calloc)
+    eat(buf, nd * sizeof(double));
+    eat(&g_k3prm.n, sizeof(int)); eat(&g_k3prm.cells, sizeof(int)); eat(&g_k3prm.cell_lo, sizeof(float)); eat(&g_k3prm.cell_scale, sizeof(float));
+    eat(&g_k3prm.off_kthr, sizeof(int)); eat(&g_k3prm.off_segf, sizeof(int)); eat(&g_k3prm.multi, sizeof(int));
+    eat(&g_k3prm.k2_narrow, sizeof(unsigned)); eat(&g_k3prm.cell_off, sizeof(float));
+    const int dec[2] = { g_k3_fm_double, g_k3_f32_ok ? 1 : 0 };
+    eat(dec, sizeof dec);
+    free(buf);
+    *hash = h;
     return KSN_OK;
 }
 

@@ -182,11 +182,28 @@ _delta_pow compute_neutrino_power_internal(const double Time, double *keff, doub
     _delta_pow d_pow;
     get_delta_nu_update(&delta_tot_table, Time, nk_nonzero, keff, delta_cdm, delta_nu, &transfer_init);
     message(0, "Done getting neutrino power: nk= %d, k = %g, delta_nu = %g, delta_cdm = %g,\n", nk_nonzero, keff[1], delta_nu[1], delta_cdm[1]);
-    /* the table interpolates delta_nu/delta_cdm in log k; both conversions are in place */
-    for (int i = 0; i < nk_nonzero; i++) {
-        keff[i] = log(keff[i]);
-        delta_cdm[i] = delta_nu[i] / delta_cdm[i];
+    /* the table interpolates delta_nu/delta_cdm in log k; both conversions are in place.  keff is the mean |k| of the
+     * modes of a bin: the same numbers step after step while the slab geometry stands, so the logarithms of the last call
+     * are kept and reused when the input compares equal (nk libm calls less between K2 and K3 of every step) */
+    {
+        static double *seen = NULL, *logs = NULL;
+        static int cap = 0, n_seen = 0;
+        if (n_seen == nk_nonzero && nk_nonzero > 0 && memcmp(seen, keff, sizeof(double) * nk_nonzero) == 0) {
+            memcpy(keff, logs, sizeof(double) * nk_nonzero);
+        } else {
+            if (cap < nk_nonzero) {
+                free(seen); free(logs);
+                seen = malloc(sizeof(double) * nk_nonzero);
+                logs = malloc(sizeof(double) * nk_nonzero);
+                cap = (seen && logs) ? nk_nonzero : 0;
+            }
+            n_seen = 0;
+            if (cap >= nk_nonzero) memcpy(seen, keff, sizeof(double) * nk_nonzero);
+            for (int i = 0; i < nk_nonzero; i++) keff[i] = log(keff[i]);
+            if (cap >= nk_nonzero) { memcpy(logs, keff, sizeof(double) * nk_nonzero); n_seen = nk_nonzero; }
+        }
     }
+    for (int i = 0; i < nk_nonzero; i++) delta_cdm[i] = delta_nu[i] / delta_cdm[i];
     /* analytic neutrino mass over mass carried by particles (hybrid particles included) */
     const double OmegaNu_nop = get_omega_nu_nopart(&omeganu_table, Time);
     const double omega_hybrid = get_omega_nu(&omeganu_table, Time) - OmegaNu_nop;

@@ -55,3 +55,37 @@ def test_bad_tables_are_rejected(ksn):
     logkk, ratio, norm = _table(64, refs.BOX, nk=10)
     assert ksn.ksn_k3_table_plan(64, refs.BOX, refs.dptr(logkk[::-1].copy()), refs.dptr(ratio), 10, norm, None, None, None, None, None) != 0
     assert ksn.ksn_k3_table_plan(64, refs.BOX, refs.dptr(logkk), refs.dptr(ratio), 1, norm, None, None, None, None, None) != 0
+
+
+def _hash(L, n, box, logkk, ratio, norm, fresh):
+    h = C.c_ulonglong()
+    assert L.ksn_k3_table_hash(n, box, refs.dptr(logkk), refs.dptr(ratio), len(logkk), norm, fresh, C.byref(h)) == 0
+    return h.value
+
+
+def test_table_built_from_cached_knot_geometry_equals_a_fresh_build(ksn):
+    """The knots of the table are log(keff) -- the same every PM step -- so what depends on them alone (k^2 of the knots,
+    reciprocals, integer thresholds, lookup cells) is kept between builds and only the ratio-dependent half is redone.
+    The bytes that go to the device, the kernel parameters and the decisions must not depend on where the knot half came
+    from: fresh, cached, cached after other knots were seen in between, cached with a different ratio / norm."""
+    rng = np.random.default_rng(7)
+    tabs = []
+    for n, nb in ((2048, 788), (4096, 1700), (256, 109), (64, 29)):
+        lk = np.log(np.geomspace(1.0, n * 0.86, nb) * 2 * np.pi / refs.BOX)
+        tabs.append((n, refs.BOX, lk, np.linspace(0.9, 0.1, nb), 0.01))
+        lk2 = np.sort(lk + rng.normal(0, 0.3 * np.diff(lk).min(), nb))
+        tabs.append((n, refs.BOX, lk2, rng.uniform(0.05, 1.0, nb), 0.02))
+        tabs.append((n, refs.BOX / 2, lk2 + 0.3, np.exp(-np.linspace(0, 5, nb)), 0.3))
+    lk = np.log(np.geomspace(1.0, 100, 40) * 2 * np.pi / refs.BOX)
+    lk[20] = lk[19] + 1e-7                                        # two knots in one lookup cell
+    tabs.append((256, refs.BOX, lk, np.linspace(0.5, 0.2, 40), 0.01))
+    fresh = [_hash(ksn, *t, 1) for t in tabs]
+    assert len(set(fresh)) == len(tabs)
+    for t, want in zip(tabs, fresh):                              # cold, then twice from the cache
+        assert [_hash(ksn, *t, f) for f in (1, 0, 0)] == [want] * 3
+    assert [_hash(ksn, *t, 0) for t in tabs] == fresh             # other knots in between: the cache is replaced, not mixed
+    n, box, lk, ratio, norm = tabs[0]
+    for step in range(4):                                         # a run of PM steps: same knots, new ratios and norm
+        r, nm = ratio * (1 + 0.07 * step), norm * (1 + 0.5 * step)
+        assert _hash(ksn, n, box, lk, r, nm, 0) == _hash(ksn, n, box, lk, r, nm, 1)
+    assert ksn.ksn_k3_table_hash(64, refs.BOX, refs.dptr(lk[::-1].copy()), refs.dptr(ratio), 10, norm, 0, C.byref(C.c_ulonglong())) != 0
